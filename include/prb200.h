@@ -1,0 +1,215 @@
+/*
+ * prb200.h — C-ABI of the B200-native PicturedRocks mutual-information hot path.
+ *
+ * Plain pointers and sizes only (no torch types).  Unless a function says
+ * "host", every pointer is a DEVICE pointer owned by the caller; functions
+ * enqueue work on `stream` (a cudaStream_t passed as void*), never allocate,
+ * never synchronise, and return 0 on success (prb_last_error() explains a
+ * non-zero status).  The reference has no FFI of its own: its seam for this
+ * path is the flat-array numba kernels of
+ *   INFOSET = picturedrocks/markers/mutualinformation/infoset.py
+ * and the numpy score algebra of
+ *   ITER    = picturedrocks/markers/mutualinformation/iterative.py
+ *   BASE    = picturedrocks/markers/_iterative.py
+ * Each entry point cites the reference lines it replaces.
+ *
+ * Device data layout
+ *   packed CSC ("by-gene"): indptr int64[P+1]; packed uint32[nnz] with
+ *     bits 0..23 = cell (row) id, bits 24..31 = bin code (1..K-1); rows
+ *     ascending inside a gene (canonical CSC, INFOSET:191-196).
+ *   labels: y int32[N] in 0..C-1.   classsizes int64[C].
+ *   count tables: cnt int32[P][C][K-1] = #cells of class c with code v+1 in
+ *     gene g (C = 1 without labels).  Zero bins are always inferred by
+ *     subtraction (INFOSET:354-359, 390-391, 418-422).
+ *   term table: double[N+1], T[c] = -(c/N)*log2(c/N) built on the HOST with
+ *     glibc log2 (INFOSET:392-397) so entropies are bit-identical to the
+ *     reference; device code only looks terms up and adds them in ascending
+ *     packed-bin order.
+ */
+#ifndef PRB200_H
+#define PRB200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PRB_ABI_VERSION 1
+#define PRB_MAX_ROWS (1 << 24) /* cell id field of the packed CSC word */
+#define PRB_MAX_CODES 256      /* K <= 256 */
+
+typedef void *prb_stream_t;
+
+/* ---- library ------------------------------------------------------------ */
+int prb_abi_version(void);
+const char *prb_last_error(void);
+/* SM count and opt-in shared memory per block of the current device. */
+int prb_device_info(int *sm_count, int *smem_optin_bytes);
+
+/* ---- HOST: fp64 term table  T[c] = -(c/N)*log2(c/N), T[0] = 0 -------------
+ * replaces the per-bin expression of INFOSET:137-141, 392-397, 423-427.
+ * out_host: double[n_rows+1] in host memory. */
+int prb_term_table(int64_t n_rows, double *out_host);
+
+/* ---- packed CSC construction (SparseInformationSet.__init__, INFOSET:188-200;
+ *      canonicalisation stays with the caller) ------------------------------ */
+int prb_pack_csc(const int32_t *rows, const uint8_t *codes, int64_t nnz, uint32_t *packed,
+                 prb_stream_t stream);
+int prb_unpack_csc(const uint32_t *packed, int64_t nnz, int32_t *rows, uint8_t *codes,
+                   prb_stream_t stream);
+/* column-major uint8 codes[P][ld] -> per-gene nnz (pass 1) and packed words (pass 2). */
+int prb_dense_count_nnz(const uint8_t *codes, int64_t N, int64_t P, int64_t ld,
+                        int64_t *nnz_per_gene, prb_stream_t stream);
+int prb_dense_fill_csc(const uint8_t *codes, int64_t N, int64_t P, int64_t ld,
+                       const int64_t *indptr, uint32_t *packed, prb_stream_t stream);
+
+/* ---- work partition of the nnz stream ------------------------------------
+ * range r covers packed[r*range_len, min((r+1)*range_len, nnz)); range_gene[r]
+ * is the gene that owns its first word. */
+int prb_range_genes(const int64_t *indptr, int64_t P, int64_t nnz, int64_t range_len,
+                    int64_t n_ranges, int32_t *range_gene, prb_stream_t stream);
+
+/* ---- the hot loop: per-gene joint histogram of (cell state, code) ----------
+ * replaces the two-pointer merge of _sparse_entropy_wrt (INFOSET:365-391).
+ *   bitmap != NULL : only cells whose bit is set ("master column non-zero") are
+ *                    counted; all others are inferred by subtraction later.
+ *   bitmap == NULL : every stored entry is counted (class-conditional tables).
+ *   state16        : uint16[N], per-cell bin base (state id * (K-1)); NULL = 0.
+ *   hits           : int32[P][n_bins], must be zero on entry; += counts of
+ *                    bin  state16[row] + code - 1.
+ *   work_counter   : int32 in device memory, must be zero on entry.
+ * Returns the dynamic shared memory it needs via prb_stream_smem_bytes(). */
+int prb_stream_smem_bytes(int64_t N, int64_t n_bins, int use_bitmap, int *teams_per_cta,
+                          int64_t *smem_bytes);
+int prb_stream_hits(const uint32_t *packed, const int64_t *indptr, const int32_t *range_gene,
+                    int64_t n_ranges, int64_t range_len, int64_t nnz, const uint32_t *bitmap,
+                    const uint16_t *state16, int64_t N, int64_t n_bins, int32_t *hits,
+                    int32_t *work_counter, prb_stream_t stream);
+
+/* ---- joint-state build ("master column", _sparse_make_master_col INFOSET:431-442) */
+/* dense uint8 x_j[N] (zeroed by caller) <- codes of gene *gene_ptr (device int32;
+ * genes outside [gene_lo, gene_lo+P) are ignored: multi-GPU owner test). */
+int prb_scatter_gene_u8(const uint32_t *packed, const int64_t *indptr, const int32_t *gene_ptr,
+                        int32_t gene_lo, int64_t P, uint8_t *xj, prb_stream_t stream);
+/* mpacked[row] |= code << shift_bits for every stored entry of gene `gene`. */
+int prb_scatter_gene_or32(const uint32_t *packed, const int64_t *indptr, int64_t gene,
+                          int shift_bits, uint32_t *mpacked, prb_stream_t stream);
+/* direct single-column state: state id = y*(K-1) + x_j - 1 (y = 0 without labels).
+ * Writes bitmap uint32[ceil(N/32)], state16[N] (= id*(K-1)), hsize int32[C*(K-1)]
+ * (zeroed here), hs_begin int32[C+1], hs_y int32[C*(K-1)], hs_ysum int32[C],
+ * ha int32[K-1]; also resets *work_counter to 0. */
+int prb_state_direct(const uint8_t *xj, const int32_t *y, int64_t N, int C, int K,
+                     uint32_t *bitmap, uint16_t *state16, int32_t *hsize, int32_t *hs_begin,
+                     int32_t *hs_y, int32_t *hs_ysum, int32_t *ha, int32_t *work_counter,
+                     prb_stream_t stream);
+/* generic multi-column state through an order-preserving presence-table
+ * compaction (the "sort/unique relabel"): key = y << mbits | mpacked.
+ * table int32[C << mbits] scratch.  n_hs_out: device int32. */
+int prb_state_table(const uint32_t *mpacked, const int32_t *y, int64_t N, int C, int K,
+                    int mbits, int32_t *table, uint32_t *bitmap, uint16_t *state16,
+                    int32_t *hsize, int32_t *hs_begin, int32_t *hs_y, int32_t *hs_ysum,
+                    int32_t *n_hs_out, int32_t *work_counter, int64_t hsize_cap,
+                    prb_stream_t stream);
+
+/* ---- entropies from histograms (INFOSET:392-397), ordered fp64 sum ----------
+ * out_full[g]  = H(y, master, x_g)   (bins ascending (y, master, code))
+ * out_marg[g]  = H(master, x_g)      (only for the direct layout; may be NULL)
+ * hits may be NULL (no master column: gives H(y,x_g) and H(x_g)).
+ * hits entries are reset to zero as they are consumed. */
+int prb_finalize(int32_t *hits, const int32_t *cnt, const int64_t *classsizes,
+                 const int32_t *hs_begin, const int32_t *hs_y, const int32_t *hsize,
+                 const int32_t *hs_ysum, const int32_t *ha, const int32_t *n_hs_ptr,
+                 int64_t n_hs_cap, int C, int K, const double *table, int64_t N, int64_t P,
+                 double *out_full, double *out_marg, prb_stream_t stream);
+/* scalar entropy of a per-cell key vector through a count table (INFOSET:218-249,
+ * 413-428): table int32[n_keys] scratch; out: device double. */
+int prb_entropy_keys(const uint32_t *mpacked, const int32_t *y, int64_t N, int mbits,
+                     int64_t n_keys, int32_t *table, const double *term_table, double *out,
+                     prb_stream_t stream);
+
+/* ---- selector algebra + argmax on device (ITER:24-134, BASE:53-66) --------- */
+enum {
+    PRB_SEL_CIFE = 0,
+    PRB_SEL_JMI = 1,
+    PRB_SEL_CIFE_UNSUP = 2
+};
+/* base = (Hx + Hy) - Hyx  (ITER:29-33) */
+int prb_mi_base(const double *Hx, double Hy, const double *Hyx, int64_t P, double *base,
+                prb_stream_t stream);
+/* one add()/remove() update (ITER:48-72, 76-100, 112-134).
+ *   delta = (((base + Hj) - Hij) - Hyj) + Hyij   (supervised)
+ *   delta = (base + Hj) - Hij                     (CIFEUnsup)
+ * Hj/Hyj are looked up at *gene_ptr in the replicated vectors Hx_all/Hyx_all.
+ * n_sel_ptr: device int32 = len(S) AFTER the add/remove.
+ * selected: uint8[P] mask of S (local genes).  Also produces per-block argmax
+ * candidates (cand_score/cand_idx, one per block of 256 genes; idx is global =
+ * gene_lo + local). */
+int prb_selector_update(int kind, int is_remove, const double *base, double *penalty,
+                        double *score, const uint8_t *selected, const double *Hij,
+                        const double *Hyij, const double *Hx_all, const double *Hyx_all,
+                        const int32_t *gene_ptr, const int32_t *n_sel_ptr, int64_t P,
+                        int32_t gene_lo, double *cand_score, int64_t *cand_idx,
+                        prb_stream_t stream);
+/* per-block argmax candidates of a score vector (first maximum wins; NaN counts
+ * as maximal, like np.argmax). */
+int prb_argmax_blocks(const double *score, int64_t P, int32_t gene_lo, double *cand_score,
+                      int64_t *cand_idx, prb_stream_t stream);
+/* reduce n_cand candidates to one (score,idx); ties -> lowest idx. */
+int prb_argmax_final(const double *cand_score, const int64_t *cand_idx, int64_t n_cand,
+                     double *best_score, int64_t *best_idx, prb_stream_t stream);
+/* commit a winner: gene_ptr <- idx, S[n_sel++] <- idx, selected[idx-gene_lo] <- 1,
+ * score[idx-gene_lo] untouched (the update masks it).  idx is read from best_idx. */
+int prb_commit_add(const int64_t *best_idx, int32_t *gene_ptr, int32_t *S, int32_t *n_sel_ptr,
+                   uint8_t *selected, int32_t gene_lo, int64_t P, prb_stream_t stream);
+
+/* ---- discretiser (quantile_discretize, INFOSET:50-83) ---------------------
+ * dtype: 0 = float32, 1 = float64, 2 = int64 (edges float64 for int64 input).
+ * Pipeline: row-major X[N][P] --transpose--> Xt[P][N] --sort_columns--> Xs[P][N]
+ *           --qd_edges--> edges[P][k-1], n_edges[P] --qd_digitize(Xt)--> codes.
+ * Edges follow numpy-2.x percentile(method="linear") arithmetic in the input
+ * dtype (float32 stays float32); codes = #edges strictly below x
+ * (np.digitize(right=True)). */
+/* row-major [N][P] -> column-major [P][N] transpose of 4- or 8-byte elements. */
+int prb_transpose(const void *X, int elem_bytes, int64_t N, int64_t P, void *out,
+                  prb_stream_t stream);
+/* ascending sort of every gene segment of a column-major [P][N] array (N*P < 2^31);
+ * workspace is caller-provided device scratch of prb_sort_columns_workspace() bytes. */
+int prb_sort_columns_workspace(int dtype, int64_t N, int64_t P, int64_t *bytes);
+int prb_sort_columns(const void *cols_in, void *cols_out, int dtype, int64_t N, int64_t P,
+                     void *workspace, int64_t workspace_bytes, prb_stream_t stream);
+int prb_qd_edges(const void *sorted, int dtype, int64_t N, int64_t P, int k, void *edges,
+                 int32_t *n_edges, prb_stream_t stream);
+/* Xt column-major [P][N] (unsorted); codes column-major uint8 [P][ld]. */
+int prb_qd_digitize(const void *Xt, int dtype, int64_t N, int64_t P, int k, const void *edges,
+                    const int32_t *n_edges, uint8_t *codes, int64_t ld, prb_stream_t stream);
+
+/* ---- synthetic discretised matrices (bench/test utility; counter-based RNG,
+ *      reproduced on the CPU by picturedrocks_b200/synth.py) -----------------
+ * cum: uint32[4][K-2] cumulative 16-bit thresholds of the code distribution. */
+int prb_synth_labels(int32_t *y, int64_t N, int C, uint64_t seed, prb_stream_t stream);
+int prb_synth_count(const int32_t *y, int64_t N, int64_t gene_lo, int64_t P, int C, int K,
+                    uint32_t mean_density_q24, uint64_t seed, const uint32_t *cum,
+                    int64_t *nnz_per_gene, prb_stream_t stream);
+int prb_synth_fill(const int32_t *y, int64_t N, int64_t gene_lo, int64_t P, int C, int K,
+                   uint32_t mean_density_q24, uint64_t seed, const uint32_t *cum,
+                   const int64_t *indptr, uint32_t *packed, prb_stream_t stream);
+
+/* ---- HOST-buffer drop-in for the reference's njit seam ---------------------
+ * Same arguments and meaning as
+ *   _sparse_entropy_wrt(dindices, dindptr, ddata, mindices, mdata, n_rows,
+ *                       n_feats, n_mcols, shift, ybits, y, classsizes)
+ * (INFOSET:306-349).  All pointers are HOST pointers; the call copies inputs to
+ * the current device, runs the kernels above and copies float64[n_feats] back.
+ * Allocates and synchronises internally (it is the synchronous reference
+ * signature).  m_nnz = len(mindices); n_classes = len(classsizes) (0 if no y). */
+int prb_sparse_entropy_wrt_host(const int32_t *dindices, const int64_t *dindptr,
+                                const int64_t *ddata, const int64_t *mindices,
+                                const int64_t *mdata, int64_t m_nnz, int64_t n_rows,
+                                int64_t n_feats, int64_t n_mcols, int64_t shift, int64_t ybits,
+                                const int64_t *y, const double *classsizes, int64_t n_classes,
+                                double *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PRB200_H */

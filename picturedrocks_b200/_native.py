@@ -1,0 +1,125 @@
+"""ctypes binding of libprb200.so (include/prb200.h).
+
+There is deliberately NO fallback: if the shared library is missing and cannot
+be built, importing the compute path raises.  PyTorch only provides device
+memory and streams; every kernel runs from libprb200.so.
+"""
+import ctypes
+import os
+
+from . import build as _build
+
+_LIB = None
+
+_vp = ctypes.c_void_p
+_i64 = ctypes.c_int64
+_i32 = ctypes.c_int32
+_int = ctypes.c_int
+_u32 = ctypes.c_uint32
+_u64 = ctypes.c_uint64
+_f64 = ctypes.c_double
+
+# name -> argtypes (all return int unless listed in _RESTYPES)
+_SIGS = {
+    "prb_abi_version": [],
+    "prb_last_error": [],
+    "prb_device_info": [ctypes.POINTER(_int), ctypes.POINTER(_int)],
+    "prb_term_table": [_i64, _vp],
+    "prb_pack_csc": [_vp, _vp, _i64, _vp, _vp],
+    "prb_unpack_csc": [_vp, _i64, _vp, _vp, _vp],
+    "prb_dense_count_nnz": [_vp, _i64, _i64, _i64, _vp, _vp],
+    "prb_dense_fill_csc": [_vp, _i64, _i64, _i64, _vp, _vp, _vp],
+    "prb_range_genes": [_vp, _i64, _i64, _i64, _i64, _vp, _vp],
+    "prb_stream_smem_bytes": [_i64, _i64, _int, ctypes.POINTER(_int), ctypes.POINTER(_i64)],
+    "prb_stream_hits": [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _i64, _i64, _vp, _vp, _vp],
+    "prb_scatter_gene_u8": [_vp, _vp, _vp, _i32, _i64, _vp, _vp],
+    "prb_scatter_gene_or32": [_vp, _vp, _i64, _int, _vp, _vp],
+    "prb_state_direct": [_vp, _vp, _i64, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "prb_state_table": [_vp, _vp, _i64, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                        _vp, _i64, _vp],
+    "prb_finalize": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _vp, _i64, _i64,
+                     _vp, _vp, _vp],
+    "prb_entropy_keys": [_vp, _vp, _i64, _int, _i64, _vp, _vp, _vp, _vp],
+    "prb_mi_base": [_vp, _f64, _vp, _i64, _vp, _vp],
+    "prb_selector_update": [_int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64,
+                            _i32, _vp, _vp, _vp],
+    "prb_argmax_blocks": [_vp, _i64, _i32, _vp, _vp, _vp],
+    "prb_argmax_final": [_vp, _vp, _i64, _vp, _vp, _vp],
+    "prb_commit_add": [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp],
+    "prb_transpose": [_vp, _int, _i64, _i64, _vp, _vp],
+    "prb_sort_columns_workspace": [_int, _i64, _i64, ctypes.POINTER(_i64)],
+    "prb_sort_columns": [_vp, _vp, _int, _i64, _i64, _vp, _i64, _vp],
+    "prb_qd_edges": [_vp, _int, _i64, _i64, _int, _vp, _vp, _vp],
+    "prb_qd_digitize": [_vp, _int, _i64, _i64, _int, _vp, _vp, _vp, _i64, _vp],
+    "prb_synth_labels": [_vp, _i64, _int, _u64, _vp],
+    "prb_synth_count": [_vp, _i64, _i64, _i64, _int, _int, _u32, _u64, _vp, _vp, _vp],
+    "prb_synth_fill": [_vp, _i64, _i64, _i64, _int, _int, _u32, _u64, _vp, _vp, _vp, _vp],
+    "prb_sparse_entropy_wrt_host": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64,
+                                    _vp, _vp, _i64, _vp],
+}
+_RESTYPES = {"prb_last_error": ctypes.c_char_p}
+
+EXPORTED = tuple(_SIGS)
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load():
+    """Load libprb200.so, building it in-tree with nvcc if it is absent/stale."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    try:
+        path = _build.build()
+    except Exception as e:  # no nvcc and no prebuilt library: fail loudly
+        if os.path.exists(_build.LIB):
+            path = _build.LIB
+        else:
+            raise ImportError(
+                "picturedrocks_b200 needs its CUDA library libprb200.so (no CPU fallback exists): "
+                + str(e))
+    lib = ctypes.CDLL(path)
+    for name, args in _SIGS.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = _RESTYPES.get(name, _int)
+    if lib.prb_abi_version() != 1:
+        raise ImportError("libprb200.so ABI version mismatch")
+    _LIB = lib
+    return lib
+
+
+class PrbError(RuntimeError):
+    pass
+
+
+def call(name, *args):
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise PrbError("%s failed: %s" % (name, lib.prb_last_error().decode()))
+
+
+def ptr(t):
+    """Device (or host) pointer of a torch tensor / numpy array; None -> NULL."""
+    if t is None:
+        return None
+    if hasattr(t, "data_ptr"):
+        return t.data_ptr()
+    return t.ctypes.data
+
+
+def stream():
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            "picturedrocks_b200 runs on a CUDA device (B200, sm_100a) only; there is no CPU path")

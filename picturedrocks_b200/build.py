@@ -1,0 +1,47 @@
+"""Build libprb200.so (hand-written sm_100a CUDA + C-ABI) in-tree with nvcc."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+SOURCES = ["stream.cu", "state.cu", "finalize.cu", "selector.cu", "discretize.cu", "synth.cu",
+           "host.cu"]
+LIB = os.path.join(HERE, "libprb200.so")
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + [
+        os.path.join(CSRC, "common.cuh"),
+        os.path.join(HERE, "..", "include", "prb200.h"),
+    ]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [
+        nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+        "-shared", "-Xcompiler", "-fPIC,-ffp-contract=off", "--fmad=true",
+        "-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++",
+        "-o", LIB,
+    ] + [os.path.join(CSRC, s) for s in SOURCES]
+    if verbose:
+        cmd.insert(1, "-Xptxas")
+        cmd.insert(2, "-v")
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed building libprb200.so")
+    if verbose:
+        sys.stderr.write(r.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose="-v" in sys.argv))

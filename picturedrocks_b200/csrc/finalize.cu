@@ -1,0 +1,179 @@
+// finalize.cu — histograms -> entropies, bit-compatible with the reference.
+//
+// Replaces the tail of entropy_wrt_i in _sparse_entropy_wrt
+// (picturedrocks/markers/mutualinformation/infoset.py:392-397):
+//     counts = counts / n_rows ; for e in counts: if e > 0: h += -e * np.log2(e)
+// The per-bin term -(c/N)*log2(c/N) comes from a HOST-built fp64 table (glibc
+// log2, the same libm call numba emits), and terms are added one at a time in
+// ascending packed-bin order (y, master, code) with __dadd_rn, so the fp64 sum
+// is the same sequence of roundings as the reference's loop.
+//
+// One warp per gene.  Bins that the streaming pass did not count are inferred
+// by subtraction (the reference's "pre-count zeros through classsizes" trick,
+// infoset.py:354-359, 390-391, taken one step further):
+//   hit bins      (y, m>0, v>0)  = hits
+//   (y, m>0, 0)   = hsize[state] - Σ_v hits
+//   (y, 0,   v>0) = cnt[g][y][v] - Σ_{states of y} hits[.][v]
+//   (y, 0,   0)   = classsize[y] - Σ hsize(states of y) - Σ_v (y,0,v)
+#include "common.cuh"
+
+namespace prb {
+
+__device__ __forceinline__ double ordered_add(double h, int c, const double *__restrict__ term)
+{
+    const double tv = c > 0 ? __ldg(term + c) : 0.0;
+    unsigned nz = __ballot_sync(0xffffffffu, c > 0);
+    while (nz) {
+        const int l = __ffs(nz) - 1;
+        nz &= nz - 1;
+        h = __dadd_rn(h, __shfl_sync(0xffffffffu, tv, l));
+    }
+    return h;
+}
+
+__global__ void __launch_bounds__(256)
+k_finalize(int32_t *__restrict__ hits, int64_t hits_stride, const int32_t *__restrict__ cnt,
+           const int64_t *__restrict__ clsz, const int32_t *__restrict__ hs_begin,
+           const int32_t *__restrict__ hs_y, const int32_t *__restrict__ hsize,
+           const int32_t *__restrict__ hs_ysum, const int32_t *__restrict__ ha,
+           const int32_t *__restrict__ n_hs_ptr, int n_hs_cap, int C, int K,
+           const double *__restrict__ term, int64_t N, int64_t P, double *__restrict__ out_full,
+           double *__restrict__ out_marg, int scratch_ints)
+{
+    extern __shared__ int sh[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wpb = blockDim.x >> 5;
+    const int K1 = K - 1;
+    const bool marg = out_marg != nullptr;
+    int n_hs = 0;
+    if (hits) n_hs = n_hs_ptr ? min(*n_hs_ptr, n_hs_cap) : n_hs_cap;
+
+    int *rs = sh + (int64_t)warp * scratch_ints;  // [n_hs_cap]
+    int *csy = rs + n_hs_cap;                      // [C*K1]
+    int *z0 = csy + C * K1;                        // [C]
+    int *m2 = z0 + C;                              // [K1*K1]  (marg only)
+    int *xc = m2 + (marg ? K1 * K1 : 0);           // [K1]     (marg only)
+
+    for (int64_t g = (int64_t)blockIdx.x * wpb + warp; g < P; g += (int64_t)gridDim.x * wpb) {
+        for (int i = lane; i < scratch_ints; i += 32) rs[i] = 0;
+        __syncwarp();
+        int32_t *hrow = hits ? hits + g * hits_stride : nullptr;
+        const int32_t *crow = cnt + g * (int64_t)C * K1;
+        // phase A: row / column sums of the hit histogram
+        for (int t = lane; t < n_hs * K1; t += 32) {
+            const int x = hrow[t];
+            if (x) {
+                const int h = t / K1, v = t - h * K1;
+                atomicAdd(rs + h, x);
+                atomicAdd(csy + hs_y[h] * K1 + v, x);
+                if (marg) atomicAdd(m2 + (h % K1) * K1 + v, x);
+            }
+        }
+        __syncwarp();
+        // phase A2: per-class totals of the master==0 group
+        for (int t = lane; t < C * K1; t += 32) {
+            const int c0 = crow[t];
+            const int yy = t / K1;
+            if (c0 - csy[t]) atomicAdd(z0 + yy, c0 - csy[t]);
+            if (marg && c0) atomicAdd(xc + (t - yy * K1), c0);
+        }
+        __syncwarp();
+        // phase B: ordered sum over (y, master, code)
+        double h_acc = 0.0;
+        for (int yy = 0; yy < C; ++yy) {
+            const int hb = n_hs ? hs_begin[yy] : 0;
+            const int he = n_hs ? min(hs_begin[yy + 1], n_hs) : 0;
+            const int nb = (1 + max(he - hb, 0)) * K;
+            for (int t0 = 0; t0 < nb; t0 += 32) {
+                const int t = t0 + lane;
+                int c = 0;
+                if (t < nb) {
+                    const int slot = t / K, v = t - slot * K;
+                    if (slot == 0) {
+                        if (v == 0)
+                            c = (int)(clsz[yy] - (n_hs ? hs_ysum[yy] : 0) - z0[yy]);
+                        else
+                            c = crow[yy * K1 + v - 1] - csy[yy * K1 + v - 1];
+                    } else {
+                        const int h = hb + slot - 1;
+                        if (v == 0) {
+                            c = hsize[h] - rs[h];
+                        } else {
+                            c = hrow[h * K1 + v - 1];
+                            if (c) hrow[h * K1 + v - 1] = 0;  // leave the buffer clean
+                        }
+                    }
+                }
+                h_acc = ordered_add(h_acc, c, term);
+            }
+        }
+        if (lane == 0) out_full[g] = h_acc;
+        if (marg) {
+            // direct layout: master value a = (state % K1) + 1; sum over y.
+            int sum_ha = 0, sum_xc = 0, sum_m2 = 0;
+            for (int a = 0; a < K1; ++a) {
+                sum_ha += (n_hs && ha) ? ha[a] : 0;
+                sum_xc += xc[a];
+            }
+            for (int i = 0; i < K1 * K1; ++i) sum_m2 += m2[i];
+            double h2 = 0.0;
+            for (int t0 = 0; t0 < K * K; t0 += 32) {
+                const int t = t0 + lane;
+                int c = 0;
+                if (t < K * K) {
+                    const int a = t / K, v = t - a * K;
+                    if (a == 0) {
+                        if (v == 0) {
+                            c = (int)(N - sum_ha - (sum_xc - sum_m2));
+                        } else {
+                            int s = 0;
+                            for (int aa = 0; aa < K1; ++aa) s += m2[aa * K1 + v - 1];
+                            c = xc[v - 1] - s;
+                        }
+                    } else if (v == 0) {
+                        int s = 0;
+                        for (int vv = 0; vv < K1; ++vv) s += m2[(a - 1) * K1 + vv];
+                        c = ((n_hs && ha) ? ha[a - 1] : 0) - s;
+                    } else {
+                        c = m2[(a - 1) * K1 + v - 1];
+                    }
+                }
+                h2 = ordered_add(h2, c, term);
+            }
+            if (lane == 0) out_marg[g] = h2;
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace prb
+
+using namespace prb;
+
+extern "C" int prb_finalize(int32_t *hits, const int32_t *cnt, const int64_t *classsizes,
+                            const int32_t *hs_begin, const int32_t *hs_y, const int32_t *hsize,
+                            const int32_t *hs_ysum, const int32_t *ha, const int32_t *n_hs_ptr,
+                            int64_t n_hs_cap, int C, int K, const double *table, int64_t N,
+                            int64_t P, double *out_full, double *out_marg, prb_stream_t stream)
+{
+    if (P == 0) return 0;
+    PRB_REQUIRE(C >= 1 && K >= 2 && K <= PRB_MAX_CODES, "bad C or K");
+    PRB_REQUIRE(out_full != nullptr, "out_full is required");
+    if (!hits) n_hs_cap = 0;
+    const int K1 = K - 1;
+    const int64_t scratch = n_hs_cap + (int64_t)C * K1 + C + (out_marg ? (int64_t)K1 * K1 + K1 : 0);
+    const int64_t smem_max = devinfo().smem_optin - 1024;
+    PRB_REQUIRE(scratch * 4 <= smem_max, "finalize scratch does not fit in shared memory");
+    int wpb = 8;
+    while (wpb > 1 && scratch * 4 * wpb > smem_max) wpb >>= 1;
+    // keep a few blocks per SM resident when scratch is small
+    const int64_t smem = scratch * 4 * wpb;
+    PRB_CUDA(cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem_max));
+    const int grid = (int)hmin(ceil_div(P, wpb), (int64_t)devinfo().sm_count * 8);
+    k_finalize<<<grid, wpb * 32, smem, S(stream)>>>(
+        hits, n_hs_cap * K1, cnt, classsizes, hs_begin, hs_y, hsize, hs_ysum, ha, n_hs_ptr,
+        (int)n_hs_cap, C, K, table, N, P, out_full, out_marg, (int)scratch);
+    PRB_LAUNCH_CHECK("k_finalize");
+    return 0;
+}

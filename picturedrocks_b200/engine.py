@@ -1,0 +1,315 @@
+"""Device-resident information set: packed by-gene CSC + count tables in HBM.
+
+Host-side orchestration of the kernels in csrc/ through the C-ABI
+(include/prb200.h).  PyTorch tensors own the device memory and provide the
+stream; every computation on the path is a libprb200.so kernel.
+
+Reference being replaced (picturedrocks/markers/mutualinformation/infoset.py):
+  SparseInformationSet.__init__/set_y :188-216, entropy :218-249,
+  entropy_wrt :251-303, _sparse_entropy_wrt :306-410, _sparse_entropy :413-428,
+  _sparse_make_master_col :431-442.
+
+Multi-GPU: an Engine may hold only the genes [gene_lo, gene_lo + P) of a
+P_total-gene matrix (one process per GPU).  Per-cell state is replicated; the
+only exchanges are a max-all-reduce of the selected gene's dense code vector
+and the (score, index) all-gather of the argmax — see dist.py.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _native as nat
+
+_I16_MAX_BINS = 65536
+
+
+def _i32(x):
+    return ctypes.c_int32(int(x))
+
+
+class Engine:
+    def __init__(self, indptr, packed, N, K, gene_lo=0, P_total=None, comm=None):
+        """indptr: int64[P+1] device tensor (local offsets, indptr[0] == 0);
+        packed: int32 device tensor holding the uint32 words code<<24 | row."""
+        nat.require_cuda()
+        nat.load()
+        assert indptr.dtype == torch.int64 and indptr.is_cuda and indptr.is_contiguous()
+        assert packed.dtype == torch.int32 and packed.is_cuda and packed.is_contiguous()
+        self.device = indptr.device
+        self.indptr = indptr
+        self.packed = packed
+        self.N = int(N)
+        self.P = indptr.numel() - 1
+        self.gene_lo = int(gene_lo)
+        self.P_total = int(P_total) if P_total is not None else self.P
+        self.comm = comm
+        if self.N <= 0 or self.N > (1 << 24):
+            raise ValueError("number of cells must be in (0, 2^24] (packed row field)")
+        self.K = int(K)
+        if comm is not None:
+            self.K = comm.max_int(self.K)
+        if not (2 <= self.K <= 256):
+            raise ValueError("bin codes must lie in [0, 255] with at least one non-zero code")
+        self.K1 = self.K - 1
+        self.shift = (self.K - 1).bit_length()  # infoset.py:199  int(log2(max)+1)
+        self.nnz = int(indptr[-1].item())
+        sm = ctypes.c_int()
+        smem = ctypes.c_int()
+        nat.call("prb_device_info", ctypes.byref(sm), ctypes.byref(smem))
+        self.sm_count, self.smem_optin = sm.value, smem.value
+        # work partition of the nnz stream
+        target = self.nnz // (self.sm_count * 32 * 4)
+        self.range_len = int(min(32768, max(512, -(-target // 512) * 512)))
+        self.n_ranges = -(-self.nnz // self.range_len)
+        self.range_gene = torch.zeros(max(self.n_ranges, 1), dtype=torch.int32, device=self.device)
+        nat.call("prb_range_genes", nat.ptr(indptr), self.P, self.nnz, self.range_len,
+                 self.n_ranges, nat.ptr(self.range_gene), nat.stream())
+        # fp64 term table, built on the host (glibc log2), resident in HBM
+        tt = np.empty(self.N + 1, dtype=np.float64)
+        nat.call("prb_term_table", self.N, tt.ctypes.data)
+        self.term = torch.from_numpy(tt).to(self.device)
+        # per-cell state workspaces
+        dev = self.device
+        bm_words = ((self.N + 31) // 32 + 3) // 4 * 4
+        self.bitmap = torch.zeros(bm_words, dtype=torch.int32, device=dev)
+        self.state16 = torch.zeros(self.N, dtype=torch.int16, device=dev)
+        self.xj = torch.zeros(self.N, dtype=torch.uint8, device=dev)
+        self.mpacked = None
+        self.hsize = torch.zeros(_I16_MAX_BINS, dtype=torch.int32, device=dev)
+        self.hs_y = torch.zeros(_I16_MAX_BINS, dtype=torch.int32, device=dev)
+        self.hs_begin = torch.zeros(258, dtype=torch.int32, device=dev)
+        self.hs_ysum = torch.zeros(257, dtype=torch.int32, device=dev)
+        self.ha = torch.zeros(256, dtype=torch.int32, device=dev)
+        self.n_hs_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.work_counter = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.gene_ptr = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._hits = None
+        self._table = None
+        self.clsz_all = torch.tensor([self.N], dtype=torch.int64, device=dev)
+        # labels
+        self.has_y = False
+        self.y = None
+        self.C = 1
+        self.classsizes = None
+        self.cnt_y = None
+        self.cnt_x = self._count_table(None, 1)
+
+    # ------------------------------------------------------------------ tables
+    def _count_table(self, y, C):
+        """cnt[g][c][v-1] = #cells of class c with code v in gene g (one streaming pass)."""
+        if C * self.K1 > _I16_MAX_BINS:
+            raise NotImplementedError("classes x codes exceeds the uint16 state range")
+        cnt = torch.zeros(max(self.P * C * self.K1, 1), dtype=torch.int32, device=self.device)
+        state = None
+        if y is not None:
+            state = (y * self.K1).to(torch.int16)  # bit pattern of uint16
+        self.work_counter.zero_()
+        nat.call("prb_stream_hits", nat.ptr(self.packed), nat.ptr(self.indptr),
+                 nat.ptr(self.range_gene), self.n_ranges, self.range_len, self.nnz, None,
+                 nat.ptr(state), self.N, C * self.K1, nat.ptr(cnt), nat.ptr(self.work_counter),
+                 nat.stream())
+        return cnt
+
+    def set_y(self, y):
+        """y: int32 device tensor [N] of labels in 0..C-1, or None (infoset.py:202-216)."""
+        if y is None:
+            self.has_y, self.y, self.C, self.classsizes, self.cnt_y = False, None, 1, None, None
+            return
+        assert y.dtype == torch.int32 and y.is_cuda and y.numel() == self.N
+        C = int(y.max().item()) + 1
+        if C > 256:
+            raise NotImplementedError("more than 256 classes")
+        self.has_y, self.y, self.C = True, y.contiguous(), C
+        self.classsizes = torch.bincount(y, minlength=C).to(torch.int64)
+        self.cnt_y = self._count_table(self.y, C)
+
+    # --------------------------------------------------------------- primitives
+    def hits_buffer(self, n_bins):
+        need = max(self.P * n_bins, 1)
+        if self._hits is None or self._hits.numel() < need:
+            self._hits = None
+            self._hits = torch.zeros(need, dtype=torch.int32, device=self.device)
+        return self._hits
+
+    def _stream(self, n_bins, hits):
+        nat.call("prb_stream_hits", nat.ptr(self.packed), nat.ptr(self.indptr),
+                 nat.ptr(self.range_gene), self.n_ranges, self.range_len, self.nnz,
+                 nat.ptr(self.bitmap), nat.ptr(self.state16), self.N, n_bins, nat.ptr(hits),
+                 nat.ptr(self.work_counter), nat.stream())
+
+    def _finalize(self, hits, cnt, clsz, C, n_hs_cap, n_hs_ptr, out_full, out_marg, direct):
+        nat.call("prb_finalize", nat.ptr(hits), nat.ptr(cnt), nat.ptr(clsz), nat.ptr(self.hs_begin),
+                 nat.ptr(self.hs_y), nat.ptr(self.hsize), nat.ptr(self.hs_ysum),
+                 nat.ptr(self.ha) if direct else None, nat.ptr(n_hs_ptr), n_hs_cap, C, self.K,
+                 nat.ptr(self.term), self.N, self.P, nat.ptr(out_full), nat.ptr(out_marg),
+                 nat.stream())
+
+    def _labels(self, with_y):
+        if with_y:
+            if not self.has_y:
+                raise AssertionError("information set has no y")
+            return self.C, self.y, self.cnt_y, self.classsizes
+        return 1, None, self.cnt_x, self.clsz_all
+
+    def scatter_selected_gene(self):
+        """x_j[N] <- dense codes of gene *gene_ptr (owner rank), replicated to all ranks."""
+        self.xj.zero_()
+        nat.call("prb_scatter_gene_u8", nat.ptr(self.packed), nat.ptr(self.indptr),
+                 nat.ptr(self.gene_ptr), _i32(self.gene_lo), self.P, nat.ptr(self.xj),
+                 nat.stream())
+        if self.comm is not None:
+            self.comm.allreduce_max_(self.xj)
+
+    def direct_step(self, with_y, out_full, out_marg):
+        """One fused pass for the gene in gene_ptr:
+        out_full = H([y,] x_j, x_i); out_marg = H(x_j, x_i) (only with_y)."""
+        C, y, cnt, clsz = self._labels(with_y)
+        n_hs = C * self.K1
+        n_bins = n_hs * self.K1
+        if n_bins > _I16_MAX_BINS:
+            raise NotImplementedError("C*(K-1)^2 exceeds the uint16 state range")
+        self.scatter_selected_gene()
+        nat.call("prb_state_direct", nat.ptr(self.xj), nat.ptr(y), self.N, C, self.K,
+                 nat.ptr(self.bitmap), nat.ptr(self.state16), nat.ptr(self.hsize),
+                 nat.ptr(self.hs_begin), nat.ptr(self.hs_y), nat.ptr(self.hs_ysum),
+                 nat.ptr(self.ha), nat.ptr(self.work_counter), nat.stream())
+        hits = self.hits_buffer(n_bins)
+        self._stream(n_bins, hits)
+        self._finalize(hits, cnt, clsz, C, n_hs, None, out_full, out_marg, True)
+
+    def _build_mpacked(self, cols):
+        """Joint-state packing of several columns (infoset.py:431-442): first column is
+        the most significant digit; each digit is `shift` bits wide."""
+        m = len(cols)
+        mbits = self.shift * m
+        if mbits > 30:
+            raise NotImplementedError("joint state of %d columns needs more than 30 bits" % m)
+        if self.mpacked is None:
+            self.mpacked = torch.zeros(self.N, dtype=torch.int32, device=self.device)
+        self.mpacked.zero_()
+        for pos, c in enumerate(cols):
+            local = c - self.gene_lo
+            if 0 <= local < self.P:
+                nat.call("prb_scatter_gene_or32", nat.ptr(self.packed), nat.ptr(self.indptr),
+                         local, self.shift * (m - 1 - pos), nat.ptr(self.mpacked), nat.stream())
+        if self.comm is not None:
+            self.comm.allreduce_sum_(self.mpacked)  # disjoint bit fields: sum == or
+        return mbits
+
+    def _table_scratch(self, n_keys):
+        if n_keys > (1 << 24):
+            raise NotImplementedError("joint state space larger than 2^24 keys")
+        if self._table is None or self._table.numel() < n_keys:
+            self._table = torch.zeros(n_keys, dtype=torch.int32, device=self.device)
+        return self._table
+
+    def _norm_cols(self, cols):
+        cols = [int(c) for c in np.asarray(cols, dtype=np.int64).ravel()]
+        with_y = len(cols) > 0 and cols[0] == -1  # infoset.py:278
+        if with_y:
+            cols = cols[1:]
+        out = []
+        for c in cols:
+            if c < 0:
+                c += self.P_total  # scipy/numpy negative column index
+            if not (0 <= c < self.P_total):
+                raise IndexError("column index out of range")
+            out.append(c)
+        return with_y, out
+
+    # -------------------------------------------------------------- public API
+    def entropy_wrt_device(self, cols):
+        """float64 device vector [P]: H(cols, x_i) for every local gene i."""
+        with_y, cols = self._norm_cols(cols)
+        C, y, cnt, clsz = self._labels(with_y)
+        out = torch.empty(self.P, dtype=torch.float64, device=self.device)
+        m = len(cols)
+        if m == 0:
+            self._finalize(None, cnt, clsz, C, 0, None, out, None, False)
+        elif m == 1:
+            self.gene_ptr.fill_(cols[0])
+            self.direct_step(with_y, out, None)
+        else:
+            mbits = self._build_mpacked(cols)
+            n_keys = C << mbits
+            table = self._table_scratch(n_keys)
+            nat.call("prb_state_table", nat.ptr(self.mpacked), nat.ptr(y), self.N, C, self.K,
+                     mbits, nat.ptr(table), nat.ptr(self.bitmap), nat.ptr(self.state16),
+                     nat.ptr(self.hsize), nat.ptr(self.hs_begin), nat.ptr(self.hs_y),
+                     nat.ptr(self.hs_ysum), nat.ptr(self.n_hs_dev), nat.ptr(self.work_counter),
+                     self.hsize.numel(), nat.stream())
+            n_hs = int(self.n_hs_dev.item())
+            if n_hs * self.K1 > _I16_MAX_BINS:
+                raise NotImplementedError(
+                    "%d joint states x %d codes exceeds the uint16 state range" % (n_hs, self.K1))
+            if n_hs == 0:
+                self._finalize(None, cnt, clsz, C, 0, None, out, None, False)
+            else:
+                n_bins = n_hs * self.K1
+                hits = self.hits_buffer(n_bins)
+                self._stream(n_bins, hits)
+                self._finalize(hits, cnt, clsz, C, n_hs, None, out, None, False)
+        return out
+
+    def entropy_scalar(self, cols):
+        """H(cols) as a Python float (infoset.py:218-249)."""
+        with_y, cols = self._norm_cols(cols)
+        C, y, _, _ = self._labels(with_y)
+        mbits = self._build_mpacked(cols) if cols else 0
+        n_keys = C << mbits
+        table = self._table_scratch(n_keys)
+        out = torch.empty(1, dtype=torch.float64, device=self.device)
+        nat.call("prb_entropy_keys", nat.ptr(self.mpacked) if cols else None, nat.ptr(y), self.N,
+                 mbits, n_keys, nat.ptr(table), nat.ptr(self.term), nat.ptr(out), nat.stream())
+        return float(out.item())
+
+    # ------------------------------------------------------------ constructors
+    @classmethod
+    def from_csc_arrays(cls, indptr, indices, data, N, **kw):
+        """indptr int64[P+1], indices int32[nnz], data uint8[nnz]: host (numpy / pinned
+        torch) or device arrays of a canonical CSC matrix of bin codes."""
+        nat.require_cuda()
+        dev = torch.device("cuda", torch.cuda.current_device())
+
+        def up(a, dt):
+            t = torch.from_numpy(np.ascontiguousarray(a)) if isinstance(a, np.ndarray) else a
+            return t.to(device=dev, dtype=dt, non_blocking=True).contiguous()
+
+        indptr_d = up(indptr, torch.int64)
+        rows_d = up(indices, torch.int32)
+        codes_d = up(data, torch.uint8)
+        nnz = rows_d.numel()
+        packed = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
+        nat.call("prb_pack_csc", nat.ptr(rows_d), nat.ptr(codes_d), nnz, nat.ptr(packed),
+                 nat.stream())
+        K = (int(codes_d.max().item()) + 1) if nnz else 1
+        return cls(indptr_d, packed, N, K, **kw)
+
+    @classmethod
+    def from_dense_codes(cls, codes, N, **kw):
+        """codes: uint8 device tensor [P, ld] (column-major cells x genes, ld >= N)."""
+        P, ld = codes.shape
+        dev = codes.device
+        counts = torch.zeros(P, dtype=torch.int64, device=dev)
+        nat.call("prb_dense_count_nnz", nat.ptr(codes), N, P, ld, nat.ptr(counts), nat.stream())
+        indptr = torch.zeros(P + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(counts, 0, out=indptr[1:])
+        nnz = int(indptr[-1].item())
+        packed = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
+        nat.call("prb_dense_fill_csc", nat.ptr(codes), N, P, ld, nat.ptr(indptr), nat.ptr(packed),
+                 nat.stream())
+        K = (int(codes[:, :N].max().item()) + 1) if P else 1
+        return cls(indptr, packed, N, K, **kw)
+
+    def to_scipy_csc(self):
+        """Host scipy.sparse.csc_matrix (int64 data like the reference's) of the local genes."""
+        import scipy.sparse
+
+        rows = torch.empty(max(self.nnz, 1), dtype=torch.int32, device=self.device)
+        codes = torch.empty(max(self.nnz, 1), dtype=torch.uint8, device=self.device)
+        nat.call("prb_unpack_csc", nat.ptr(self.packed), self.nnz, nat.ptr(rows), nat.ptr(codes),
+                 nat.stream())
+        return scipy.sparse.csc_matrix(
+            (codes[: self.nnz].cpu().numpy().astype(np.int64), rows[: self.nnz].cpu().numpy(),
+             self.indptr.cpu().numpy()), shape=(self.N, self.P))

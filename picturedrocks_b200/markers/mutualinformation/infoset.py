@@ -1,0 +1,315 @@
+"""Information sets — host-side mirror of the reference interface
+(picturedrocks/markers/mutualinformation/infoset.py), computing on the GPU.
+
+Same names, argument meaning and error behaviour as the reference:
+  makeinfoset(adata, include_y, k=5)            infoset.py:25-47
+  quantile_discretize(X, k=5)                   infoset.py:50-83
+  InformationSet(X, has_y=False)                infoset.py:86-173
+  SparseInformationSet(X, y=None)               infoset.py:176-303
+Everything numeric runs in libprb200.so (see ../../engine.py); there is no CPU
+fallback.
+"""
+import ctypes
+
+import numpy as np
+import scipy.sparse
+import torch
+
+from ... import _native as nat
+from ...engine import Engine
+
+_DT = {np.dtype(np.float32): (0, torch.float32, torch.float32),
+       np.dtype(np.float64): (1, torch.float64, torch.float64),
+       np.dtype(np.int64): (2, torch.int64, torch.float64)}
+
+
+def _device():
+    nat.require_cuda()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def discretize_to_device(X, k=5, gene_block=None):
+    """quantile_discretize on the GPU; returns column-major uint8 codes as a device
+    tensor [P, N] (row g = gene g) — the layout the entropy kernels consume."""
+    if not (2 <= int(k) <= 256):
+        raise ValueError("k must be in [2, 256]")
+    k = int(k)
+    dev = _device()
+    if scipy.sparse.issparse(X):
+        X = X.toarray()  # same semantics as infoset.py:66-67 (zeros take part in the quantiles)
+    if isinstance(X, torch.Tensor):
+        Xh = None
+        Xd_full = X.to(dev)
+        np_dt = {torch.float32: np.float32, torch.float64: np.float64}.get(Xd_full.dtype, np.int64)
+        N, P = Xd_full.shape
+    else:
+        Xh = np.asarray(X)
+        if Xh.ndim != 2:
+            raise ValueError("X must be 2-d")
+        if Xh.dtype not in (np.float32, np.float64):
+            if not (np.issubdtype(Xh.dtype, np.integer) or Xh.dtype == np.bool_):
+                raise TypeError("unsupported dtype %s" % Xh.dtype)
+            Xh = Xh.astype(np.int64)
+        np_dt = Xh.dtype.type
+        N, P = Xh.shape
+        Xd_full = None
+    code, tdt, edt = _DT[np.dtype(np_dt)]
+    esz = 4 if code == 0 else 8
+    codes = torch.empty((P, N), dtype=torch.uint8, device=dev)
+    if P == 0 or N == 0:
+        return codes
+    if gene_block is None:
+        gene_block = max(1, min(P, 60000, ((1 << 31) - 1) // max(N, 1), (1 << 28) // max(N, 1) + 1))
+    s = nat.stream()
+    for g0 in range(0, P, gene_block):
+        g1 = min(P, g0 + gene_block)
+        pb = g1 - g0
+        if Xd_full is not None:
+            Xd = Xd_full[:, g0:g1].to(tdt).contiguous()
+        else:
+            Xd = torch.from_numpy(np.ascontiguousarray(Xh[:, g0:g1])).to(dev)
+        Xt = torch.empty((pb, N), dtype=tdt, device=dev)
+        nat.call("prb_transpose", nat.ptr(Xd), esz, N, pb, nat.ptr(Xt), s)
+        Xs = torch.empty_like(Xt)
+        ws_bytes = ctypes.c_int64()
+        nat.call("prb_sort_columns_workspace", code, N, pb, ctypes.byref(ws_bytes))
+        ws = torch.empty(ws_bytes.value, dtype=torch.uint8, device=dev)
+        nat.call("prb_sort_columns", nat.ptr(Xt), nat.ptr(Xs), code, N, pb, nat.ptr(ws),
+                 ws_bytes.value, s)
+        edges = torch.zeros((pb, max(k - 1, 1)), dtype=edt, device=dev)
+        n_edges = torch.zeros(pb, dtype=torch.int32, device=dev)
+        nat.call("prb_qd_edges", nat.ptr(Xs), code, N, pb, k, nat.ptr(edges), nat.ptr(n_edges), s)
+        nat.call("prb_qd_digitize", nat.ptr(Xt), code, N, pb, k, nat.ptr(edges), nat.ptr(n_edges),
+                 nat.ptr(codes[g0:g1]), N, s)
+    return codes
+
+
+def quantile_discretize(X, k=5):
+    """Discretize a data matrix with the recursive quantile transform (infoset.py:50-83).
+
+    Returns the reference's type: dense int64 ndarray [n_obs, n_features]."""
+    codes = discretize_to_device(X, k)
+    return np.ascontiguousarray(codes.cpu().numpy().T).astype(np.int64)
+
+
+def makeinfoset(adata, include_y, k=5):
+    """Discretize `adata.X` and wrap it in a SparseInformationSet (infoset.py:25-47).
+    The codes never leave the GPU: dense codes -> packed by-gene CSC on device."""
+    codes = discretize_to_device(adata.X, k)
+    infoset = SparseInformationSet._from_device_codes(codes)
+    if include_y:
+        infoset.set_y(adata.obs["y"].values)
+    return infoset
+
+
+def _check_codes_u8(vals):
+    if vals.size and (vals.min() < 0 or vals.max() > 255):
+        raise ValueError("bin codes must lie in [0, 255]")
+
+
+class _SelectorBackend:
+    """What the greedy selectors need from an information set, as device tensors."""
+
+    def __init__(self, engine, n_feats, ycol=None):
+        self.engine = engine
+        self.n_feats = n_feats  # local candidate features
+        self.ycol = ycol  # dense sets: index of the label column inside the matrix
+
+    @property
+    def device(self):
+        return self.engine.device
+
+    def base_vectors(self, supervised):
+        e = self.engine
+        if self.ycol is None:
+            Hx = e.entropy_wrt_device([])
+            if not supervised:
+                return Hx, None, None
+            return Hx, e.entropy_scalar([-1]), e.entropy_wrt_device([-1])
+        Hx = e.entropy_wrt_device([])[: self.n_feats].contiguous()
+        if not supervised:
+            return Hx, None, None
+        return (Hx, e.entropy_scalar([self.ycol]),
+                e.entropy_wrt_device([self.ycol])[: self.n_feats].contiguous())
+
+    def step(self, supervised, host_ind=None):
+        """(H(x_j, x_.), H(y, x_j, x_.)) for the gene held in engine.gene_ptr."""
+        e = self.engine
+        if self.ycol is None:
+            full = torch.empty(e.P, dtype=torch.float64, device=e.device)
+            if supervised:
+                marg = torch.empty_like(full)
+                e.direct_step(True, full, marg)
+                return marg, full
+            e.direct_step(False, full, None)
+            return full, None
+        j = int(e.gene_ptr.item()) if host_ind is None else int(host_ind)
+        Hij = e.entropy_wrt_device([j])[: self.n_feats].contiguous()
+        if not supervised:
+            return Hij, None
+        return Hij, e.entropy_wrt_device([self.ycol, j])[: self.n_feats].contiguous()
+
+
+class SparseInformationSet:
+    """Sparse discrete gene-expression matrix on the GPU (infoset.py:176-303).
+
+    Args
+    ----
+    X: scipy.sparse matrix or ndarray, shape (num_obs, num_vars), integer dtype
+    y: None or integer ndarray of shape (num_obs,) with non-negative labels
+
+    Extra keyword arguments (multi-GPU, one process per GPU): `gene_lo`, `P_total`
+    and `comm` declare that X holds only genes [gene_lo, gene_lo + X.shape[1]).
+    """
+
+    def __init__(self, X, y=None, gene_lo=0, P_total=None, comm=None):
+        Xc = scipy.sparse.csc_matrix(X)
+        assert np.issubdtype(Xc.dtype, np.integer), "X should be integer dtype"
+        Xc.sum_duplicates()
+        Xc.eliminate_zeros()
+        assert Xc.has_canonical_format, "Sparse matrix not in canonical format"
+        _check_codes_u8(Xc.data)
+        self._X = Xc
+        N, P = Xc.shape
+        eng = Engine.from_csc_arrays(Xc.indptr.astype(np.int64), Xc.indices.astype(np.int32),
+                                     Xc.data.astype(np.uint8), N, gene_lo=gene_lo,
+                                     P_total=P_total, comm=comm)
+        self._attach(eng)
+        self.set_y(y)
+
+    def _attach(self, eng):
+        self._engine = eng
+        self.N = eng.N
+        self.P = eng.P_total
+        # infoset.py:199 int(np.log2(X.max()) + 1); an all-zero matrix raises there too
+        if eng.K < 2:
+            raise OverflowError("cannot convert float infinity to integer")
+        self._shift = eng.shift
+        self.has_y = False
+        self.y = None
+
+    @classmethod
+    def _from_engine(cls, eng, y=None):
+        self = cls.__new__(cls)
+        self._X = None
+        self._attach(eng)
+        self.set_y(y)
+        return self
+
+    @classmethod
+    def _from_device_codes(cls, codes, **kw):
+        P, N = codes.shape
+        return cls._from_engine(Engine.from_dense_codes(codes, N, **kw))
+
+    @property
+    def X(self):
+        if self._X is None:
+            self._X = self._engine.to_scipy_csc()
+        return self._X
+
+    def set_y(self, y):
+        """Attach / replace / drop (None) the target labels (infoset.py:202-216)."""
+        self.has_y = y is not None
+        self.y = y
+        if not self.has_y:
+            self._engine.set_y(None)
+            return
+        if isinstance(y, torch.Tensor):
+            yd = y.to(self._engine.device)
+            assert not yd.dtype.is_floating_point, "y should be integer dtype"
+            assert tuple(yd.shape) == (self.N,)
+            assert int(yd.min().item()) >= 0, \
+                "y should have non-negative integers only; try using np.unique with return_inverse"
+            yd = yd.to(torch.int32).contiguous()
+            self.y = y
+        else:
+            if scipy.sparse.issparse(y):
+                y = y.toarray().flatten()
+            y = np.asarray(y)
+            self.y = y
+            assert np.issubdtype(y.dtype, np.integer), "y should be integer dtype"
+            assert y.shape == (self.N,)
+            assert y.min() >= 0, \
+                "y should have non-negative integers only; try using np.unique with return_inverse"
+            if y.max() == 0:
+                raise OverflowError("cannot convert float infinity to integer")  # infoset.py:216
+            yd = torch.from_numpy(y.astype(np.int32)).to(self._engine.device)
+        self._engine.set_y(yd)
+        self.classsizes = self._engine.classsizes.cpu().numpy().astype(np.float64)
+        self._ybits = int(self.classsizes.size - 1).bit_length()
+
+    def entropy(self, cols):
+        """Shannon entropy of the joint of `cols` (-1 as FIRST entry = y; infoset.py:218-249)."""
+        return self._engine.entropy_scalar(cols)
+
+    def entropy_wrt(self, cols):
+        """H(cols, x_i) for every feature i (infoset.py:251-303) as float64 ndarray."""
+        out = self._engine.entropy_wrt_device(cols)
+        return self._gather(out)
+
+    def _gather(self, t):
+        comm = self._engine.comm
+        if comm is not None:
+            t = comm.all_gather_shards(t)
+        return t.cpu().numpy()
+
+    def _selector_backend(self):
+        return _SelectorBackend(self._engine, self._engine.P)
+
+
+class InformationSet:
+    """Dense discrete gene-expression matrix (infoset.py:86-173).
+
+    Args
+    ----
+    X: ndarray (num_obs, num_vars) of dtype int; if `has_y`, the LAST column is the
+       target label column.
+    The matrix (label column included, exactly like the reference, which also sizes
+    `_shift` from it, infoset.py:112) is compacted on the GPU into the packed by-gene
+    form, so dense and sparse sets share one set of kernels.
+    """
+
+    def __init__(self, X, has_y=False):
+        X = np.asarray(X)
+        assert np.issubdtype(X.dtype, np.integer), "X should be integer dtype"
+        assert X.ndim == 2
+        _check_codes_u8(X)
+        self.has_y = bool(has_y)
+        self.X = X.astype(np.int64)
+        self.N, self.P = X.shape
+        if X.max() <= 0:
+            raise OverflowError("cannot convert float infinity to integer")  # infoset.py:112
+        self._shift = int(X.max()).bit_length()
+        dev = _device()
+        codes = torch.from_numpy(np.ascontiguousarray(X.T.astype(np.uint8))).to(dev)
+        self._engine = Engine.from_dense_codes(codes, self.N)
+        self._n_feats = self.P - 1 if self.has_y else self.P  # infoset.py:162
+
+    def entropy(self, cols):
+        """Entropy of the joint of `cols`; negative indices count from the end (numpy)."""
+        return self._engine.entropy_scalar(self._cols(cols))
+
+    def entropy_wrt(self, cols):
+        out = self._engine.entropy_wrt_device(self._cols(cols))
+        return out[: self._n_feats].cpu().numpy()
+
+    def _cols(self, cols):
+        cols = [int(c) for c in np.asarray(cols, dtype=np.int64).ravel()]
+        # every column (the label column too) is an ordinary column here
+        return [c + self.P if c < 0 else c for c in cols]
+
+    def _selector_backend(self):
+        return _SelectorBackend(self._engine, self._n_feats,
+                                ycol=self.P - 1 if self.has_y else None) \
+            if self.has_y else _DenseNoY(self._engine, self._n_feats)
+
+
+class _DenseNoY(_SelectorBackend):
+    """Dense set without labels: unsupervised selectors only, generic column path."""
+
+    def __init__(self, engine, n_feats):
+        super().__init__(engine, n_feats, ycol=-1)
+
+    def base_vectors(self, supervised):
+        assert not supervised
+        return self.engine.entropy_wrt_device([]).contiguous(), None, None

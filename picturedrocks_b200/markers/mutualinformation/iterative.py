@@ -1,0 +1,251 @@
+"""Greedy mutual-information selectors, device-resident
+(reference: picturedrocks/markers/mutualinformation/iterative.py:24-134).
+
+Class names, constructor signature, attributes (`infoset`, `S`, `base_score`,
+`penalty`, `score`) and methods (`add`, `remove`, `autoselect`) follow the
+reference.  Scores live on the GPU; `score` / `penalty` / `base_score` are
+materialised as float64 ndarrays on access, `S` as a Python list.
+`autoselect(n)` runs n greedy steps without any host synchronisation:
+
+    argmax (device)  ->  commit winner  ->  scatter x_j / build per-cell state
+    ->  one streaming pass (joint histograms)  ->  entropies  ->  score update
+
+Score algebra is evaluated in the reference's order (iterative.py:29-33, 50-58,
+78-86, 114-120) so results are bit-identical given bit-identical entropies.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from ... import _native as nat
+from .._iterative import IterativeFeatureSelection, UnivariateMixin
+
+_KIND = {"CIFE": 0, "JMI": 1, "CIFEUnsup": 2}
+
+
+def _backend(infoset):
+    try:
+        return infoset._selector_backend()
+    except AttributeError:
+        raise TypeError(
+            "picturedrocks_b200 selectors need a picturedrocks_b200 information set "
+            "(GPU-resident); got %r" % type(infoset).__name__)
+
+
+class _DeviceScores:
+    """base/penalty/score vectors of one selector, resident on the GPU."""
+
+    def __init__(self, infoset, supervised):
+        self.be = _backend(infoset)
+        e = self.be.engine
+        self.engine = e
+        self.comm = e.comm
+        self.dev = e.device
+        self.P = self.be.n_feats  # local candidates
+        self.gene_lo = e.gene_lo
+        self.P_total = e.P_total if self.be.ycol is None else self.be.n_feats
+        self.supervised = supervised
+        Hx, Hy, Hyx = self.be.base_vectors(supervised)
+        f64 = dict(dtype=torch.float64, device=self.dev)
+        if supervised:
+            self.base = torch.empty(self.P, **f64)
+            nat.call("prb_mi_base", nat.ptr(Hx), ctypes.c_double(Hy), nat.ptr(Hyx), self.P,
+                     nat.ptr(self.base), nat.stream())
+        else:
+            self.base = Hx.clone()
+        # replicated H(x_j), H(y,x_j) lookup vectors (== the reference's scalar
+        # entropy([j]) / entropy([-1, j]) bit-for-bit: same bins, same order)
+        self.Hx_all = self._replicate(Hx)
+        self.Hyx_all = self._replicate(Hyx) if supervised else None
+        self.penalty = torch.zeros(self.P, **f64)
+        self.score = self.base.clone()
+        self.selected = torch.zeros(max(self.P, 1), dtype=torch.uint8, device=self.dev)
+        self.n_blocks = max(1, -(-self.P // 256))
+        self.cand_score = torch.zeros(self.n_blocks, **f64)
+        self.cand_idx = torch.full((self.n_blocks,), -1, dtype=torch.int64, device=self.dev)
+        self.best_score = torch.zeros(1, **f64)
+        self.best_idx = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        self.S_dev = torch.zeros(self.P_total + 1, dtype=torch.int32, device=self.dev)
+        self.n_sel = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.cand_valid = False
+
+    def _replicate(self, v):
+        if self.comm is None:
+            return v
+        return self.comm.all_gather_shards(v)
+
+    def gather(self, v):
+        if self.comm is not None:
+            v = self.comm.all_gather_shards(v)
+        return v.cpu().numpy()
+
+    # -- device steps ---------------------------------------------------------
+    def pick_best(self):
+        """best_idx <- argmax(score) (global index; lowest index on ties)."""
+        s = nat.stream()
+        if not self.cand_valid:
+            nat.call("prb_argmax_blocks", nat.ptr(self.score), self.P, ctypes.c_int32(self.gene_lo),
+                     nat.ptr(self.cand_score), nat.ptr(self.cand_idx), s)
+        nat.call("prb_argmax_final", nat.ptr(self.cand_score), nat.ptr(self.cand_idx),
+                 self.n_blocks, nat.ptr(self.best_score), nat.ptr(self.best_idx), s)
+        if self.comm is not None:
+            gs = self.comm.all_gather_cat(self.best_score)
+            gi = self.comm.all_gather_cat(self.best_idx)
+            nat.call("prb_argmax_final", nat.ptr(gs), nat.ptr(gi), gs.numel(),
+                     nat.ptr(self.best_score), nat.ptr(self.best_idx), s)
+
+    def commit_best(self):
+        nat.call("prb_commit_add", nat.ptr(self.best_idx), nat.ptr(self.engine.gene_ptr),
+                 nat.ptr(self.S_dev), nat.ptr(self.n_sel), nat.ptr(self.selected),
+                 ctypes.c_int32(self.gene_lo), self.P, nat.stream())
+
+    def apply(self, kind, is_remove, host_ind=None):
+        """penalty/score update for the gene in engine.gene_ptr."""
+        Hij, Hyij = self.be.step(self.supervised, host_ind)
+        nat.call("prb_selector_update", _KIND[kind], int(is_remove), nat.ptr(self.base),
+                 nat.ptr(self.penalty), nat.ptr(self.score), nat.ptr(self.selected), nat.ptr(Hij),
+                 nat.ptr(Hyij), nat.ptr(self.Hx_all), nat.ptr(self.Hyx_all),
+                 nat.ptr(self.engine.gene_ptr), nat.ptr(self.n_sel), self.P,
+                 ctypes.c_int32(self.gene_lo), nat.ptr(self.cand_score), nat.ptr(self.cand_idx),
+                 nat.stream())
+        self.cand_valid = True
+
+
+class _GreedyDevice(IterativeFeatureSelection):
+    """Shared machinery of CIFE / JMI / CIFEUnsup."""
+
+    _kind = None
+    _supervised = True
+
+    def __init__(self, infoset):
+        if self._supervised:
+            assert infoset.has_y, "Information Set must have target labels"
+        self.infoset = infoset
+        self._d = _DeviceScores(infoset, self._supervised)
+        self._S = []
+        self._pending = 0  # selections made on device, not yet mirrored in _S
+
+    # -- host-visible state -----------------------------------------------------
+    @property
+    def S(self):
+        if self._pending:
+            n = len(self._S) + self._pending
+            self._S = [int(v) for v in self._d.S_dev[:n].cpu().numpy()]
+            self._pending = 0
+        return self._S
+
+    @S.setter
+    def S(self, value):
+        self._S = list(value)
+        self._pending = 0
+        self._push_S()
+
+    @property
+    def score(self):
+        return self._d.gather(self._d.score)
+
+    @property
+    def penalty(self):
+        return self._d.gather(self._d.penalty)
+
+    @property
+    def base_score(self):
+        return self._d.gather(self._d.base)
+
+    def _push_S(self):
+        d = self._d
+        S = self._S
+        d.n_sel.fill_(len(S))
+        if S:
+            d.S_dev[: len(S)] = torch.tensor(S, dtype=torch.int32, device=d.dev)
+        d.selected.zero_()
+        loc = [s - d.gene_lo for s in S if 0 <= s - d.gene_lo < d.P]
+        if loc:
+            d.selected[torch.tensor(loc, dtype=torch.int64, device=d.dev)] = 1
+
+    def _check(self, ind):
+        ind = int(ind)
+        if ind < 0:
+            ind += self._d.P_total
+        if not (0 <= ind < self._d.P_total):
+            raise IndexError("feature index out of range")
+        return ind
+
+    # -- reference API ------------------------------------------------------------
+    def add(self, ind):
+        ind = self._check(ind)
+        self.S.append(ind)
+        self._push_S()
+        self._d.engine.gene_ptr.fill_(ind)
+        self._d.apply(self._kind, False, ind)
+
+    def remove(self, ind):
+        ind = self._check(ind)
+        self.S.remove(ind)  # ValueError if absent, like list.remove in the reference
+        self._push_S()
+        self._d.engine.gene_ptr.fill_(ind)
+        self._d.apply(self._kind, True, ind)
+
+    def autoselect(self, n_feats):
+        n_feats = int(n_feats)
+        d = self._d
+        if len(self._S) + self._pending + n_feats > d.P_total:
+            raise ValueError("cannot select more features than there are")
+        for _ in range(n_feats):
+            d.pick_best()
+            d.commit_best()
+            d.apply(self._kind, False)
+        self._pending += n_feats
+
+
+class CIFE(_GreedyDevice):
+    """Conditional infomax feature extraction: score = I(x;y) - Σ_j I(x;x_j;y)."""
+
+    _kind = "CIFE"
+
+
+class JMI(_GreedyDevice):
+    """Joint mutual information: score = I(x;y) - mean_j I(x;x_j;y)."""
+
+    _kind = "JMI"
+
+
+class CIFEUnsup(_GreedyDevice):
+    """Unsupervised CIFE: score = H(x) - Σ_j I(x;x_j)."""
+
+    _kind = "CIFEUnsup"
+    _supervised = False
+
+
+class MIMixin:
+    """Univariate supervised base score I(x_i; y) (iterative.py:24-35)."""
+
+    def __init__(self, infoset):
+        assert infoset.has_y, "Information Set must have target labels"
+        self.infoset = infoset
+        self.S = []
+        d = _DeviceScores(infoset, True)
+        self.base_score = d.gather(d.base)
+        self.penalty = np.zeros(len(self.base_score))
+        self.score = self.base_score.copy()
+
+
+class EntropyMixin:
+    """Univariate unsupervised base score H(x_i) (iterative.py:38-44)."""
+
+    def __init__(self, infoset):
+        self.infoset = infoset
+        self.S = []
+        d = _DeviceScores(infoset, False)
+        self.base_score = d.gather(d.base)
+        self.penalty = np.zeros(len(self.base_score))
+        self.score = self.base_score.copy()
+
+
+class MIM(MIMixin, UnivariateMixin, IterativeFeatureSelection):
+    """Mutual information maximisation (no redundancy term)."""
+
+
+class UniEntropy(EntropyMixin, UnivariateMixin, IterativeFeatureSelection):
+    """Highest-entropy features."""

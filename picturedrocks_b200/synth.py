@@ -1,0 +1,178 @@
+"""Synthetic inputs for benchmarks and parity tests.
+
+BASELINE.json names shapes only; the recipes here are ours and are frozen:
+
+* `poisson_gamma(N, P, C, seed)` — small dense count matrices (configs 1-2) that go
+  through the real discretiser.  numpy RandomState, host side.
+* `DiscretisedSpec` — large pre-discretised sparse matrices (configs 3-5) defined by
+  a counter-based integer hash, generated directly as packed by-gene CSC on the GPU by
+  csrc/synth.cu and reproducible for ANY gene subset on the CPU by `cpu_codes` /
+  `cpu_csc` below (same 64-bit arithmetic), which is what lets the oracle check
+  full-size runs on sampled genes.
+"""
+import ctypes
+from dataclasses import dataclass
+
+import numpy as np
+
+M64 = (1 << 64) - 1
+GOLD = 0x9E3779B97F4A7C15
+M2 = 0xD1B54A32D192ED03
+SALT_A = 0x1234567
+SALT_B = 0xC1A55
+SALT_Y = 0xA5A5A5A5A5A5A5A5
+_MULT = np.array([1, 2, 3, 4, 4, 6, 8, 12], dtype=np.uint64)
+_P_GEOM = (0.35, 0.5, 0.65, 0.8)
+
+
+def poisson_gamma(N, P, C, seed, dtype=np.float32):
+    """Count-like expression matrix with class effects; returns (X[N,P], y[N])."""
+    rng = np.random.RandomState(seed)
+    y = rng.randint(0, C, N)
+    lam = rng.gamma(0.3, 3.0, P)
+    eff = np.exp(0.5 * rng.randn(C, P))
+    X = rng.poisson(lam * eff[y]).astype(dtype)
+    return X, y.astype(np.int64)
+
+
+def _mix64(z):
+    z = np.asarray(z, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        z = z ^ (z >> np.uint64(30))
+        z = z * np.uint64(0xBF58476D1CE4E5B9)
+        z = z ^ (z >> np.uint64(27))
+        z = z * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return z
+
+
+def _mix64_int(z):
+    z &= M64
+    z ^= z >> 30
+    z = (z * 0xBF58476D1CE4E5B9) & M64
+    z ^= z >> 27
+    z = (z * 0x94D049BB133111EB) & M64
+    z ^= z >> 31
+    return z
+
+
+@dataclass(frozen=True)
+class DiscretisedSpec:
+    N: int
+    P: int
+    C: int
+    K: int = 5
+    mean_density: float = 0.07
+    seed: int = 4
+
+    @property
+    def mean_q24(self):
+        return int(round(self.mean_density * (1 << 24)))
+
+    def cum_table(self):
+        """uint32[4][K-2]: 16-bit cumulative thresholds of the geometric code law."""
+        K = self.K
+        out = np.zeros((4, max(K - 2, 1)), dtype=np.uint32)
+        for pi, p in enumerate(_P_GEOM):
+            for t in range(1, K - 1):
+                out[pi, t - 1] = int(65536.0 * (1.0 - p ** t))
+        return out
+
+    # ---- CPU reproduction -----------------------------------------------------
+    def cpu_labels(self):
+        i = np.arange(self.N, dtype=np.uint64)
+        with np.errstate(over="ignore"):
+            h = _mix64(np.uint64((self.seed ^ SALT_Y) & M64) + i * np.uint64(GOLD))
+        return ((h >> np.uint64(33)) % np.uint64(self.C)).astype(np.int64)
+
+    def _gene_params(self, gene):
+        gene_eff = gene - 1 if (gene % 4001 == 17 and gene > 0) else gene
+        all_zero = gene_eff % 5003 == 29
+        gk = _mix64_int(self.seed ^ ((gene_eff * GOLD) & M64))
+        u32 = _mix64_int(gk ^ SALT_A) >> 32
+        u2 = (u32 * u32) >> 32
+        u4 = (u2 * u2) >> 32
+        u8 = (u4 * u4) >> 32
+        cap = int(0.95 * 16777216.0)
+        dmax = min(9 * self.mean_q24, int(0.9 * 16777216.0))
+        base = ((u8 * dmax) >> 32) + (self.mean_q24 >> 4)
+        thr = np.zeros(self.C, dtype=np.uint64)
+        pidx = np.zeros(self.C, dtype=np.int64)
+        for c in range(self.C):
+            ck = _mix64_int(gk ^ ((SALT_B + c * GOLD) & M64))
+            t = min(base * int(_MULT[ck & 7]) // 4, cap)
+            thr[c] = 0 if all_zero else t
+            pidx[c] = (ck >> 3) & 3
+        return gk, thr, pidx
+
+    def cpu_codes(self, gene, y=None):
+        """uint8[N] codes of one gene (dense)."""
+        if y is None:
+            y = self.cpu_labels()
+        gk, thr, pidx = self._gene_params(int(gene))
+        cell = np.arange(self.N, dtype=np.uint64)
+        with np.errstate(over="ignore"):
+            h = _mix64(np.uint64(gk) + cell * np.uint64(M2))
+        nz = (h >> np.uint64(40)) < thr[y]
+        r16 = ((h >> np.uint64(8)) & np.uint64(0xFFFF)).astype(np.int64)
+        cum = self.cum_table().astype(np.int64)
+        code = np.ones(self.N, dtype=np.int64)
+        for t in range(self.K - 2):
+            code += r16 >= cum[pidx[y], t]
+        return np.where(nz, code, 0).astype(np.uint8)
+
+    def cpu_csc(self, genes, y=None):
+        """scipy CSC (N x len(genes), int64 data) of the listed genes."""
+        import scipy.sparse
+
+        if y is None:
+            y = self.cpu_labels()
+        indptr, rows, data = [0], [], []
+        for g in genes:
+            col = self.cpu_codes(g, y)
+            nzr = np.flatnonzero(col)
+            rows.append(nzr.astype(np.int32))
+            data.append(col[nzr].astype(np.int64))
+            indptr.append(indptr[-1] + nzr.size)
+        return scipy.sparse.csc_matrix(
+            (np.concatenate(data) if data else np.zeros(0, np.int64),
+             np.concatenate(rows) if rows else np.zeros(0, np.int32),
+             np.asarray(indptr, dtype=np.int64)), shape=(self.N, len(genes)))
+
+    # ---- device generation ------------------------------------------------------
+    def device_labels(self):
+        import torch
+
+        from . import _native as nat
+
+        nat.require_cuda()
+        y = torch.empty(self.N, dtype=torch.int32, device="cuda")
+        nat.call("prb_synth_labels", nat.ptr(y), self.N, self.C,
+                 ctypes.c_uint64(self.seed & M64), nat.stream())
+        return y
+
+    def device_engine(self, gene_lo=0, gene_hi=None, comm=None, y=None):
+        """Engine holding genes [gene_lo, gene_hi) generated on the current GPU."""
+        import torch
+
+        from . import _native as nat
+        from .engine import Engine
+
+        nat.require_cuda()
+        gene_hi = self.P if gene_hi is None else gene_hi
+        Pl = gene_hi - gene_lo
+        if y is None:
+            y = self.device_labels()
+        cum = torch.from_numpy(self.cum_table().astype(np.int32).view(np.int32)).cuda()
+        counts = torch.zeros(Pl, dtype=torch.int64, device="cuda")
+        s = nat.stream()
+        args = (nat.ptr(y), self.N, gene_lo, Pl, self.C, self.K, ctypes.c_uint32(self.mean_q24),
+                ctypes.c_uint64(self.seed & M64), nat.ptr(cum))
+        nat.call("prb_synth_count", *args, nat.ptr(counts), s)
+        indptr = torch.zeros(Pl + 1, dtype=torch.int64, device="cuda")
+        torch.cumsum(counts, 0, out=indptr[1:])
+        nnz = int(indptr[-1].item())
+        packed = torch.empty(max(nnz, 1), dtype=torch.int32, device="cuda")
+        nat.call("prb_synth_fill", *args, nat.ptr(indptr), nat.ptr(packed), s)
+        eng = Engine(indptr, packed, self.N, self.K, gene_lo=gene_lo, P_total=self.P, comm=comm)
+        return eng, y
