@@ -95,8 +95,23 @@ class PrbError(RuntimeError):
     pass
 
 
+# kernels launched per entry point (for bench.py's gpu_launches claim)
+KERNELS = {
+    "prb_pack_csc": 1, "prb_unpack_csc": 1, "prb_dense_count_nnz": 1, "prb_dense_fill_csc": 1,
+    "prb_range_genes": 1, "prb_stream_hits": 1, "prb_scatter_gene_u8": 1,
+    "prb_scatter_gene_or32": 1, "prb_state_direct": 2, "prb_state_table": 3, "prb_finalize": 1,
+    "prb_entropy_keys": 2, "prb_mi_base": 1, "prb_selector_update": 1, "prb_argmax_blocks": 1,
+    "prb_argmax_final": 1, "prb_commit_add": 1, "prb_transpose": 1, "prb_sort_columns": 1,
+    "prb_qd_edges": 1, "prb_qd_digitize": 1, "prb_synth_labels": 1, "prb_synth_count": 1,
+    "prb_synth_fill": 1,
+}
+LAUNCHES = 0
+
+
 def call(name, *args):
+    global LAUNCHES
     lib = load()
+    LAUNCHES += KERNELS.get(name, 0)
     rc = getattr(lib, name)(*args)
     if rc != 0:
         raise PrbError("%s failed: %s" % (name, lib.prb_last_error().decode()))

@@ -133,6 +133,18 @@ class Engine:
         return self._hits
 
     def _stream(self, n_bins, hits):
+        ev = getattr(self, "profile_events", None)
+        if ev is not None:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            self._stream_launch(n_bins, hits)
+            e1.record()
+            ev.append((e0, e1))
+        else:
+            self._stream_launch(n_bins, hits)
+
+    def _stream_launch(self, n_bins, hits):
         nat.call("prb_stream_hits", nat.ptr(self.packed), nat.ptr(self.indptr),
                  nat.ptr(self.range_gene), self.n_ranges, self.range_len, self.nnz,
                  nat.ptr(self.bitmap), nat.ptr(self.state16), self.N, n_bins, nat.ptr(hits),

