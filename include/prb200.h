@@ -63,28 +63,25 @@ int prb_dense_count_nnz(const uint8_t *codes, int64_t N, int64_t P, int64_t ld,
 int prb_dense_fill_csc(const uint8_t *codes, int64_t N, int64_t P, int64_t ld,
                        const int64_t *indptr, uint32_t *packed, prb_stream_t stream);
 
-/* ---- work partition of the nnz stream ------------------------------------
- * range r covers packed[r*range_len, min((r+1)*range_len, nnz)); range_gene[r]
- * is the gene that owns its first word. */
-int prb_range_genes(const int64_t *indptr, int64_t P, int64_t nnz, int64_t range_len,
-                    int64_t n_ranges, int32_t *range_gene, prb_stream_t stream);
-
 /* ---- the hot loop: per-gene joint histogram of (cell state, code) ----------
  * replaces the two-pointer merge of _sparse_entropy_wrt (INFOSET:365-391).
- *   bitmap != NULL : only cells whose bit is set ("master column non-zero") are
- *                    counted; all others are inferred by subtraction later.
- *   bitmap == NULL : every stored entry is counted (class-conditional tables).
- *   state16        : uint16[N], per-cell bin base (state id * (K-1)); NULL = 0.
- *   hits           : int32[P][n_bins], must be zero on entry; += counts of
- *                    bin  state16[row] + code - 1.
- *   work_counter   : int32 in device memory, must be zero on entry.
- * Returns the dynamic shared memory it needs via prb_stream_smem_bytes(). */
-int prb_stream_smem_bytes(int64_t N, int64_t n_bins, int use_bitmap, int *teams_per_cta,
-                          int64_t *smem_bytes);
-int prb_stream_hits(const uint32_t *packed, const int64_t *indptr, const int32_t *range_gene,
-                    int64_t n_ranges, int64_t range_len, int64_t nnz, const uint32_t *bitmap,
-                    const uint16_t *state16, int64_t N, int64_t n_bins, int32_t *hits,
-                    int32_t *work_counter, prb_stream_t stream);
+ * Per-cell state: uint8 (when n_states + 1 <= 256) or uint16, 0 = "not a master row"
+ * (skipped; inferred by subtraction later), else 1 + joint-state id in [0, n_states).
+ * The state of one TILE of cells is staged in shared memory; prb_stream_plan() gives the
+ * tile size / count for (N, n_states, K-1) and prb_tile_ptrs() the per-(tile, gene)
+ * sub-ranges of the packed stream: tp int64[n_tiles+1][P].
+ *   hits     : int32[P][n_states*(K-1)], zero on entry; bin of a counted entry is
+ *              h*(K-1) + code-1 with h = state id, or, for the direct single-gene layout
+ *              (direct_C = C > 0, state id = (x_j-1)*C + y), h = y*(K-1) + x_j-1.
+ *   counters : int32[n_tiles] scratch (reset by the call).
+ *   state    : buffer padded to a multiple of 16 bytes. */
+int prb_stream_plan(int64_t N, int64_t n_states, int K1, int64_t *tile_cells, int *n_tiles,
+                    int *teams_per_cta, int *state_bytes, int64_t *smem_bytes);
+int prb_tile_ptrs(const uint32_t *packed, const int64_t *indptr, int64_t P, int64_t tile_cells,
+                  int n_tiles, int64_t *tp, prb_stream_t stream);
+int prb_stream_hits(const uint32_t *packed, const int64_t *tp, int64_t P, int64_t nnz,
+                    const void *state, int64_t N, int64_t n_states, int K1, int direct_C,
+                    int32_t *hits, int32_t *counters, prb_stream_t stream);
 
 /* ---- joint-state build ("master column", _sparse_make_master_col INFOSET:431-442) */
 /* dense uint8 x_j[N] (zeroed by caller) <- codes of gene *gene_ptr (device int32;
@@ -94,22 +91,22 @@ int prb_scatter_gene_u8(const uint32_t *packed, const int64_t *indptr, const int
 /* mpacked[row] |= code << shift_bits for every stored entry of gene `gene`. */
 int prb_scatter_gene_or32(const uint32_t *packed, const int64_t *indptr, int64_t gene,
                           int shift_bits, uint32_t *mpacked, prb_stream_t stream);
-/* direct single-column state: state id = y*(K-1) + x_j - 1 (y = 0 without labels).
- * Writes bitmap uint32[ceil(N/32)], state16[N] (= id*(K-1)), hsize int32[C*(K-1)]
- * (zeroed here), hs_begin int32[C+1], hs_y int32[C*(K-1)], hs_ysum int32[C],
- * ha int32[K-1]; also resets *work_counter to 0. */
-int prb_state_direct(const uint8_t *xj, const int32_t *y, int64_t N, int C, int K,
-                     uint32_t *bitmap, uint16_t *state16, int32_t *hsize, int32_t *hs_begin,
-                     int32_t *hs_y, int32_t *hs_ysum, int32_t *ha, int32_t *work_counter,
-                     prb_stream_t stream);
-/* generic multi-column state through an order-preserving presence-table
- * compaction (the "sort/unique relabel"): key = y << mbits | mpacked.
- * table int32[C << mbits] scratch.  n_hs_out: device int32. */
-int prb_state_table(const uint32_t *mpacked, const int32_t *y, int64_t N, int C, int K,
-                    int mbits, int32_t *table, uint32_t *bitmap, uint16_t *state16,
-                    int32_t *hsize, int32_t *hs_begin, int32_t *hs_y, int32_t *hs_ysum,
-                    int32_t *n_hs_out, int32_t *work_counter, int64_t hsize_cap,
-                    prb_stream_t stream);
+/* direct single-column state: state = 1 + (x_j-1)*C + y for x_j > 0 (y = 0 without
+ * labels).  Writes state[N] (state_bytes 1|2), hsize int32[C*(K-1)] indexed
+ * y*(K-1)+x_j-1 (zeroed here), hs_begin int32[C+1], hs_y int32[C*(K-1)],
+ * hs_ysum int32[C], ha int32[K-1]. */
+int prb_state_direct(const uint8_t *xj, const int32_t *y, int64_t N, int C, int K, void *state,
+                     int state_bytes, int32_t *hsize, int32_t *hs_begin, int32_t *hs_y,
+                     int32_t *hs_ysum, int32_t *ha, prb_stream_t stream);
+/* generic multi-column state through an order-preserving presence-table compaction
+ * (the "sort/unique relabel"): key = y << mbits | mpacked.  table int32[C << mbits]
+ * scratch; after the call it maps key -> rank.  n_hs_out: device int32.
+ * prb_state_assign then writes state = 1 + rank (0 where mpacked == 0). */
+int prb_state_table(const uint32_t *mpacked, const int32_t *y, int64_t N, int C, int mbits,
+                    int32_t *table, int32_t *hsize, int32_t *hs_begin, int32_t *hs_y,
+                    int32_t *hs_ysum, int32_t *n_hs_out, int64_t hsize_cap, prb_stream_t stream);
+int prb_state_assign(const uint32_t *mpacked, const int32_t *y, int64_t N, int mbits,
+                     const int32_t *table, void *state, int state_bytes, prb_stream_t stream);
 
 /* ---- entropies from histograms (INFOSET:392-397), ordered fp64 sum ----------
  * out_full[g]  = H(y, master, x_g)   (bins ascending (y, master, code))
@@ -121,6 +118,13 @@ int prb_finalize(int32_t *hits, const int32_t *cnt, const int64_t *classsizes,
                  const int32_t *hs_ysum, const int32_t *ha, const int32_t *n_hs_ptr,
                  int64_t n_hs_cap, int C, int K, const double *table, int64_t N, int64_t P,
                  double *out_full, double *out_marg, prb_stream_t stream);
+/* Same result for the DIRECT single-gene layout (state id = y*(K-1) + x_j - 1, as
+ * written by prb_state_direct), one thread per gene; hits int32[P][C][K-1][K-1] or
+ * NULL (then out_full = H(y, x_g), out_marg = H(x_g)). */
+int prb_finalize_direct(int32_t *hits, const int32_t *cnt, const int64_t *classsizes,
+                        const int32_t *hsize, const int32_t *hs_ysum, const int32_t *ha, int C,
+                        int K, const double *table, int64_t N, int64_t P, double *out_full,
+                        double *out_marg, prb_stream_t stream);
 /* scalar entropy of a per-cell key vector through a count table (INFOSET:218-249,
  * 413-428): table int32[n_keys] scratch; out: device double. */
 int prb_entropy_keys(const uint32_t *mpacked, const int32_t *y, int64_t N, int mbits,

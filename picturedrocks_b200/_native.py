@@ -29,16 +29,19 @@ _SIGS = {
     "prb_unpack_csc": [_vp, _i64, _vp, _vp, _vp],
     "prb_dense_count_nnz": [_vp, _i64, _i64, _i64, _vp, _vp],
     "prb_dense_fill_csc": [_vp, _i64, _i64, _i64, _vp, _vp, _vp],
-    "prb_range_genes": [_vp, _i64, _i64, _i64, _i64, _vp, _vp],
-    "prb_stream_smem_bytes": [_i64, _i64, _int, ctypes.POINTER(_int), ctypes.POINTER(_i64)],
-    "prb_stream_hits": [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _i64, _i64, _vp, _vp, _vp],
+    "prb_stream_plan": [_i64, _i64, _int, ctypes.POINTER(_i64), ctypes.POINTER(_int),
+                        ctypes.POINTER(_int), ctypes.POINTER(_int), ctypes.POINTER(_i64)],
+    "prb_tile_ptrs": [_vp, _vp, _i64, _i64, _int, _vp, _vp],
+    "prb_stream_hits": [_vp, _vp, _i64, _i64, _vp, _i64, _i64, _int, _int, _vp, _vp, _vp],
     "prb_scatter_gene_u8": [_vp, _vp, _vp, _i32, _i64, _vp, _vp],
     "prb_scatter_gene_or32": [_vp, _vp, _i64, _int, _vp, _vp],
-    "prb_state_direct": [_vp, _vp, _i64, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
-    "prb_state_table": [_vp, _vp, _i64, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                        _vp, _i64, _vp],
+    "prb_state_direct": [_vp, _vp, _i64, _int, _int, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp],
+    "prb_state_table": [_vp, _vp, _i64, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
+    "prb_state_assign": [_vp, _vp, _i64, _int, _vp, _vp, _int, _vp],
     "prb_finalize": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _vp, _i64, _i64,
                      _vp, _vp, _vp],
+    "prb_finalize_direct": [_vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _vp, _i64, _i64, _vp, _vp,
+                            _vp],
     "prb_entropy_keys": [_vp, _vp, _i64, _int, _i64, _vp, _vp, _vp, _vp],
     "prb_mi_base": [_vp, _f64, _vp, _i64, _vp, _vp],
     "prb_selector_update": [_int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64,
@@ -98,8 +101,8 @@ class PrbError(RuntimeError):
 # kernels launched per entry point (for bench.py's gpu_launches claim)
 KERNELS = {
     "prb_pack_csc": 1, "prb_unpack_csc": 1, "prb_dense_count_nnz": 1, "prb_dense_fill_csc": 1,
-    "prb_range_genes": 1, "prb_stream_hits": 1, "prb_scatter_gene_u8": 1,
-    "prb_scatter_gene_or32": 1, "prb_state_direct": 2, "prb_state_table": 3, "prb_finalize": 1,
+    "prb_tile_ptrs": 1, "prb_stream_hits": 1, "prb_scatter_gene_u8": 1,
+    "prb_scatter_gene_or32": 1, "prb_state_direct": 2, "prb_state_table": 2, "prb_state_assign": 1, "prb_finalize": 1, "prb_finalize_direct": 1,
     "prb_entropy_keys": 2, "prb_mi_base": 1, "prb_selector_update": 1, "prb_argmax_blocks": 1,
     "prb_argmax_final": 1, "prb_commit_add": 1, "prb_transpose": 1, "prb_sort_columns": 1,
     "prb_qd_edges": 1, "prb_qd_digitize": 1, "prb_synth_labels": 1, "prb_synth_count": 1,

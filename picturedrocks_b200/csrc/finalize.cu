@@ -146,6 +146,116 @@ k_finalize(int32_t *__restrict__ hits, int64_t hits_stride, const int32_t *__res
     }
 }
 
+
+// ---------------------------------------------------------------------------
+// Direct (single selected gene) layout, one THREAD per gene: state id of a hit
+// cell is y*(K-1) + x_j - 1, so hits[g] is a [C][K-1][K-1] cube and every bin of
+// the (y, x_j, x_i) histogram follows from it, cnt[g][y][.], hsize[y][.] and
+// classsizes by subtraction.  Each lane walks its own gene sequentially in the
+// reference's bin order, so the ordered fp64 sum needs no cross-lane traffic and
+// all 32 lanes stay busy.  TK1 > 0 fixes K-1 at compile time (loops unroll and
+// the term-table gathers of a class are issued together).
+// Scratch (shared memory, one int column per thread, stride = blockDim.x):
+//   cs[K1] rs[K1] m2[K1*K1] xc[K1]
+// ---------------------------------------------------------------------------
+template <int TK1>
+__global__ void __launch_bounds__(128)
+k_finalize_direct(int32_t *__restrict__ hits, int64_t hits_stride,
+                  const int32_t *__restrict__ cnt, const int64_t *__restrict__ clsz,
+                  const int32_t *__restrict__ hsize, const int32_t *__restrict__ hs_ysum,
+                  const int32_t *__restrict__ ha, int C, int k1_rt,
+                  const double *__restrict__ term, int64_t N, int64_t P,
+                  double *__restrict__ out_full, double *__restrict__ out_marg)
+{
+    extern __shared__ int sh[];
+    const int K1 = TK1 ? TK1 : k1_rt;
+    const int nt = blockDim.x;
+    int *cs = sh + threadIdx.x;
+    int *rs = cs + K1 * nt;
+    int *m2 = rs + K1 * nt;
+    int *xc = m2 + K1 * K1 * nt;
+    const bool marg = out_marg != nullptr;
+    const int64_t g = blockIdx.x * (int64_t)nt + threadIdx.x;
+    if (g >= P) return;
+    if (marg) {
+#pragma unroll
+        for (int i = 0; i < K1 * K1; ++i) m2[i * nt] = 0;
+#pragma unroll
+        for (int i = 0; i < K1; ++i) xc[i * nt] = 0;
+    }
+    const int32_t *crow = cnt + g * (int64_t)C * K1;
+    int32_t *hrow = hits ? hits + g * hits_stride : nullptr;
+    double h = 0.0;
+    for (int y = 0; y < C; ++y, crow += K1) {
+        // pass 1: row / column sums of this class's hit square
+#pragma unroll
+        for (int v = 0; v < K1; ++v) cs[v * nt] = 0;
+        if (hrow) {
+#pragma unroll
+            for (int a = 0; a < K1; ++a) {
+                int r = 0;
+#pragma unroll
+                for (int v = 0; v < K1; ++v) {
+                    const int x = hrow[a * K1 + v];
+                    r += x;
+                    cs[v * nt] += x;
+                    if (marg) m2[(a * K1 + v) * nt] += x;
+                }
+                rs[a * nt] = r;
+            }
+        }
+        int tot0 = 0;
+#pragma unroll
+        for (int v = 0; v < K1; ++v) {
+            const int c0 = crow[v];
+            tot0 += c0 - cs[v * nt];
+            if (marg) xc[v * nt] += c0;
+        }
+        // master == 0 group: (y,0,0), (y,0,v)
+        const int c00 = (int)(clsz[y] - (hrow ? hs_ysum[y] : 0) - tot0);
+        h = __dadd_rn(h, __ldg(term + c00));
+#pragma unroll
+        for (int v = 0; v < K1; ++v) h = __dadd_rn(h, __ldg(term + (crow[v] - cs[v * nt])));
+        // master == a groups
+        if (hrow) {
+#pragma unroll
+            for (int a = 0; a < K1; ++a) {
+                h = __dadd_rn(h, __ldg(term + (hsize[y * K1 + a] - rs[a * nt])));
+#pragma unroll
+                for (int v = 0; v < K1; ++v) {
+                    const int x = hrow[a * K1 + v];
+                    h = __dadd_rn(h, __ldg(term + x));
+                    if (x) hrow[a * K1 + v] = 0;  // leave the buffer clean
+                }
+            }
+            hrow += K1 * K1;
+        }
+    }
+    out_full[g] = h;
+    if (marg) {
+        int sum_ha = 0, sum_xc = 0, sum_m2 = 0;
+        for (int a = 0; a < K1; ++a) {
+            sum_ha += (hits && ha) ? ha[a] : 0;
+            sum_xc += xc[a * nt];
+        }
+        for (int i = 0; i < K1 * K1; ++i) sum_m2 += m2[i * nt];
+        double h2 = __ldg(term + (int)(N - sum_ha - (sum_xc - sum_m2)));
+        h2 = __dadd_rn(0.0, h2);
+        for (int v = 0; v < K1; ++v) {
+            int s = 0;
+            for (int a = 0; a < K1; ++a) s += m2[(a * K1 + v) * nt];
+            h2 = __dadd_rn(h2, __ldg(term + (xc[v * nt] - s)));
+        }
+        for (int a = 0; a < K1; ++a) {
+            int s = 0;
+            for (int v = 0; v < K1; ++v) s += m2[(a * K1 + v) * nt];
+            h2 = __dadd_rn(h2, __ldg(term + (((hits && ha) ? ha[a] : 0) - s)));
+            for (int v = 0; v < K1; ++v) h2 = __dadd_rn(h2, __ldg(term + m2[(a * K1 + v) * nt]));
+        }
+        out_marg[g] = h2;
+    }
+}
+
 }  // namespace prb
 
 using namespace prb;
@@ -176,4 +286,51 @@ extern "C" int prb_finalize(int32_t *hits, const int32_t *cnt, const int64_t *cl
         (int)n_hs_cap, C, K, table, N, P, out_full, out_marg, (int)scratch);
     PRB_LAUNCH_CHECK("k_finalize");
     return 0;
+}
+
+
+template <int TK1>
+static int launch_direct(int32_t *hits, int64_t stride, const int32_t *cnt, const int64_t *clsz,
+                         const int32_t *hsize, const int32_t *hs_ysum, const int32_t *ha, int C,
+                         int K1, const double *table, int64_t N, int64_t P, double *out_full,
+                         double *out_marg, cudaStream_t st)
+{
+    const int64_t per_thread = (int64_t)(3 * K1 + K1 * K1) * 4;
+    int threads = 128;
+    const int64_t smem_max = devinfo().smem_optin - 1024;
+    while (threads > 32 && per_thread * threads > smem_max) threads >>= 1;
+    PRB_REQUIRE(per_thread * threads <= smem_max, "finalize scratch does not fit in shared memory");
+    // spread genes over all SMs: small blocks when there are few genes
+    while (threads > 32 && ceil_div(P, threads) < 2 * devinfo().sm_count) threads >>= 1;
+    auto kern = k_finalize_direct<TK1>;
+    PRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem_max));
+    kern<<<(unsigned)ceil_div(P, threads), threads, per_thread * threads, st>>>(
+        hits, stride, cnt, clsz, hsize, hs_ysum, ha, C, K1, table, N, P, out_full, out_marg);
+    PRB_LAUNCH_CHECK("k_finalize_direct");
+    return 0;
+}
+
+extern "C" int prb_finalize_direct(int32_t *hits, const int32_t *cnt, const int64_t *classsizes,
+                                   const int32_t *hsize, const int32_t *hs_ysum,
+                                   const int32_t *ha, int C, int K, const double *table,
+                                   int64_t N, int64_t P, double *out_full, double *out_marg,
+                                   prb_stream_t stream)
+{
+    if (P == 0) return 0;
+    PRB_REQUIRE(C >= 1 && K >= 2 && K <= PRB_MAX_CODES, "bad C or K");
+    PRB_REQUIRE(out_full != nullptr, "out_full is required");
+    const int K1 = K - 1;
+    const int64_t stride = (int64_t)C * K1 * K1;
+#define PRB_FD(T)                                                                              \
+    return launch_direct<T>(hits, stride, cnt, classsizes, hsize, hs_ysum, ha, C, K1, table, N, \
+                            P, out_full, out_marg, S(stream))
+    switch (K1) {
+        case 1: PRB_FD(1);
+        case 2: PRB_FD(2);
+        case 3: PRB_FD(3);
+        case 4: PRB_FD(4);
+        default: PRB_FD(0);
+    }
+#undef PRB_FD
 }

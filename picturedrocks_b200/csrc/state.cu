@@ -4,8 +4,8 @@
 // 2^shift, eliminate_zeros, sort_indices) and the y-packing of
 // SparseInformationSet.entropy (infoset.py:225-249).  Instead of a sparse
 // packed column the device keeps, per cell,
-//   bitmap  : 1 bit  "some selected column is non-zero here" (the master rows)
-//   state16 : uint16 (id of the cell's (y, master) state) * (K-1)
+//   state : uint8 / uint16, 0 = "every selected column is zero here" (not a master
+//           row), else 1 + id of the cell's (y, master) joint state
 // where ids are ORDER-PRESERVING w.r.t. the reference's packed id
 // (y most significant, then cols[0], ..., cols[m-1]) so that entropies can be
 // accumulated in the reference's ascending-bin order.
@@ -43,35 +43,29 @@ __global__ void k_scatter_or32(const uint32_t *__restrict__ packed,
 }
 
 // ---- direct single-column state -------------------------------------------
-// id = y*(K-1) + (x_j - 1); grid-stride over 32-cell words.
+// state = 1 + (x_j - 1)*C + y  (class id fastest: bank-friendly shared histograms);
+// hsize is indexed y*(K-1) + (x_j - 1) (the reference's bin order).
+template <typename ST>
 __global__ void __launch_bounds__(256)
 k_state_direct(const uint8_t *__restrict__ xj, const int32_t *__restrict__ y, int64_t N, int K1,
-               int n_hs, uint32_t *__restrict__ bitmap, uint16_t *__restrict__ state16,
-               int32_t *__restrict__ hsize, int use_smem_hist)
+               int C, ST *__restrict__ state, int32_t *__restrict__ hsize, int use_smem_hist)
 {
     extern __shared__ int sh_hist[];
+    const int n_hs = C * K1;
     if (use_smem_hist) {
         for (int i = threadIdx.x; i < n_hs; i += blockDim.x) sh_hist[i] = 0;
         __syncthreads();
     }
-    const int lane = threadIdx.x & 31;
-    const int64_t n_words = ceil_div(N, 32);
-    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t wd = warp0; wd < n_words; wd += n_warps) {
-        const int64_t cell = wd * 32 + lane;
-        const uint32_t a = cell < N ? xj[cell] : 0u;
-        const unsigned m = __ballot_sync(0xffffffffu, a != 0);
-        if (lane == 0) bitmap[wd] = m;
-        if (cell < N) {
-            uint32_t s = 0;
-            if (a) {
-                const int h = (y ? y[cell] : 0) * K1 + (int)a - 1;
-                s = (uint32_t)h * (uint32_t)K1;
-                atomicAdd(use_smem_hist ? sh_hist + h : hsize + h, 1);
-            }
-            state16[cell] = (uint16_t)s;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t cell = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; cell < N; cell += stride) {
+        const int a = xj[cell];
+        uint32_t s = 0;
+        if (a) {
+            const int yy = y ? y[cell] : 0;
+            s = 1u + (uint32_t)((a - 1) * C + yy);
+            atomicAdd(use_smem_hist ? sh_hist + yy * K1 + a - 1 : hsize + yy * K1 + a - 1, 1);
         }
+        state[cell] = (ST)s;
     }
     if (use_smem_hist) {
         __syncthreads();
@@ -98,7 +92,7 @@ __global__ void k_state_direct_sums(const int32_t *__restrict__ hsize, int C, in
         for (int yy = 0; yy < C; ++yy) s += hsize[yy * K1 + a];
         ha[a] = s;
     }
-    if (t == 0 && work_counter) *work_counter = 0;
+    (void)work_counter;
 }
 
 // ---- generic multi-column state through a presence table --------------------
@@ -181,32 +175,24 @@ k_table_rank(int32_t *__restrict__ table, int64_t n_keys, int C, int mbits,
     if (t == 0) {
         hs_begin[C] = base_s;
         *n_hs_out = base_s;
-        if (work_counter) *work_counter = 0;
+        (void)work_counter;
     }
 }
 
+template <typename ST>
 __global__ void __launch_bounds__(256)
 k_table_assign(const uint32_t *__restrict__ mpacked, const int32_t *__restrict__ y, int64_t N,
-               int mbits, int K1, const int32_t *__restrict__ table,
-               uint32_t *__restrict__ bitmap, uint16_t *__restrict__ state16)
+               int mbits, const int32_t *__restrict__ table, ST *__restrict__ state)
 {
-    const int lane = threadIdx.x & 31;
-    const int64_t n_words = ceil_div(N, 32);
-    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t wd = warp0; wd < n_words; wd += n_warps) {
-        const int64_t cell = wd * 32 + lane;
-        const uint32_t m = cell < N ? mpacked[cell] : 0u;
-        const unsigned bal = __ballot_sync(0xffffffffu, m != 0);
-        if (lane == 0) bitmap[wd] = bal;
-        if (cell < N) {
-            uint32_t s = 0;
-            if (m) {
-                const int64_t key = ((int64_t)(y ? y[cell] : 0) << mbits) | m;
-                s = (uint32_t)table[key] * (uint32_t)K1;
-            }
-            state16[cell] = (uint16_t)s;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t cell = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; cell < N; cell += stride) {
+        const uint32_t m = mpacked[cell];
+        uint32_t s = 0;
+        if (m) {
+            const int64_t key = ((int64_t)(y ? y[cell] : 0) << mbits) | m;
+            s = 1u + (uint32_t)table[key];
         }
+        state[cell] = (ST)s;
     }
 }
 
@@ -260,22 +246,28 @@ extern "C" int prb_scatter_gene_or32(const uint32_t *packed, const int64_t *indp
 }
 
 extern "C" int prb_state_direct(const uint8_t *xj, const int32_t *y, int64_t N, int C, int K,
-                                uint32_t *bitmap, uint16_t *state16, int32_t *hsize,
-                                int32_t *hs_begin, int32_t *hs_y, int32_t *hs_ysum, int32_t *ha,
-                                int32_t *work_counter, prb_stream_t stream)
+                                void *state, int state_bytes, int32_t *hsize, int32_t *hs_begin,
+                                int32_t *hs_y, int32_t *hs_ysum, int32_t *ha, prb_stream_t stream)
 {
     PRB_REQUIRE(N > 0 && N <= PRB_MAX_ROWS, "N out of range");
     PRB_REQUIRE(C >= 1 && K >= 2 && K <= PRB_MAX_CODES, "bad C or K");
     const int K1 = K - 1;
     const int64_t n_hs = (int64_t)C * K1;
-    PRB_REQUIRE(n_hs * K1 <= 65536, "C*(K-1)^2 exceeds the uint16 state range");
+    PRB_REQUIRE(n_hs * K1 <= 65536, "C*(K-1)^2 exceeds 65536 histogram bins");
+    PRB_REQUIRE(state_bytes == 2 || (state_bytes == 1 && n_hs + 1 <= 256), "state width too small");
     PRB_CUDA(cudaMemsetAsync(hsize, 0, sizeof(int32_t) * n_hs, S(stream)));
     const int use_smem = n_hs <= 8192;
-    k_state_direct<<<cell_grid(N, 256), 256, use_smem ? n_hs * 4 : 0, S(stream)>>>(
-        xj, y, N, K1, (int)n_hs, bitmap, state16, hsize, use_smem);
+    const int grid = cell_grid(N, 256);
+    const size_t sm = use_smem ? n_hs * 4 : 0;
+    if (state_bytes == 1)
+        k_state_direct<uint8_t><<<grid, 256, sm, S(stream)>>>(xj, y, N, K1, C, (uint8_t *)state,
+                                                              hsize, use_smem);
+    else
+        k_state_direct<uint16_t><<<grid, 256, sm, S(stream)>>>(xj, y, N, K1, C, (uint16_t *)state,
+                                                               hsize, use_smem);
     PRB_LAUNCH_CHECK("k_state_direct");
     k_state_direct_sums<<<1, 256, 0, S(stream)>>>(hsize, C, K1, hs_begin, hs_y, hs_ysum, ha,
-                                                  work_counter);
+                                                  nullptr);
     PRB_LAUNCH_CHECK("k_state_direct_sums");
     return 0;
 }
@@ -294,23 +286,34 @@ static int table_count(const uint32_t *mpacked, const int32_t *y, int64_t N, int
     return 0;
 }
 
-extern "C" int prb_state_table(const uint32_t *mpacked, const int32_t *y, int64_t N, int C, int K,
-                               int mbits, int32_t *table, uint32_t *bitmap, uint16_t *state16,
-                               int32_t *hsize, int32_t *hs_begin, int32_t *hs_y,
-                               int32_t *hs_ysum, int32_t *n_hs_out, int32_t *work_counter,
+extern "C" int prb_state_table(const uint32_t *mpacked, const int32_t *y, int64_t N, int C,
+                               int mbits, int32_t *table, int32_t *hsize, int32_t *hs_begin,
+                               int32_t *hs_y, int32_t *hs_ysum, int32_t *n_hs_out,
                                int64_t hsize_cap, prb_stream_t stream)
 {
     PRB_REQUIRE(N > 0 && N <= PRB_MAX_ROWS, "N out of range");
-    PRB_REQUIRE(C >= 1 && K >= 2 && K <= PRB_MAX_CODES, "bad C or K");
+    PRB_REQUIRE(C >= 1, "bad C");
     PRB_REQUIRE(mbits >= 1 && mbits <= 30, "master column needs 1..30 bits");
     const int64_t n_keys = (int64_t)C << mbits;
     PRB_REQUIRE(n_keys <= (int64_t(1) << 24), "joint state space too large for the presence table");
     if (table_count(mpacked, y, N, mbits, n_keys, table, 0, S(stream))) return 1;
     k_table_rank<<<1, 1024, 0, S(stream)>>>(table, n_keys, C, mbits, hsize, hs_begin, hs_y,
-                                            hs_ysum, n_hs_out, hsize_cap, work_counter);
+                                            hs_ysum, n_hs_out, hsize_cap, nullptr);
     PRB_LAUNCH_CHECK("k_table_rank");
-    k_table_assign<<<cell_grid(N, 256), 256, 0, S(stream)>>>(mpacked, y, N, mbits, K - 1, table,
-                                                             bitmap, state16);
+    return 0;
+}
+
+extern "C" int prb_state_assign(const uint32_t *mpacked, const int32_t *y, int64_t N, int mbits,
+                                const int32_t *table, void *state, int state_bytes,
+                                prb_stream_t stream)
+{
+    PRB_REQUIRE(state_bytes == 1 || state_bytes == 2, "state_bytes must be 1 or 2");
+    if (state_bytes == 1)
+        k_table_assign<uint8_t><<<cell_grid(N, 256), 256, 0, S(stream)>>>(mpacked, y, N, mbits,
+                                                                          table, (uint8_t *)state);
+    else
+        k_table_assign<uint16_t><<<cell_grid(N, 256), 256, 0, S(stream)>>>(
+            mpacked, y, N, mbits, table, (uint16_t *)state);
     PRB_LAUNCH_CHECK("k_table_assign");
     return 0;
 }

@@ -32,38 +32,73 @@ const DevInfo &devinfo()
 }
 
 constexpr int CTA_THREADS = 1024;
-constexpr int SLOT_WORDS = 64;  // per-team work slots at the front of smem
+constexpr int SLOT_WORDS = 64;  // per-team work slots (+ the tile-skip flag) at the front of smem
 
+// Shared-memory plan of one streaming launch.
+//   [slots 256 B][remap u16 x bins][per-cell state of one cell TILE][teams x hist int32]
+// The per-cell state (0 = not a master row, else joint-state id + 1; uint8 when the ids
+// fit, else uint16) of a tile of cells is staged in shared memory, so the probe of every
+// stored entry is ONE shared load and hits need no global gather.  Cells are tiled when N
+// does not fit; rows are ascending inside a gene, so a gene's entries of one tile are a
+// contiguous sub-range found once by binary search (prb_tile_ptrs).
 struct StreamPlan {
     int teams;
     int team_shift;  // log2(threads per team)
-    int64_t bm_words;
-    int64_t bm_words_pad;
+    int state_bytes;
+    int n_bins;
     int bins_pad;
-    bool bm_smem;
+    int64_t remap_bytes;
+    int64_t tile_cells;
+    int64_t tile_bytes;
+    int n_tiles;
     int64_t smem_bytes;
 };
 
-static int plan_stream(int64_t N, int64_t n_bins, int use_bitmap, StreamPlan *p)
+static int plan_stream(int64_t N, int64_t n_states, int K1, StreamPlan *p)
 {
     const int64_t smem_max = devinfo().smem_optin;
-    p->bm_words = use_bitmap ? ceil_div(N, 32) : 0;
-    p->bm_words_pad = (p->bm_words + 3) & ~int64_t(3);
+    const int64_t n_bins = n_states * K1;
+    if (n_bins <= 0 || n_bins > 65536) return fail("prb_stream", "bin count outside (0, 65536]");
+    p->n_bins = (int)n_bins;
+    p->state_bytes = (n_states + 1 <= 256) ? 1 : 2;
     p->bins_pad = (int)((n_bins + 3) & ~int64_t(3));
-    if (p->bins_pad < 4) p->bins_pad = 4;
+    p->remap_bytes = ((int64_t)p->bins_pad * 2 + 15) & ~int64_t(15);
     const int64_t hist_bytes = (int64_t)p->bins_pad * 4;
-    const int64_t fixed = SLOT_WORDS * 4;
-    int64_t avail = smem_max - fixed - p->bm_words_pad * 4;
-    p->bm_smem = use_bitmap && avail >= hist_bytes;
-    if (!p->bm_smem) avail = smem_max - fixed;
-    if (avail < hist_bytes) return fail("prb_stream", "joint histogram does not fit in shared memory");
-    int teams = 1;
-    while (teams < 32 && (int64_t)(teams * 2) * hist_bytes <= avail) teams *= 2;
+    const int64_t fixed = SLOT_WORDS * 4 + p->remap_bytes;
+    const int64_t full = ((N * p->state_bytes + 127) & ~int64_t(127));
+    const int64_t want = full < 128 * 1024 ? full : 128 * 1024;
+    // warp-sized teams need no named barriers; larger teams use barrier ids 1..8
+    static const int cand[] = {32, 8, 4, 2, 1};
+    int teams = 0;
+    int64_t avail = 0;
+    for (int c : cand) {
+        avail = smem_max - fixed - c * hist_bytes;
+        if (avail >= want) {
+            teams = c;
+            break;
+        }
+    }
+    if (!teams) {
+        avail = smem_max - fixed - hist_bytes;
+        if (avail < 4096) return fail("prb_stream", "joint histogram does not fit in shared memory");
+        teams = 1;
+    }
     p->teams = teams;
-    int shift = 10;  // 1024 threads
+    int shift = 10;
     for (int t = teams; t > 1; t >>= 1) --shift;
     p->team_shift = shift;
-    p->smem_bytes = fixed + (p->bm_smem ? p->bm_words_pad * 4 : 0) + (int64_t)teams * hist_bytes;
+    int64_t tile = (avail / p->state_bytes) & ~int64_t(127);
+    if (tile >= N) {
+        p->tile_cells = N;
+        p->n_tiles = 1;
+    } else {
+        p->n_tiles = (int)ceil_div(N, tile);
+        // equalise the tiles
+        p->tile_cells = (ceil_div(N, p->n_tiles) + 127) & ~int64_t(127);
+        p->n_tiles = (int)ceil_div(N, p->tile_cells);
+    }
+    p->tile_bytes = (p->tile_cells * p->state_bytes + 15) & ~int64_t(15);
+    p->smem_bytes = fixed + p->tile_bytes + (int64_t)teams * hist_bytes;
     return 0;
 }
 
@@ -83,147 +118,166 @@ __device__ __forceinline__ void team_sync(int team, int team_shift)
     else if (team_shift == 10)
         __syncthreads();
     else
-        asm volatile("bar.sync %0, %1;" ::"r"(team), "r"(1 << team_shift) : "memory");
+        asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(1 << team_shift) : "memory");
 }
 
-template <bool FILTER>
-__device__ __forceinline__ void count_one(uint32_t w, const uint32_t *__restrict__ bmp,
-                                          const uint16_t *__restrict__ state16, int *hist)
+template <typename ST>
+__device__ __forceinline__ void count_one(uint32_t w, const ST *__restrict__ st, int n_states,
+                                          int *hist)
 {
-    bool hit = true;
-    if (FILTER) {
-        const uint32_t bits = bmp[(w & ROW_MASK) >> 5];
-        hit = (bits >> (w & 31u)) & 1u;
-    }
-    if (hit) {
-        const uint32_t base = state16 ? (uint32_t)__ldg(state16 + (w & ROW_MASK)) : 0u;
-        atomicAdd(hist + base + (w >> 24) - 1u, 1);
-    }
+    const uint32_t s = st[w & ROW_MASK];
+    if (s) atomicAdd(hist + (s - 1u) + (uint32_t)n_states * ((w >> 24) - 1u), 1);
 }
 
-template <bool FILTER, bool BM_SMEM>
+// 8 stored entries: all state probes (shared loads) are issued before the first shared
+// atomic so their latencies overlap.
+template <typename ST>
+__device__ __forceinline__ void count8(const uint4 qa, const uint4 qb, const ST *__restrict__ st,
+                                       int n_states, int *hist)
+{
+    const uint32_t w[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+    uint32_t s[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = st[w[i] & ROW_MASK];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        if (s[i]) atomicAdd(hist + (s[i] - 1u) + (uint32_t)n_states * ((w[i] >> 24) - 1u), 1);
+}
+
+template <typename ST>
 __global__ void __launch_bounds__(CTA_THREADS, 1)
-k_stream(const uint32_t *__restrict__ packed, const int64_t *__restrict__ indptr,
-         const int32_t *__restrict__ range_gene, int64_t n_ranges, int64_t range_len,
-         int64_t nnz, const uint32_t *__restrict__ bitmap, int64_t bm_words,
-         int64_t bm_words_pad, const uint16_t *__restrict__ state16, int n_bins, int bins_pad,
-         int32_t *__restrict__ hits, int *work_counter, int team_shift)
+k_stream(const uint32_t *__restrict__ packed, const int64_t *__restrict__ tp, int64_t P,
+         int n_tiles, int64_t tile_cells, int64_t N, const ST *__restrict__ state, int n_states,
+         int K1, int direct_C, int n_bins, int bins_pad, int64_t remap_bytes, int64_t tile_bytes,
+         int32_t *__restrict__ hits, int *counters, int genes_per_item, int team_shift)
 {
-    extern __shared__ __align__(16) uint32_t smem[];
-    int *slots = (int *)smem;
-    uint32_t *bm = smem + SLOT_WORDS;
-    int *hist_base = (int *)(bm + (BM_SMEM ? bm_words_pad : 0));
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int *slots = (int *)smem_raw;
+    uint16_t *remap = (uint16_t *)(smem_raw + SLOT_WORDS * 4);
+    ST *tile_state = (ST *)(smem_raw + SLOT_WORDS * 4 + remap_bytes);
+    int *hist_base = (int *)(smem_raw + SLOT_WORDS * 4 + remap_bytes + tile_bytes);
     const int tid = threadIdx.x;
     const int team_threads = 1 << team_shift;
     const int team = tid >> team_shift;
     const int tl = tid & (team_threads - 1);
     int *hist = hist_base + (int64_t)team * bins_pad;
 
-    if (FILTER && BM_SMEM) {
-        // bitmap: global -> shared, 128-bit copies (bm_words_pad is a multiple of 4;
-        // the global buffer is allocated padded).
-        const uint4 *src = (const uint4 *)bitmap;
-        uint4 *dst = (uint4 *)bm;
-        for (int64_t i = tid; i < (bm_words_pad >> 2); i += CTA_THREADS) dst[i] = __ldg(src + i);
+    // shared bin (state + n_states*(code-1): class id fastest, so the popular low codes of
+    // different classes fall in different banks) -> global bin (state-major, code fastest)
+    for (int b = tid; b < n_bins; b += CTA_THREADS) {
+        const int v = b / n_states, s = b - v * n_states;
+        const int h = direct_C ? (s % direct_C) * K1 + s / direct_C : s;
+        remap[b] = (uint16_t)(h * K1 + v);
     }
     for (int i = tl; i < bins_pad; i += team_threads) hist[i] = 0;
-    __syncthreads();
-    const uint32_t *bmp = BM_SMEM ? bm : bitmap;
-    (void)bm_words;
+    const int n_items = (int)((P + genes_per_item - 1) / genes_per_item);
 
-    for (;;) {
-        int r;
-        if (team_shift == 5) {
-            r = 0;
-            if (tl == 0) r = atomicAdd(work_counter, 1);
-            r = __shfl_sync(0xffffffffu, r, 0);
-        } else {
-            if (tl == 0) slots[team] = atomicAdd(work_counter, 1);
-            team_sync(team, team_shift);
-            r = slots[team];
+    for (int tt = 0; tt < n_tiles; ++tt) {
+        const int tile = (int)((blockIdx.x + tt) % (unsigned)n_tiles);
+        __syncthreads();  // every team has left the previous tile
+        if (tid == 0) slots[SLOT_WORDS - 1] = *(volatile int *)(counters + tile) < n_items;
+        __syncthreads();
+        if (!slots[SLOT_WORDS - 1]) continue;  // tile already drained by other CTAs
+        const int64_t cell0 = (int64_t)tile * tile_cells;
+        const int64_t ncell = min(tile_cells, N - cell0);
+        {
+            // tile state: global -> shared, 128-bit copies (buffers are padded to 16 B)
+            const int64_t nvec = (ncell * (int64_t)sizeof(ST) + 15) >> 4;
+            const uint4 *src = (const uint4 *)(state + cell0);
+            uint4 *dst = (uint4 *)tile_state;
+            for (int64_t i = tid; i < nvec; i += CTA_THREADS) dst[i] = __ldg(src + i);
         }
-        if (r >= n_ranges) break;
-        int64_t pos = (int64_t)r * range_len;
-        const int64_t end = min(pos + range_len, nnz);
-        int g = range_gene[r];
-        while (pos < end) {
-            int64_t gend = __ldg(indptr + g + 1);
-            while (gend <= pos) {
-                ++g;
-                gend = __ldg(indptr + g + 1);
+        __syncthreads();
+        const ST *st = tile_state - cell0;  // indexed by absolute row id
+        const int64_t *tp0 = tp + (int64_t)tile * P, *tp1 = tp0 + P;
+        for (;;) {
+            int item;
+            if (team_shift == 5) {
+                item = 0;
+                if (tl == 0) item = atomicAdd(counters + tile, 1);
+                item = __shfl_sync(0xffffffffu, item, 0);
+            } else {
+                if (tl == 0) slots[team] = atomicAdd(counters + tile, 1);
+                team_sync(team, team_shift);
+                item = slots[team];
             }
-            const int64_t seg_end = min(gend, end);
-            // head (unaligned prefix, <= 3 words)
-            const int64_t a0 = min((pos + 3) & ~int64_t(3), seg_end);
-            if (pos + tl < a0) count_one<FILTER>(__ldg(packed + pos + tl), bmp, state16, hist);
-            // body: 128-bit loads, 4 in flight per thread
-            const int64_t nvec = (seg_end - a0) >> 2;
-            const uint4 *vp = (const uint4 *)(packed + a0);
-            int64_t v = tl;
-            for (; v + 3 * (int64_t)team_threads < nvec; v += 4 * (int64_t)team_threads) {
-                const uint4 q0 = ld_stream(vp + v);
-                const uint4 q1 = ld_stream(vp + v + team_threads);
-                const uint4 q2 = ld_stream(vp + v + 2 * team_threads);
-                const uint4 q3 = ld_stream(vp + v + 3 * team_threads);
-                count_one<FILTER>(q0.x, bmp, state16, hist);
-                count_one<FILTER>(q0.y, bmp, state16, hist);
-                count_one<FILTER>(q0.z, bmp, state16, hist);
-                count_one<FILTER>(q0.w, bmp, state16, hist);
-                count_one<FILTER>(q1.x, bmp, state16, hist);
-                count_one<FILTER>(q1.y, bmp, state16, hist);
-                count_one<FILTER>(q1.z, bmp, state16, hist);
-                count_one<FILTER>(q1.w, bmp, state16, hist);
-                count_one<FILTER>(q2.x, bmp, state16, hist);
-                count_one<FILTER>(q2.y, bmp, state16, hist);
-                count_one<FILTER>(q2.z, bmp, state16, hist);
-                count_one<FILTER>(q2.w, bmp, state16, hist);
-                count_one<FILTER>(q3.x, bmp, state16, hist);
-                count_one<FILTER>(q3.y, bmp, state16, hist);
-                count_one<FILTER>(q3.z, bmp, state16, hist);
-                count_one<FILTER>(q3.w, bmp, state16, hist);
-            }
-            for (; v < nvec; v += team_threads) {
-                const uint4 q = ld_stream(vp + v);
-                count_one<FILTER>(q.x, bmp, state16, hist);
-                count_one<FILTER>(q.y, bmp, state16, hist);
-                count_one<FILTER>(q.z, bmp, state16, hist);
-                count_one<FILTER>(q.w, bmp, state16, hist);
-            }
-            // tail (<= 3 words)
-            const int64_t a1 = a0 + (nvec << 2);
-            if (a1 + tl < seg_end) count_one<FILTER>(__ldg(packed + a1 + tl), bmp, state16, hist);
-            team_sync(team, team_shift);
-            // flush this gene segment's non-empty bins
-            int32_t *out = hits + (int64_t)g * n_bins;
-            for (int b = tl; b < n_bins; b += team_threads) {
-                const int c = hist[b];
-                if (c) {
-                    atomicAdd(out + b, c);
-                    hist[b] = 0;
+            if (item >= n_items) break;
+            const int64_t g_end = min((int64_t)(item + 1) * genes_per_item, P);
+            for (int64_t g = (int64_t)item * genes_per_item; g < g_end; ++g) {
+                const int64_t pos = __ldg(tp0 + g), seg_end = __ldg(tp1 + g);
+                if (pos >= seg_end) continue;
+                // head (unaligned prefix, <= 3 words)
+                const int64_t a0 = min((pos + 3) & ~int64_t(3), seg_end);
+                if (pos + tl < a0) count_one<ST>(__ldg(packed + pos + tl), st, n_states, hist);
+                // body: 128-bit loads, 4 in flight per thread
+                const int64_t nvec = (seg_end - a0) >> 2;
+                const uint4 *vp = (const uint4 *)(packed + a0);
+                int64_t v = tl;
+                for (; v + 3 * (int64_t)team_threads < nvec; v += 4 * (int64_t)team_threads) {
+                    const uint4 q0 = ld_stream(vp + v);
+                    const uint4 q1 = ld_stream(vp + v + team_threads);
+                    const uint4 q2 = ld_stream(vp + v + 2 * team_threads);
+                    const uint4 q3 = ld_stream(vp + v + 3 * team_threads);
+                    count8<ST>(q0, q1, st, n_states, hist);
+                    count8<ST>(q2, q3, st, n_states, hist);
                 }
+                for (; v + (int64_t)team_threads < nvec; v += 2 * (int64_t)team_threads) {
+                    const uint4 q0 = ld_stream(vp + v);
+                    const uint4 q1 = ld_stream(vp + v + team_threads);
+                    count8<ST>(q0, q1, st, n_states, hist);
+                }
+                for (; v < nvec; v += team_threads) {
+                    const uint4 q = ld_stream(vp + v);
+                    count_one<ST>(q.x, st, n_states, hist);
+                    count_one<ST>(q.y, st, n_states, hist);
+                    count_one<ST>(q.z, st, n_states, hist);
+                    count_one<ST>(q.w, st, n_states, hist);
+                }
+                // tail (<= 3 words)
+                const int64_t a1 = a0 + (nvec << 2);
+                if (a1 + tl < seg_end) count_one<ST>(__ldg(packed + a1 + tl), st, n_states, hist);
+                team_sync(team, team_shift);
+                // flush this gene segment's non-empty bins
+                int32_t *out = hits + g * n_bins;
+                for (int b = tl; b < n_bins; b += team_threads) {
+                    const int c = hist[b];
+                    if (c) {
+                        atomicAdd(out + remap[b], c);
+                        hist[b] = 0;
+                    }
+                }
+                team_sync(team, team_shift);
             }
-            team_sync(team, team_shift);
-            pos = seg_end;
         }
     }
 }
 
-__global__ void k_range_genes(const int64_t *__restrict__ indptr, int64_t P, int64_t range_len,
-                              int64_t n_ranges, int32_t *__restrict__ range_gene)
+// tp[t][g] = first position of gene g whose row id is >= t * tile_cells
+__global__ void k_tile_ptrs(const uint32_t *__restrict__ packed,
+                            const int64_t *__restrict__ indptr, int64_t P, int64_t tile_cells,
+                            int n_tiles, int64_t *__restrict__ tp)
 {
-    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (r >= n_ranges) return;
-    const int64_t pos = r * range_len;
-    // largest g in [0, P) with indptr[g] <= pos < indptr[g+1]  (upper_bound - 1)
-    int64_t lo = 0, hi = P;  // search over indptr[1..P]
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= P * (int64_t)(n_tiles + 1)) return;
+    const int64_t t = i / P, g = i - t * P;
+    int64_t lo = indptr[g], hi = indptr[g + 1];
+    if (t == 0) {
+        tp[i] = lo;
+        return;
+    }
+    if (t == n_tiles) {
+        tp[i] = hi;
+        return;
+    }
+    const uint32_t row0 = (uint32_t)(t * tile_cells);
     while (lo < hi) {
         const int64_t mid = (lo + hi) >> 1;
-        if (indptr[mid + 1] <= pos)
+        if ((packed[mid] & ROW_MASK) < row0)
             lo = mid + 1;
         else
             hi = mid;
     }
-    range_gene[r] = (int32_t)min(lo, P - 1);
+    tp[i] = lo;
 }
 
 __global__ void k_pack(const int32_t *__restrict__ rows, const uint8_t *__restrict__ codes,
@@ -346,51 +400,58 @@ extern "C" int prb_dense_fill_csc(const uint8_t *codes, int64_t N, int64_t P, in
     return 0;
 }
 
-extern "C" int prb_range_genes(const int64_t *indptr, int64_t P, int64_t nnz, int64_t range_len,
-                               int64_t n_ranges, int32_t *range_gene, prb_stream_t stream)
-{
-    (void)nnz;
-    if (n_ranges == 0) return 0;
-    PRB_REQUIRE(P > 0 && range_len > 0, "bad arguments");
-    k_range_genes<<<(unsigned)ceil_div(n_ranges, 256), 256, 0, S(stream)>>>(indptr, P, range_len,
-                                                                            n_ranges, range_gene);
-    PRB_LAUNCH_CHECK("k_range_genes");
-    return 0;
-}
-
-extern "C" int prb_stream_smem_bytes(int64_t N, int64_t n_bins, int use_bitmap,
-                                     int *teams_per_cta, int64_t *smem_bytes)
+extern "C" int prb_stream_plan(int64_t N, int64_t n_states, int K1, int64_t *tile_cells,
+                               int *n_tiles, int *teams_per_cta, int *state_bytes,
+                               int64_t *smem_bytes)
 {
     StreamPlan p;
-    if (plan_stream(N, n_bins, use_bitmap, &p)) return 1;
+    PRB_REQUIRE(N > 0 && N <= PRB_MAX_ROWS, "N out of range for the packed row field");
+    if (plan_stream(N, n_states, K1, &p)) return 1;
+    if (tile_cells) *tile_cells = p.tile_cells;
+    if (n_tiles) *n_tiles = p.n_tiles;
     if (teams_per_cta) *teams_per_cta = p.teams;
+    if (state_bytes) *state_bytes = p.state_bytes;
     if (smem_bytes) *smem_bytes = p.smem_bytes;
     return 0;
 }
 
-extern "C" int prb_stream_hits(const uint32_t *packed, const int64_t *indptr,
-                               const int32_t *range_gene, int64_t n_ranges, int64_t range_len,
-                               int64_t nnz, const uint32_t *bitmap, const uint16_t *state16,
-                               int64_t N, int64_t n_bins, int32_t *hits, int32_t *work_counter,
+extern "C" int prb_tile_ptrs(const uint32_t *packed, const int64_t *indptr, int64_t P,
+                             int64_t tile_cells, int n_tiles, int64_t *tp, prb_stream_t stream)
+{
+    PRB_REQUIRE(P > 0 && n_tiles >= 1 && tile_cells > 0, "bad arguments");
+    const int64_t n = P * (int64_t)(n_tiles + 1);
+    k_tile_ptrs<<<(unsigned)ceil_div(n, 256), 256, 0, S(stream)>>>(packed, indptr, P, tile_cells,
+                                                                  n_tiles, tp);
+    PRB_LAUNCH_CHECK("k_tile_ptrs");
+    return 0;
+}
+
+extern "C" int prb_stream_hits(const uint32_t *packed, const int64_t *tp, int64_t P, int64_t nnz,
+                               const void *state, int64_t N, int64_t n_states, int K1,
+                               int direct_C, int32_t *hits, int32_t *counters,
                                prb_stream_t stream)
 {
-    if (n_ranges == 0 || nnz == 0) return 0;
+    if (P == 0 || nnz == 0) return 0;
     PRB_REQUIRE(N > 0 && N <= PRB_MAX_ROWS, "N out of range for the packed row field");
-    PRB_REQUIRE(n_bins > 0 && n_bins < (int64_t(1) << 30), "bad bin count");
-    PRB_REQUIRE(n_ranges < (int64_t(1) << 31) - 65536, "too many ranges");
+    PRB_REQUIRE(K1 >= 1 && K1 < PRB_MAX_CODES, "bad K");
+    PRB_REQUIRE(direct_C == 0 || n_states % direct_C == 0, "direct layout needs n_states = C*(K-1)");
     StreamPlan p;
-    if (plan_stream(N, n_bins, bitmap != nullptr, &p)) return 1;
-    const int grid = (int)hmin(devinfo().sm_count, ceil_div(n_ranges, p.teams));
-    auto launch = [&](auto kern) -> int {
+    if (plan_stream(N, n_states, K1, &p)) return 1;
+    PRB_CUDA(cudaMemsetAsync(counters, 0, sizeof(int32_t) * p.n_tiles, S(stream)));
+    // ~16 work items per team and tile
+    const int64_t teams_per_tile = hmax(1, (int64_t)devinfo().sm_count * p.teams / p.n_tiles);
+    const int gpi = (int)hmin(64, hmax(1, P / (teams_per_tile * 16)));
+    const int64_t n_items = ceil_div(P, gpi) * p.n_tiles;
+    const int grid = (int)hmax(1, hmin(devinfo().sm_count, ceil_div(n_items, p.teams)));
+    auto launch = [&](auto kern, auto *st) -> int {
         PRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)p.smem_bytes));
         kern<<<grid, CTA_THREADS, p.smem_bytes, S(stream)>>>(
-            packed, indptr, range_gene, n_ranges, range_len, nnz, bitmap, p.bm_words,
-            p.bm_words_pad, state16, (int)n_bins, p.bins_pad, hits, work_counter, p.team_shift);
+            packed, tp, P, p.n_tiles, p.tile_cells, N, st, (int)n_states, K1, direct_C, p.n_bins,
+            p.bins_pad, p.remap_bytes, p.tile_bytes, hits, counters, gpi, p.team_shift);
         PRB_LAUNCH_CHECK("k_stream");
         return 0;
     };
-    if (bitmap == nullptr) return launch(k_stream<false, false>);
-    if (p.bm_smem) return launch(k_stream<true, true>);
-    return launch(k_stream<true, false>);
+    if (p.state_bytes == 1) return launch(k_stream<uint8_t>, (const uint8_t *)state);
+    return launch(k_stream<uint16_t>, (const uint16_t *)state);
 }

@@ -58,22 +58,14 @@ class Engine:
         smem = ctypes.c_int()
         nat.call("prb_device_info", ctypes.byref(sm), ctypes.byref(smem))
         self.sm_count, self.smem_optin = sm.value, smem.value
-        # work partition of the nnz stream
-        target = self.nnz // (self.sm_count * 32 * 4)
-        self.range_len = int(min(32768, max(512, -(-target // 512) * 512)))
-        self.n_ranges = -(-self.nnz // self.range_len)
-        self.range_gene = torch.zeros(max(self.n_ranges, 1), dtype=torch.int32, device=self.device)
-        nat.call("prb_range_genes", nat.ptr(indptr), self.P, self.nnz, self.range_len,
-                 self.n_ranges, nat.ptr(self.range_gene), nat.stream())
         # fp64 term table, built on the host (glibc log2), resident in HBM
         tt = np.empty(self.N + 1, dtype=np.float64)
         nat.call("prb_term_table", self.N, tt.ctypes.data)
         self.term = torch.from_numpy(tt).to(self.device)
         # per-cell state workspaces
         dev = self.device
-        bm_words = ((self.N + 31) // 32 + 3) // 4 * 4
-        self.bitmap = torch.zeros(bm_words, dtype=torch.int32, device=dev)
-        self.state16 = torch.zeros(self.N, dtype=torch.int16, device=dev)
+        # per-cell joint state (uint8 or uint16 view), padded for 128-bit tile copies
+        self.state_buf = torch.zeros(2 * self.N + 64, dtype=torch.uint8, device=dev)
         self.xj = torch.zeros(self.N, dtype=torch.uint8, device=dev)
         self.mpacked = None
         self.hsize = torch.zeros(_I16_MAX_BINS, dtype=torch.int32, device=dev)
@@ -82,7 +74,9 @@ class Engine:
         self.hs_ysum = torch.zeros(257, dtype=torch.int32, device=dev)
         self.ha = torch.zeros(256, dtype=torch.int32, device=dev)
         self.n_hs_dev = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.work_counter = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.counters = torch.zeros(8192, dtype=torch.int32, device=dev)
+        self._plans = {}
+        self._tps = {}
         self.gene_ptr = torch.zeros(1, dtype=torch.int32, device=dev)
         self._hits = None
         self._table = None
@@ -96,19 +90,50 @@ class Engine:
         self.cnt_x = self._count_table(None, 1)
 
     # ------------------------------------------------------------------ tables
+    def _plan(self, n_states):
+        """(tile_cells, n_tiles, teams, state_bytes) of a streaming launch with n_states states."""
+        pl = self._plans.get(n_states)
+        if pl is None:
+            tile, nt, teams, sb, smem = (ctypes.c_int64(), ctypes.c_int(), ctypes.c_int(),
+                                         ctypes.c_int(), ctypes.c_int64())
+            nat.call("prb_stream_plan", self.N, n_states, self.K1, ctypes.byref(tile),
+                     ctypes.byref(nt), ctypes.byref(teams), ctypes.byref(sb), ctypes.byref(smem))
+            pl = (tile.value, nt.value, teams.value, sb.value)
+            if nt.value > self.counters.numel():
+                raise NotImplementedError("too many cell tiles")
+            self._plans[n_states] = pl
+        return pl
+
+    def _tile_ptrs(self, tile_cells, n_tiles):
+        key = (tile_cells, n_tiles)
+        tp = self._tps.get(key)
+        if tp is None:
+            tp = torch.empty((n_tiles + 1) * max(self.P, 1), dtype=torch.int64, device=self.device)
+            if self.P:
+                nat.call("prb_tile_ptrs", nat.ptr(self.packed), nat.ptr(self.indptr), self.P,
+                         tile_cells, n_tiles, nat.ptr(tp), nat.stream())
+            self._tps[key] = tp
+        return tp
+
+    def _store_state(self, values, sb):
+        """values: int32 device tensor [N] of state ids + 1 -> state_buf as uint8/uint16."""
+        if sb == 1:
+            self.state_buf[: self.N] = values.to(torch.uint8)
+        else:
+            self.state_buf[: 2 * self.N] = values.to(torch.int16).view(torch.uint8)
+
     def _count_table(self, y, C):
-        """cnt[g][c][v-1] = #cells of class c with code v in gene g (one streaming pass)."""
+        """cnt[g][c][v-1] = #cells of class c with code v in gene g (one streaming pass in
+        which every cell is a "master row" whose state is its class)."""
         if C * self.K1 > _I16_MAX_BINS:
-            raise NotImplementedError("classes x codes exceeds the uint16 state range")
+            raise NotImplementedError("classes x codes exceeds 65536 histogram bins")
         cnt = torch.zeros(max(self.P * C * self.K1, 1), dtype=torch.int32, device=self.device)
-        state = None
-        if y is not None:
-            state = (y * self.K1).to(torch.int16)  # bit pattern of uint16
-        self.work_counter.zero_()
-        nat.call("prb_stream_hits", nat.ptr(self.packed), nat.ptr(self.indptr),
-                 nat.ptr(self.range_gene), self.n_ranges, self.range_len, self.nnz, None,
-                 nat.ptr(state), self.N, C * self.K1, nat.ptr(cnt), nat.ptr(self.work_counter),
-                 nat.stream())
+        sb = self._plan(C)[3]
+        if y is None:
+            self._store_state(torch.ones(self.N, dtype=torch.int32, device=self.device), sb)
+        else:
+            self._store_state(y + 1, sb)
+        self._stream(C, 0, cnt)
         return cnt
 
     def set_y(self, y):
@@ -132,25 +157,33 @@ class Engine:
             self._hits = torch.zeros(need, dtype=torch.int32, device=self.device)
         return self._hits
 
-    def _stream(self, n_bins, hits):
+    def _stream(self, n_states, direct_C, hits):
         ev = getattr(self, "profile_events", None)
         if ev is not None:
             e0 = torch.cuda.Event(enable_timing=True)
             e1 = torch.cuda.Event(enable_timing=True)
             e0.record()
-            self._stream_launch(n_bins, hits)
+            self._stream_launch(n_states, direct_C, hits)
             e1.record()
             ev.append((e0, e1))
         else:
-            self._stream_launch(n_bins, hits)
+            self._stream_launch(n_states, direct_C, hits)
 
-    def _stream_launch(self, n_bins, hits):
-        nat.call("prb_stream_hits", nat.ptr(self.packed), nat.ptr(self.indptr),
-                 nat.ptr(self.range_gene), self.n_ranges, self.range_len, self.nnz,
-                 nat.ptr(self.bitmap), nat.ptr(self.state16), self.N, n_bins, nat.ptr(hits),
-                 nat.ptr(self.work_counter), nat.stream())
+    def _stream_launch(self, n_states, direct_C, hits):
+        tile, nt, _, _ = self._plan(n_states)
+        tp = self._tile_ptrs(tile, nt)
+        nat.call("prb_stream_hits", nat.ptr(self.packed), nat.ptr(tp), self.P, self.nnz,
+                 nat.ptr(self.state_buf), self.N, n_states, self.K1, direct_C, nat.ptr(hits),
+                 nat.ptr(self.counters), nat.stream())
 
     def _finalize(self, hits, cnt, clsz, C, n_hs_cap, n_hs_ptr, out_full, out_marg, direct):
+        if direct or hits is None:
+            # single-gene layout (or no master column at all): one thread per gene
+            nat.call("prb_finalize_direct", nat.ptr(hits), nat.ptr(cnt), nat.ptr(clsz),
+                     nat.ptr(self.hsize), nat.ptr(self.hs_ysum), nat.ptr(self.ha), C, self.K,
+                     nat.ptr(self.term), self.N, self.P, nat.ptr(out_full), nat.ptr(out_marg),
+                     nat.stream())
+            return
         nat.call("prb_finalize", nat.ptr(hits), nat.ptr(cnt), nat.ptr(clsz), nat.ptr(self.hs_begin),
                  nat.ptr(self.hs_y), nat.ptr(self.hsize), nat.ptr(self.hs_ysum),
                  nat.ptr(self.ha) if direct else None, nat.ptr(n_hs_ptr), n_hs_cap, C, self.K,
@@ -180,14 +213,14 @@ class Engine:
         n_hs = C * self.K1
         n_bins = n_hs * self.K1
         if n_bins > _I16_MAX_BINS:
-            raise NotImplementedError("C*(K-1)^2 exceeds the uint16 state range")
+            raise NotImplementedError("C*(K-1)^2 exceeds 65536 histogram bins")
         self.scatter_selected_gene()
+        sb = self._plan(n_hs)[3]
         nat.call("prb_state_direct", nat.ptr(self.xj), nat.ptr(y), self.N, C, self.K,
-                 nat.ptr(self.bitmap), nat.ptr(self.state16), nat.ptr(self.hsize),
-                 nat.ptr(self.hs_begin), nat.ptr(self.hs_y), nat.ptr(self.hs_ysum),
-                 nat.ptr(self.ha), nat.ptr(self.work_counter), nat.stream())
+                 nat.ptr(self.state_buf), sb, nat.ptr(self.hsize), nat.ptr(self.hs_begin),
+                 nat.ptr(self.hs_y), nat.ptr(self.hs_ysum), nat.ptr(self.ha), nat.stream())
         hits = self.hits_buffer(n_bins)
-        self._stream(n_bins, hits)
+        self._stream(n_hs, C, hits)
         self._finalize(hits, cnt, clsz, C, n_hs, None, out_full, out_marg, True)
 
     def _build_mpacked(self, cols):
@@ -246,21 +279,22 @@ class Engine:
             mbits = self._build_mpacked(cols)
             n_keys = C << mbits
             table = self._table_scratch(n_keys)
-            nat.call("prb_state_table", nat.ptr(self.mpacked), nat.ptr(y), self.N, C, self.K,
-                     mbits, nat.ptr(table), nat.ptr(self.bitmap), nat.ptr(self.state16),
-                     nat.ptr(self.hsize), nat.ptr(self.hs_begin), nat.ptr(self.hs_y),
-                     nat.ptr(self.hs_ysum), nat.ptr(self.n_hs_dev), nat.ptr(self.work_counter),
+            nat.call("prb_state_table", nat.ptr(self.mpacked), nat.ptr(y), self.N, C, mbits,
+                     nat.ptr(table), nat.ptr(self.hsize), nat.ptr(self.hs_begin),
+                     nat.ptr(self.hs_y), nat.ptr(self.hs_ysum), nat.ptr(self.n_hs_dev),
                      self.hsize.numel(), nat.stream())
             n_hs = int(self.n_hs_dev.item())
             if n_hs * self.K1 > _I16_MAX_BINS:
                 raise NotImplementedError(
-                    "%d joint states x %d codes exceeds the uint16 state range" % (n_hs, self.K1))
+                    "%d joint states x %d codes exceeds 65536 histogram bins" % (n_hs, self.K1))
             if n_hs == 0:
                 self._finalize(None, cnt, clsz, C, 0, None, out, None, False)
             else:
-                n_bins = n_hs * self.K1
-                hits = self.hits_buffer(n_bins)
-                self._stream(n_bins, hits)
+                sb = self._plan(n_hs)[3]
+                nat.call("prb_state_assign", nat.ptr(self.mpacked), nat.ptr(y), self.N, mbits,
+                         nat.ptr(table), nat.ptr(self.state_buf), sb, nat.stream())
+                hits = self.hits_buffer(n_hs * self.K1)
+                self._stream(n_hs, 0, hits)
                 self._finalize(hits, cnt, clsz, C, n_hs, None, out, None, False)
         return out
 

@@ -67,7 +67,9 @@ class DiscretisedSpec:
 
     @property
     def mean_q24(self):
-        return int(round(self.mean_density * (1 << 24)))
+        # E[class multiplier] * E[u^8-law + floor] ~= 1.27: normalise so that the overall
+        # fraction of non-zero codes comes out at `mean_density`
+        return int(round(self.mean_density / 1.27 * (1 << 24)))
 
     def cum_table(self):
         """uint32[4][K-2]: 16-bit cumulative thresholds of the geometric code law."""
