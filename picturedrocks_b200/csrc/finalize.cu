@@ -186,6 +186,86 @@ k_finalize_direct(int32_t *__restrict__ hits, int64_t hits_stride,
     const int32_t *crow = cnt + g * (int64_t)C * K1;
     int32_t *hrow = hits ? hits + g * hits_stride : nullptr;
     double h = 0.0;
+    if (TK1 > 0) {
+        // compile-time K-1: the class's hit square lives in registers (one pass over
+        // global memory, 128-bit loads when the square is a multiple of 4 ints)
+        constexpr int KK = TK1 > 0 ? TK1 * TK1 : 1;
+        constexpr int TK = TK1 > 0 ? TK1 : 1;
+        for (int y = 0; y < C; ++y, crow += TK) {
+            int x[KK];
+            int c0[TK];
+#pragma unroll
+            for (int v = 0; v < TK; ++v) c0[v] = crow[v];
+            bool any = false;
+            if (hrow) {
+                if (KK % 4 == 0) {
+#pragma unroll
+                    for (int q = 0; q < KK / 4; ++q) {
+                        const int4 t = *reinterpret_cast<const int4 *>(hrow + 4 * q);
+                        x[4 * q] = t.x, x[4 * q + 1] = t.y, x[4 * q + 2] = t.z, x[4 * q + 3] = t.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < KK; ++i) x[i] = hrow[i];
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < KK; ++i) x[i] = 0;
+            }
+            int cs[TK], rs[TK];
+#pragma unroll
+            for (int v = 0; v < TK; ++v) cs[v] = 0;
+#pragma unroll
+            for (int a = 0; a < TK; ++a) {
+                rs[a] = 0;
+#pragma unroll
+                for (int v = 0; v < TK; ++v) {
+                    const int t = x[a * TK + v];
+                    rs[a] += t;
+                    cs[v] += t;
+                    any |= t != 0;
+                    if (marg) m2[(a * TK + v) * nt] += t;
+                }
+            }
+            int tot0 = 0;
+#pragma unroll
+            for (int v = 0; v < TK; ++v) {
+                tot0 += c0[v] - cs[v];
+                if (marg) xc[v * nt] += c0[v];
+            }
+            // term-table gathers of the whole class are independent: issue them together
+            double t0[TK + 1], ta[TK * (TK + 1)];
+            t0[0] = __ldg(term + (int)(clsz[y] - (hrow ? hs_ysum[y] : 0) - tot0));
+#pragma unroll
+            for (int v = 0; v < TK; ++v) t0[v + 1] = __ldg(term + (c0[v] - cs[v]));
+            if (hrow) {
+#pragma unroll
+                for (int a = 0; a < TK; ++a) {
+                    ta[a * (TK + 1)] = __ldg(term + (hsize[y * TK + a] - rs[a]));
+#pragma unroll
+                    for (int v = 0; v < TK; ++v)
+                        ta[a * (TK + 1) + v + 1] = __ldg(term + x[a * TK + v]);
+                }
+            }
+#pragma unroll
+            for (int v = 0; v <= TK; ++v) h = __dadd_rn(h, t0[v]);
+            if (hrow) {
+#pragma unroll
+                for (int i = 0; i < TK * (TK + 1); ++i) h = __dadd_rn(h, ta[i]);
+                if (any) {  // leave the buffer clean for the next pass
+                    if (KK % 4 == 0) {
+#pragma unroll
+                        for (int q = 0; q < KK / 4; ++q)
+                            *reinterpret_cast<int4 *>(hrow + 4 * q) = make_int4(0, 0, 0, 0);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < KK; ++i) hrow[i] = 0;
+                    }
+                }
+                hrow += KK;
+            }
+        }
+    } else
     for (int y = 0; y < C; ++y, crow += K1) {
         // pass 1: row / column sums of this class's hit square
 #pragma unroll

@@ -11,6 +11,8 @@
 // HBM-bound by design: 4 bytes per stored entry, read exactly once with
 // 128-bit coalesced loads; one persistent CTA per SM; dynamic ranges of the nnz
 // stream are claimed per team (1..32 warps) so skewed genes balance.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace prb {
@@ -71,7 +73,12 @@ static int plan_stream(int64_t N, int64_t n_states, int K1, StreamPlan *p)
     static const int cand[] = {32, 8, 4, 2, 1};
     int teams = 0;
     int64_t avail = 0;
+    static const int forced = [] {
+        const char *e = getenv("PRB_STREAM_TEAMS");  // tuning knob: 32, 8, 4, 2 or 1
+        return e ? atoi(e) : 0;
+    }();
     for (int c : cand) {
+        if (forced && c > forced) continue;
         avail = smem_max - fixed - c * hist_bytes;
         if (avail >= want) {
             teams = c;
