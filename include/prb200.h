@@ -158,9 +158,12 @@ int prb_selector_update(int kind, int is_remove, const double *base, double *pen
  * as maximal, like np.argmax). */
 int prb_argmax_blocks(const double *score, int64_t P, int32_t gene_lo, double *cand_score,
                       int64_t *cand_idx, prb_stream_t stream);
-/* reduce n_cand candidates to one (score,idx); ties -> lowest idx. */
+/* reduce n_cand candidates to one (score,idx); ties -> lowest idx.  Candidate c is
+ * read at cand_score[c*stride], cand_idx[c*stride] (stride 2 = interleaved 16-byte
+ * (score, idx) records, the layout of the multi-GPU all-gather). */
 int prb_argmax_final(const double *cand_score, const int64_t *cand_idx, int64_t n_cand,
-                     double *best_score, int64_t *best_idx, prb_stream_t stream);
+                     int64_t stride, double *best_score, int64_t *best_idx,
+                     prb_stream_t stream);
 /* commit a winner: gene_ptr <- idx, S[n_sel++] <- idx, selected[idx-gene_lo] <- 1,
  * score[idx-gene_lo] untouched (the update masks it).  idx is read from best_idx. */
 int prb_commit_add(const int64_t *best_idx, int32_t *gene_ptr, int32_t *S, int32_t *n_sel_ptr,

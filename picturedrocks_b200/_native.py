@@ -47,7 +47,7 @@ _SIGS = {
     "prb_selector_update": [_int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64,
                             _i32, _vp, _vp, _vp],
     "prb_argmax_blocks": [_vp, _i64, _i32, _vp, _vp, _vp],
-    "prb_argmax_final": [_vp, _vp, _i64, _vp, _vp, _vp],
+    "prb_argmax_final": [_vp, _vp, _i64, _i64, _vp, _vp, _vp],
     "prb_commit_add": [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp],
     "prb_transpose": [_vp, _int, _i64, _i64, _vp, _vp],
     "prb_sort_columns_workspace": [_int, _i64, _i64, ctypes.POINTER(_i64)],

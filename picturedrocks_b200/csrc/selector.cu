@@ -114,13 +114,14 @@ k_argmax_blocks(const double *__restrict__ score, int64_t P, int32_t gene_lo,
 
 __global__ void __launch_bounds__(SEL_BLOCK)
 k_argmax_final(const double *__restrict__ cand_score, const int64_t *__restrict__ cand_idx,
-               int64_t n_cand, double *__restrict__ best_score, int64_t *__restrict__ best_idx)
+               int64_t n_cand, int64_t stride, double *__restrict__ best_score,
+               int64_t *__restrict__ best_idx)
 {
     double sc = 0.0;
     int64_t idx = -1;
     for (int64_t c = threadIdx.x; c < n_cand; c += SEL_BLOCK) {
-        const double s2 = cand_score[c];
-        const int64_t i2 = cand_idx[c];
+        const double s2 = cand_score[c * stride];
+        const int64_t i2 = cand_idx[c * stride];
         if (i2 >= 0 && (idx < 0 || better(s2, i2, sc, idx))) {
             sc = s2;
             idx = i2;
@@ -187,10 +188,12 @@ extern "C" int prb_argmax_blocks(const double *score, int64_t P, int32_t gene_lo
 }
 
 extern "C" int prb_argmax_final(const double *cand_score, const int64_t *cand_idx, int64_t n_cand,
-                                double *best_score, int64_t *best_idx, prb_stream_t stream)
+                                int64_t stride, double *best_score, int64_t *best_idx,
+                                prb_stream_t stream)
 {
-    k_argmax_final<<<1, SEL_BLOCK, 0, S(stream)>>>(cand_score, cand_idx, n_cand, best_score,
-                                                   best_idx);
+    PRB_REQUIRE(stride >= 1, "stride must be >= 1");
+    k_argmax_final<<<1, SEL_BLOCK, 0, S(stream)>>>(cand_score, cand_idx, n_cand, stride,
+                                                   best_score, best_idx);
     PRB_LAUNCH_CHECK("k_argmax_final");
     return 0;
 }

@@ -80,6 +80,7 @@ class Engine:
         self.gene_ptr = torch.zeros(1, dtype=torch.int32, device=dev)
         self._hits = None
         self._table = None
+        self.epoch = 0  # bumped whenever device buffers a captured graph points at change
         self.clsz_all = torch.tensor([self.N], dtype=torch.int64, device=dev)
         # labels
         self.has_y = False
@@ -138,6 +139,7 @@ class Engine:
 
     def set_y(self, y):
         """y: int32 device tensor [N] of labels in 0..C-1, or None (infoset.py:202-216)."""
+        self.epoch += 1
         if y is None:
             self.has_y, self.y, self.C, self.classsizes, self.cnt_y = False, None, 1, None, None
             return
@@ -154,6 +156,7 @@ class Engine:
         need = max(self.P * n_bins, 1)
         if self._hits is None or self._hits.numel() < need:
             self._hits = None
+            self.epoch += 1
             self._hits = torch.zeros(need, dtype=torch.int32, device=self.device)
         return self._hits
 

@@ -14,6 +14,7 @@ Score algebra is evaluated in the reference's order (iterative.py:29-33, 50-58,
 78-86, 114-120) so results are bit-identical given bit-identical entropies.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -22,6 +23,8 @@ from ... import _native as nat
 from .._iterative import IterativeFeatureSelection, UnivariateMixin
 
 _KIND = {"CIFE": 0, "JMI": 1, "CIFEUnsup": 2}
+# capture the greedy step as a CUDA graph (set False to launch every kernel eagerly)
+USE_CUDA_GRAPH = os.environ.get("PRB_CUDA_GRAPH", "1") != "0"
 
 
 def _backend(infoset):
@@ -64,8 +67,10 @@ class _DeviceScores:
         self.n_blocks = max(1, -(-self.P // 256))
         self.cand_score = torch.zeros(self.n_blocks, **f64)
         self.cand_idx = torch.full((self.n_blocks,), -1, dtype=torch.int64, device=self.dev)
-        self.best_score = torch.zeros(1, **f64)
-        self.best_idx = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        # one 16-byte (score, idx) record: a single all-gather moves both
+        self.best = torch.zeros(2, **f64)
+        self.best_score = self.best[0:1]
+        self.best_idx = self.best.view(torch.int64)[1:2]
         self.S_dev = torch.zeros(self.P_total + 1, dtype=torch.int32, device=self.dev)
         self.n_sel = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.cand_valid = False
@@ -88,11 +93,10 @@ class _DeviceScores:
             nat.call("prb_argmax_blocks", nat.ptr(self.score), self.P, ctypes.c_int32(self.gene_lo),
                      nat.ptr(self.cand_score), nat.ptr(self.cand_idx), s)
         nat.call("prb_argmax_final", nat.ptr(self.cand_score), nat.ptr(self.cand_idx),
-                 self.n_blocks, nat.ptr(self.best_score), nat.ptr(self.best_idx), s)
+                 self.n_blocks, 1, nat.ptr(self.best_score), nat.ptr(self.best_idx), s)
         if self.comm is not None:
-            gs = self.comm.all_gather_cat(self.best_score)
-            gi = self.comm.all_gather_cat(self.best_idx)
-            nat.call("prb_argmax_final", nat.ptr(gs), nat.ptr(gi), gs.numel(),
+            g = self.comm.all_gather_cat(self.best)  # [world][score, idx]
+            nat.call("prb_argmax_final", nat.ptr(g), nat.ptr(g) + 8, self.comm.world, 2,
                      nat.ptr(self.best_score), nat.ptr(self.best_idx), s)
 
     def commit_best(self):
@@ -125,6 +129,9 @@ class _GreedyDevice(IterativeFeatureSelection):
         self._d = _DeviceScores(infoset, self._supervised)
         self._S = []
         self._pending = 0  # selections made on device, not yet mirrored in _S
+        self._graph = None
+        self._graph_epoch = -1
+        self.graph_kernels_per_step = 0
 
     # -- host-visible state -----------------------------------------------------
     @property
@@ -187,15 +194,44 @@ class _GreedyDevice(IterativeFeatureSelection):
         self._d.engine.gene_ptr.fill_(ind)
         self._d.apply(self._kind, True, ind)
 
+    def _one_step(self):
+        d = self._d
+        d.pick_best()
+        d.commit_best()
+        d.apply(self._kind, False)
+
+    def _graph_ok(self):
+        d = self._d
+        return (d.be.ycol is None and USE_CUDA_GRAPH
+                and getattr(d.engine, "profile_events", None) is None)
+
     def autoselect(self, n_feats):
+        """Greedy selection of n_feats features, entirely on the device.  After one eager
+        step the step is captured once as a CUDA graph (kernels + the two NCCL collectives)
+        and replayed, so the host neither synchronises nor pays per-launch overhead."""
         n_feats = int(n_feats)
         d = self._d
         if len(self._S) + self._pending + n_feats > d.P_total:
             raise ValueError("cannot select more features than there are")
-        for _ in range(n_feats):
-            d.pick_best()
-            d.commit_best()
-            d.apply(self._kind, False)
+        left = n_feats
+        if self._graph_ok():
+            if self._graph is not None and self._graph_epoch != d.engine.epoch:
+                self._graph = None
+            if self._graph is None and left >= 3:
+                self._one_step()  # warm: lazy buffers, NCCL, function attributes
+                left -= 1
+                g = torch.cuda.CUDAGraph()
+                n0 = nat.LAUNCHES
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    self._one_step()
+                self.graph_kernels_per_step = nat.LAUNCHES - n0
+                self._graph, self._graph_epoch = g, d.engine.epoch
+            if self._graph is not None:
+                for _ in range(left):
+                    self._graph.replay()
+                left = 0
+        for _ in range(left):
+            self._one_step()
         self._pending += n_feats
 
 
