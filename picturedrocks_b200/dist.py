@@ -68,3 +68,18 @@ class Comm:
         pad[: t.numel()] = t
         g = self.all_gather_cat(pad).view(self.world, m)
         return torch.cat([g[r, : sizes[r]] for r in range(self.world)])
+
+
+def shutdown():
+    """Release captured graphs, then tear the process group down."""
+    import gc
+
+    from .markers.mutualinformation.iterative import release_graphs
+
+    release_graphs()
+    gc.collect()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    if dist.is_initialized():
+        dist.barrier()
+        dist.destroy_process_group()

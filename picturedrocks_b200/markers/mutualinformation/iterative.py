@@ -15,6 +15,7 @@ Score algebra is evaluated in the reference's order (iterative.py:29-33, 50-58,
 """
 import ctypes
 import os
+import weakref
 
 import numpy as np
 import torch
@@ -25,6 +26,15 @@ from .._iterative import IterativeFeatureSelection, UnivariateMixin
 _KIND = {"CIFE": 0, "JMI": 1, "CIFEUnsup": 2}
 # capture the greedy step as a CUDA graph (set False to launch every kernel eagerly)
 USE_CUDA_GRAPH = os.environ.get("PRB_CUDA_GRAPH", "1") != "0"
+GRAPH_MIN_STEPS = int(os.environ.get("PRB_GRAPH_MIN_STEPS", "8"))
+_LIVE = weakref.WeakSet()  # selectors that may hold a captured graph
+
+
+def release_graphs():
+    """Drop every captured CUDA graph (must precede destroy_process_group: a live graph
+    that contains NCCL nodes makes the communicator teardown hang)."""
+    for fs in list(_LIVE):
+        fs._graph = None
 
 
 def _backend(infoset):
@@ -132,6 +142,7 @@ class _GreedyDevice(IterativeFeatureSelection):
         self._graph = None
         self._graph_epoch = -1
         self.graph_kernels_per_step = 0
+        _LIVE.add(self)
 
     # -- host-visible state -----------------------------------------------------
     @property
@@ -200,6 +211,23 @@ class _GreedyDevice(IterativeFeatureSelection):
         d.commit_best()
         d.apply(self._kind, False)
 
+    def _capture(self):
+        """Capture one greedy step (kernels + collectives) on a side stream."""
+        d = self._d
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        n0 = nat.LAUNCHES
+        with torch.cuda.stream(side):
+            g.capture_begin(capture_error_mode="thread_local")
+            try:
+                self._one_step()
+            finally:
+                g.capture_end()
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph_kernels_per_step = nat.LAUNCHES - n0
+        self._graph, self._graph_epoch = g, d.engine.epoch
+
     def _graph_ok(self):
         d = self._d
         return (d.be.ycol is None and USE_CUDA_GRAPH
@@ -217,15 +245,10 @@ class _GreedyDevice(IterativeFeatureSelection):
         if self._graph_ok():
             if self._graph is not None and self._graph_epoch != d.engine.epoch:
                 self._graph = None
-            if self._graph is None and left >= 3:
+            if self._graph is None and left >= GRAPH_MIN_STEPS:
                 self._one_step()  # warm: lazy buffers, NCCL, function attributes
                 left -= 1
-                g = torch.cuda.CUDAGraph()
-                n0 = nat.LAUNCHES
-                with torch.cuda.graph(g, capture_error_mode="thread_local"):
-                    self._one_step()
-                self.graph_kernels_per_step = nat.LAUNCHES - n0
-                self._graph, self._graph_epoch = g, d.engine.epoch
+                self._capture()
             if self._graph is not None:
                 for _ in range(left):
                     self._graph.replay()

@@ -38,7 +38,7 @@ def _worker(rank, world, port, ret):
         out = {}
         for kind in ("CIFE", "JMI", "CIFEUnsup"):
             fs = getattr(pr.markers, kind)(inf)
-            fs.autoselect(5)
+            fs.autoselect(12)  # >= GRAPH_MIN_STEPS: the step (incl. NCCL) runs as a CUDA graph
             fs.remove(fs.S[2])
             fs.add(7)
             fs.autoselect(2)
@@ -49,7 +49,9 @@ def _worker(rank, world, port, ret):
         if rank == 0:
             ret.update(out)
     finally:
-        dist.destroy_process_group()
+        from picturedrocks_b200.dist import shutdown
+
+        shutdown()
 
 
 @pytest.mark.timeout(600)
@@ -70,7 +72,7 @@ def test_two_rank_selection_equals_single_gpu():
     inf = pr.markers.SparseInformationSet._from_engine(eng, yd)
     for kind in ("CIFE", "JMI", "CIFEUnsup"):
         fs = getattr(pr.markers, kind)(inf)
-        fs.autoselect(5)
+        fs.autoselect(12)
         fs.remove(fs.S[2])
         fs.add(7)
         fs.autoselect(2)
