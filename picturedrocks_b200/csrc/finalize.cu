@@ -336,6 +336,163 @@ k_finalize_direct(int32_t *__restrict__ hits, int64_t hits_stride,
     }
 }
 
+
+// ---------------------------------------------------------------------------
+// Direct layout, compile-time K-1, L lanes per gene.  The L lanes of a group take L
+// consecutive classes: each lane loads its class's hit square, derives the 1+K1+K1*(K1+1)
+// bin counts by subtraction and gathers their terms — this part (most of the
+// instructions and all of the memory latency) runs on all lanes in parallel.  The ordered
+// sum then walks the L classes in order: every lane extends the running sum by ITS terms,
+// and the value of the lane that owns the next class in order is broadcast with a shuffle,
+// so the sequence of fp64 roundings is exactly the reference's (y, x_j, x_i) bin order.
+// Classes past C contribute +0.0 terms (exact no-ops).
+// ---------------------------------------------------------------------------
+template <int TK1, int L>
+__global__ void __launch_bounds__(256)
+k_finalize_direct_grp(int32_t *__restrict__ hits, int64_t hits_stride,
+                      const int32_t *__restrict__ cnt, const int64_t *__restrict__ clsz,
+                      const int32_t *__restrict__ hsize, const int32_t *__restrict__ hs_ysum,
+                      const int32_t *__restrict__ ha, int C, const double *__restrict__ term,
+                      int64_t N, int64_t P, double *__restrict__ out_full,
+                      double *__restrict__ out_marg)
+{
+    constexpr int TK = TK1, KK = TK1 * TK1, NT = 1 + TK + TK * (TK + 1);
+    const int lane = threadIdx.x & 31;
+    const int sub = lane & (L - 1);
+    const int grp0 = lane & ~(L - 1);
+    const int64_t g_raw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / L;
+    const bool active = g_raw < P;
+    const int64_t g = active ? g_raw : P - 1;  // keep whole warps alive for the shuffles
+    const bool marg = out_marg != nullptr;
+    const int32_t *crow = cnt + g * (int64_t)C * TK;
+    int32_t *hrow = hits ? hits + g * hits_stride : nullptr;
+    auto T = [&](int c) -> double { return c ? __ldg(term + c) : 0.0; };
+    int m2[KK], xc[TK];
+#pragma unroll
+    for (int i = 0; i < KK; ++i) m2[i] = 0;
+#pragma unroll
+    for (int i = 0; i < TK; ++i) xc[i] = 0;
+    double h = 0.0;
+    for (int y0 = 0; y0 < C; y0 += L) {
+        const int y = y0 + sub;
+        double t[NT];
+        if (y < C) {
+            int x[KK], c0[TK];
+#pragma unroll
+            for (int v = 0; v < TK; ++v) c0[v] = crow[y * TK + v];
+            bool any = false;
+            if (hrow) {
+                int32_t *hr = hrow + (int64_t)y * KK;
+                if (KK % 4 == 0) {
+#pragma unroll
+                    for (int q = 0; q < KK / 4; ++q) {
+                        const int4 w = *reinterpret_cast<const int4 *>(hr + 4 * q);
+                        x[4 * q] = w.x, x[4 * q + 1] = w.y, x[4 * q + 2] = w.z, x[4 * q + 3] = w.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < KK; ++i) x[i] = hr[i];
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < KK; ++i) x[i] = 0;
+            }
+            int cs[TK], rs[TK];
+#pragma unroll
+            for (int v = 0; v < TK; ++v) cs[v] = 0;
+#pragma unroll
+            for (int a = 0; a < TK; ++a) {
+                rs[a] = 0;
+#pragma unroll
+                for (int v = 0; v < TK; ++v) {
+                    const int q = x[a * TK + v];
+                    rs[a] += q;
+                    cs[v] += q;
+                    any |= q != 0;
+                    m2[a * TK + v] += q;
+                }
+            }
+            int tot0 = 0;
+#pragma unroll
+            for (int v = 0; v < TK; ++v) {
+                tot0 += c0[v] - cs[v];
+                xc[v] += c0[v];
+            }
+            t[0] = T((int)(clsz[y] - (hrow ? hs_ysum[y] : 0) - tot0));
+#pragma unroll
+            for (int v = 0; v < TK; ++v) t[1 + v] = T(c0[v] - cs[v]);
+#pragma unroll
+            for (int a = 0; a < TK; ++a) {
+                t[1 + TK + a * (TK + 1)] = T((hrow ? hsize[y * TK + a] : 0) - rs[a]);
+#pragma unroll
+                for (int v = 0; v < TK; ++v) t[2 + TK + a * (TK + 1) + v] = T(x[a * TK + v]);
+            }
+            if (any && active) {  // leave the buffer clean for the next pass
+                int32_t *hr = hrow + (int64_t)y * KK;
+                if (KK % 4 == 0) {
+#pragma unroll
+                    for (int q = 0; q < KK / 4; ++q)
+                        *reinterpret_cast<int4 *>(hr + 4 * q) = make_int4(0, 0, 0, 0);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < KK; ++i) hr[i] = 0;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NT; ++i) t[i] = 0.0;
+        }
+        // ordered accumulation over the L classes of this round
+#pragma unroll
+        for (int l2 = 0; l2 < L; ++l2) {
+            double hh = h;
+#pragma unroll
+            for (int i = 0; i < NT; ++i) hh = __dadd_rn(hh, t[i]);
+            h = __shfl_sync(0xffffffffu, hh, grp0 + l2);
+        }
+    }
+    if (active && sub == 0) out_full[g] = h;
+    if (marg) {
+        // class sums of the group -> every lane
+#pragma unroll
+        for (int o = 1; o < L; o <<= 1) {
+#pragma unroll
+            for (int i = 0; i < KK; ++i) m2[i] += __shfl_xor_sync(0xffffffffu, m2[i], o);
+#pragma unroll
+            for (int i = 0; i < TK; ++i) xc[i] += __shfl_xor_sync(0xffffffffu, xc[i], o);
+        }
+        if (active && sub == 0) {
+            int sum_ha = 0, sum_xc = 0, sum_m2 = 0, hav[TK];
+#pragma unroll
+            for (int a = 0; a < TK; ++a) {
+                hav[a] = (hits && ha) ? ha[a] : 0;
+                sum_ha += hav[a];
+                sum_xc += xc[a];
+            }
+#pragma unroll
+            for (int i = 0; i < KK; ++i) sum_m2 += m2[i];
+            double h2 = __dadd_rn(0.0, T((int)(N - sum_ha - (sum_xc - sum_m2))));
+#pragma unroll
+            for (int v = 0; v < TK; ++v) {
+                int s = 0;
+#pragma unroll
+                for (int a = 0; a < TK; ++a) s += m2[a * TK + v];
+                h2 = __dadd_rn(h2, T(xc[v] - s));
+            }
+#pragma unroll
+            for (int a = 0; a < TK; ++a) {
+                int s = 0;
+#pragma unroll
+                for (int v = 0; v < TK; ++v) s += m2[a * TK + v];
+                h2 = __dadd_rn(h2, T(hav[a] - s));
+#pragma unroll
+                for (int v = 0; v < TK; ++v) h2 = __dadd_rn(h2, T(m2[a * TK + v]));
+            }
+            out_marg[g] = h2;
+        }
+    }
+}
+
 }  // namespace prb
 
 using namespace prb;
@@ -375,6 +532,14 @@ static int launch_direct(int32_t *hits, int64_t stride, const int32_t *cnt, cons
                          int K1, const double *table, int64_t N, int64_t P, double *out_full,
                          double *out_marg, cudaStream_t st)
 {
+    if constexpr (TK1 > 0) {
+        constexpr int L = 8;  // lanes per gene
+        const int threads = 256;
+        k_finalize_direct_grp<TK1, L><<<(unsigned)ceil_div(P * L, threads), threads, 0, st>>>(
+            hits, stride, cnt, clsz, hsize, hs_ysum, ha, C, table, N, P, out_full, out_marg);
+        PRB_LAUNCH_CHECK("k_finalize_direct_grp");
+        return 0;
+    }
     const int64_t per_thread = (int64_t)(3 * K1 + K1 * K1) * 4;
     int threads = 128;
     const int64_t smem_max = devinfo().smem_optin - 1024;
