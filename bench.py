@@ -175,15 +175,8 @@ def cpu_baseline_sample(spec, eng, y_host, budget_s=15.0):
 
     cores = O.max_threads()
     G = int(min(eng.P, max(64, 8 * cores)))
-    ip = eng.indptr[: G + 1].cpu().numpy()
-    n = int(ip[-1])
-    rows = torch.empty(max(n, 1), dtype=torch.int32, device=eng.device)
-    codes = torch.empty(max(n, 1), dtype=torch.uint8, device=eng.device)
-    nat.call("prb_unpack_csc", nat.ptr(eng.packed), n, nat.ptr(rows), nat.ptr(codes), nat.stream())
-    import scipy.sparse
-
-    X = scipy.sparse.csc_matrix((codes[:n].cpu().numpy().astype(np.int64), rows[:n].cpu().numpy(), ip),
-                                shape=(spec.N, G))
+    X = eng.to_scipy_csc(G)  # original cell order, int64 data like the reference's
+    ip = X.indptr
     inf = O.SparseInformationSet(X, y_host, nthreads=cores)
     dens = np.diff(ip)
     j = int(np.argsort(dens)[len(dens) // 2])

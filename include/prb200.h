@@ -83,6 +83,41 @@ int prb_stream_hits(const uint32_t *packed, const int64_t *tp, int64_t P, int64_
                     const void *state, int64_t N, int64_t n_states, int K1, int direct_C,
                     int32_t *hits, int32_t *counters, prb_stream_t stream);
 
+/* ---- the hot loop for K <= 5: class-sorted cells + register counters (swar.cu) ----
+ * Same job as prb_stream_hits for the direct single-gene layout — the merge of
+ * INFOSET:365-391 for entropy_wrt([j]) / entropy_wrt([-1, j]) (ITER:53, 55) and the
+ * class-conditional count tables behind entropy_wrt([]) / ([-1]) (ITER:30, 32) — on a
+ * matrix whose cells have been relabelled so that classes are contiguous
+ * (prb_class_sort; entropies do not depend on the order of cells).
+ * Segment plan (host-built, device arrays): seg_cell0 int32[n_seg+1] ascending cell
+ * boundaries of the class segments (last = N); seg_class int32[n_seg] or NULL (= all
+ * class 0); st_seg0 int32[n_st+1]: super-tile t = segments [st_seg0[t], st_seg0[t+1]),
+ * at most max_segs of them and at most max_cells cells (prb_swar_tile_capacity);
+ * tpf int32[P][n_seg+1] from prb_seg_ptrs: first entry of gene g, relative to
+ * indptr[g], whose cell id is >= seg_cell0[s].
+ *   sx  : int8[N] (+16 bytes padding) from prb_state_swar, or NULL = count-table mode
+ *   out : hits int32[P][C][K-1][K-1] (added to; bin = (x_j-1)*(K-1) + x_g-1), or in
+ *         count-table mode cnt int32[P][C][K-1].
+ *   counters : int32[n_st] scratch (reset by the call). */
+int prb_swar_tile_capacity(int64_t *max_cells, int *max_segs);
+int prb_seg_ptrs(const uint32_t *packed, const int64_t *indptr, int64_t P,
+                 const int32_t *seg_cell0, int n_seg, int32_t *tpf, prb_stream_t stream);
+int prb_stream_swar(const uint32_t *packed, const int64_t *indptr, const int32_t *tpf, int n_seg,
+                    int64_t P, int64_t nnz, const int32_t *st_seg0, const int32_t *seg_cell0,
+                    const int32_t *seg_class, int n_st, int64_t max_tile_cells, const int8_t *sx,
+                    int K1, int C, int32_t *out, int32_t *counters, prb_stream_t stream);
+/* per-cell shift code of the selected gene for prb_stream_swar (sx int8[N]) plus the
+ * same hsize / hs_begin / hs_y / hs_ysum / ha tables as prb_state_direct. */
+int prb_state_swar(const uint8_t *xj, const int32_t *y, int64_t N, int C, int K, int8_t *sx,
+                   int32_t *hsize, int32_t *hs_begin, int32_t *hs_y, int32_t *hs_ysum,
+                   int32_t *ha, prb_stream_t stream);
+/* relabel cells and keep every gene's entries ascending: out word = code | newpos[row],
+ * entries of a gene stably partitioned by cls[row] (int32[N], class of the CURRENT cell
+ * id; newpos must be increasing inside a class).  queue: device int32 scratch. */
+int prb_class_sort(const uint32_t *packed_in, const int64_t *indptr, int64_t P,
+                   const int32_t *newpos, const int32_t *cls, int C, uint32_t *packed_out,
+                   int32_t *queue, prb_stream_t stream);
+
 /* ---- joint-state build ("master column", _sparse_make_master_col INFOSET:431-442) */
 /* dense uint8 x_j[N] (zeroed by caller) <- codes of gene *gene_ptr (device int32;
  * genes outside [gene_lo, gene_lo+P) are ignored: multi-GPU owner test). */

@@ -15,6 +15,7 @@ only exchanges are a max-all-reduce of the selected gene's dense code vector
 and the (score, index) all-gather of the argmax — see dist.py.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -22,6 +23,10 @@ import torch
 from . import _native as nat
 
 _I16_MAX_BINS = 65536
+# K <= 5: class-sorted cells + register counters (csrc/swar.cu); PRB_NO_SWAR=1 forces the
+# generic shared-histogram kernel (csrc/stream.cu) everywhere
+USE_SWAR = os.environ.get("PRB_NO_SWAR", "0") != "1"
+PACKED_PAD = 4  # words of slack after the last stored entry
 
 
 def _i32(x):
@@ -54,6 +59,9 @@ class Engine:
         self.K1 = self.K - 1
         self.shift = (self.K - 1).bit_length()  # infoset.py:199  int(log2(max)+1)
         self.nnz = int(indptr[-1].item())
+        if packed.numel() < self.nnz + PACKED_PAD:  # csrc/swar.cu reads whole 16-byte chunks
+            packed = torch.cat([packed[: self.nnz], packed.new_zeros(PACKED_PAD)])
+            self.packed = packed
         sm = ctypes.c_int()
         smem = ctypes.c_int()
         nat.call("prb_device_info", ctypes.byref(sm), ctypes.byref(smem))
@@ -77,6 +85,10 @@ class Engine:
         self.counters = torch.zeros(8192, dtype=torch.int32, device=dev)
         self._plans = {}
         self._tps = {}
+        self._swar = {}
+        self.swar = USE_SWAR and self.K1 <= 4
+        self.cell_of_pos = None  # int64[N]: original cell id at each position (None = identity)
+        self.classsizes_host = None
         self.gene_ptr = torch.zeros(1, dtype=torch.int32, device=dev)
         self._hits = None
         self._table = None
@@ -129,6 +141,9 @@ class Engine:
         if C * self.K1 > _I16_MAX_BINS:
             raise NotImplementedError("classes x codes exceeds 65536 histogram bins")
         cnt = torch.zeros(max(self.P * C * self.K1, 1), dtype=torch.int32, device=self.device)
+        if self.swar:
+            self._stream_swar(y is not None, None, C, cnt)
+            return cnt
         sb = self._plan(C)[3]
         if y is None:
             self._store_state(torch.ones(self.N, dtype=torch.int32, device=self.device), sb)
@@ -138,18 +153,103 @@ class Engine:
         return cnt
 
     def set_y(self, y):
-        """y: int32 device tensor [N] of labels in 0..C-1, or None (infoset.py:202-216)."""
+        """y: int32 device tensor [N] of labels in 0..C-1 (original cell order), or None
+        (infoset.py:202-216).  The cells are re-ordered so that classes are contiguous
+        (stable, so every gene's entries stay ascending): entropies do not depend on the
+        order of cells, and csrc/swar.cu needs class-contiguous cells."""
         self.epoch += 1
         if y is None:
             self.has_y, self.y, self.C, self.classsizes, self.cnt_y = False, None, 1, None, None
+            self.classsizes_host = None
             return
         assert y.dtype == torch.int32 and y.is_cuda and y.numel() == self.N
         C = int(y.max().item()) + 1
         if C > 256:
             raise NotImplementedError("more than 256 classes")
-        self.has_y, self.y, self.C = True, y.contiguous(), C
-        self.classsizes = torch.bincount(y, minlength=C).to(torch.int64)
+        y_cur = y if self.cell_of_pos is None else y[self.cell_of_pos]
+        if self.N > 1 and not bool((y_cur[1:] >= y_cur[:-1]).all().item()):
+            order = torch.argsort(y_cur, stable=True)
+            newpos = torch.empty(self.N, dtype=torch.int32, device=self.device)
+            newpos[order] = torch.arange(self.N, dtype=torch.int32, device=self.device)
+            out = torch.empty_like(self.packed)
+            nat.call("prb_class_sort", nat.ptr(self.packed), nat.ptr(self.indptr), self.P,
+                     nat.ptr(newpos), nat.ptr(y_cur.contiguous()), C, nat.ptr(out),
+                     nat.ptr(self.counters), nat.stream())
+            self.packed = out
+            self.cell_of_pos = order if self.cell_of_pos is None else self.cell_of_pos[order]
+            y_cur = y_cur[order]
+            self._tps, self._swar = {}, {}
+        self.has_y, self.y, self.C = True, y_cur.contiguous(), C
+        self.classsizes = torch.bincount(self.y, minlength=C).to(torch.int64)
+        self.classsizes_host = [int(v) for v in self.classsizes.cpu().numpy()]
+        self._swar.pop(True, None)
         self.cnt_y = self._count_table(self.y, C)
+
+    # ------------------------------------------------ register-counter path (K <= 5)
+    def _swar_plan(self, classes):
+        """Segment plan of csrc/swar.cu: class segments (split when a class exceeds the
+        shared-memory capacity) packed into super-tiles; cached until the cells move."""
+        pl = self._swar.get(classes)
+        if pl is not None:
+            return pl
+        cap, max_segs = ctypes.c_int64(), ctypes.c_int()
+        nat.call("prb_swar_tile_capacity", ctypes.byref(cap), ctypes.byref(max_segs))
+        cap = max(128, min(int(os.environ.get("PRB_SWAR_TILE_CELLS", cap.value)), cap.value))
+        sizes = self.classsizes_host if classes else [self.N]
+        cell0, cls, pos = [], [], 0
+        for c, n in enumerate(sizes):
+            pieces = -(-n // cap)
+            for k in range(pieces):
+                cell0.append(pos + n * k // pieces)
+                cls.append(c)
+            pos += n
+        assert pos == self.N
+        cell0.append(self.N)
+        n_seg = len(cls)
+        n_st_min = -(-self.N // cap)
+        target = -(-self.N // n_st_min)
+        st, cur_cells, cur_n = [0], 0, 0
+        for i in range(n_seg):
+            sz = cell0[i + 1] - cell0[i]
+            if cur_n and (cur_cells + sz > cap or cur_n == max_segs.value or cur_cells >= target):
+                st.append(i)
+                cur_cells, cur_n = 0, 0
+            cur_cells += sz
+            cur_n += 1
+        st.append(n_seg)
+        n_st = len(st) - 1
+        if n_st > self.counters.numel():
+            raise NotImplementedError("too many cell tiles")
+        max_cells = max(cell0[st[t + 1]] - cell0[st[t]] for t in range(n_st))
+        i32 = dict(dtype=torch.int32, device=self.device)
+        pl = dict(n_seg=n_seg, n_st=n_st, max_cells=max_cells,
+                  seg_cell0=torch.tensor(cell0, **i32), st_seg0=torch.tensor(st, **i32),
+                  seg_class=torch.tensor(cls, **i32) if classes else None,
+                  tpf=torch.empty(max(self.P, 1) * (n_seg + 1), **i32))
+        if self.P:
+            nat.call("prb_seg_ptrs", nat.ptr(self.packed), nat.ptr(self.indptr), self.P,
+                     nat.ptr(pl["seg_cell0"]), n_seg, nat.ptr(pl["tpf"]), nat.stream())
+        self._swar[classes] = pl
+        return pl
+
+    def _stream_swar(self, classes, sx, C, out):
+        ev = getattr(self, "profile_events", None)
+        if ev is not None:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            self._stream_swar_launch(classes, sx, C, out)
+            e1.record()
+            ev.append((e0, e1))
+        else:
+            self._stream_swar_launch(classes, sx, C, out)
+
+    def _stream_swar_launch(self, classes, sx, C, out):
+        pl = self._swar_plan(classes)
+        nat.call("prb_stream_swar", nat.ptr(self.packed), nat.ptr(self.indptr), nat.ptr(pl["tpf"]),
+                 pl["n_seg"], self.P, self.nnz, nat.ptr(pl["st_seg0"]), nat.ptr(pl["seg_cell0"]),
+                 nat.ptr(pl["seg_class"]), pl["n_st"], pl["max_cells"], nat.ptr(sx), self.K1, C,
+                 nat.ptr(out), nat.ptr(self.counters), nat.stream())
 
     # --------------------------------------------------------------- primitives
     def hits_buffer(self, n_bins):
@@ -218,6 +318,14 @@ class Engine:
         if n_bins > _I16_MAX_BINS:
             raise NotImplementedError("C*(K-1)^2 exceeds 65536 histogram bins")
         self.scatter_selected_gene()
+        if self.swar:
+            nat.call("prb_state_swar", nat.ptr(self.xj), nat.ptr(y), self.N, C, self.K,
+                     nat.ptr(self.state_buf), nat.ptr(self.hsize), nat.ptr(self.hs_begin),
+                     nat.ptr(self.hs_y), nat.ptr(self.hs_ysum), nat.ptr(self.ha), nat.stream())
+            hits = self.hits_buffer(n_bins)
+            self._stream_swar(with_y, self.state_buf, C, hits)
+            self._finalize(hits, cnt, clsz, C, n_hs, None, out_full, out_marg, True)
+            return
         sb = self._plan(n_hs)[3]
         nat.call("prb_state_direct", nat.ptr(self.xj), nat.ptr(y), self.N, C, self.K,
                  nat.ptr(self.state_buf), sb, nat.ptr(self.hsize), nat.ptr(self.hs_begin),
@@ -329,7 +437,7 @@ class Engine:
         rows_d = up(indices, torch.int32)
         codes_d = up(data, torch.uint8)
         nnz = rows_d.numel()
-        packed = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
+        packed = torch.zeros(nnz + PACKED_PAD, dtype=torch.int32, device=dev)
         nat.call("prb_pack_csc", nat.ptr(rows_d), nat.ptr(codes_d), nnz, nat.ptr(packed),
                  nat.stream())
         K = (int(codes_d.max().item()) + 1) if nnz else 1
@@ -345,20 +453,29 @@ class Engine:
         indptr = torch.zeros(P + 1, dtype=torch.int64, device=dev)
         torch.cumsum(counts, 0, out=indptr[1:])
         nnz = int(indptr[-1].item())
-        packed = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
+        packed = torch.zeros(nnz + PACKED_PAD, dtype=torch.int32, device=dev)
         nat.call("prb_dense_fill_csc", nat.ptr(codes), N, P, ld, nat.ptr(indptr), nat.ptr(packed),
                  nat.stream())
         K = (int(codes[:, :N].max().item()) + 1) if P else 1
         return cls(indptr, packed, N, K, **kw)
 
-    def to_scipy_csc(self):
-        """Host scipy.sparse.csc_matrix (int64 data like the reference's) of the local genes."""
+    def to_scipy_csc(self, n_genes=None):
+        """Host scipy.sparse.csc_matrix (int64 data like the reference's) of the first
+        n_genes local genes (default all), in the ORIGINAL cell order."""
         import scipy.sparse
 
-        rows = torch.empty(max(self.nnz, 1), dtype=torch.int32, device=self.device)
-        codes = torch.empty(max(self.nnz, 1), dtype=torch.uint8, device=self.device)
-        nat.call("prb_unpack_csc", nat.ptr(self.packed), self.nnz, nat.ptr(rows), nat.ptr(codes),
+        G = self.P if n_genes is None else min(int(n_genes), self.P)
+        ip = self.indptr[: G + 1].cpu().numpy()
+        n = int(ip[-1])
+        rows = torch.empty(max(n, 1), dtype=torch.int32, device=self.device)
+        codes = torch.empty(max(n, 1), dtype=torch.uint8, device=self.device)
+        nat.call("prb_unpack_csc", nat.ptr(self.packed), n, nat.ptr(rows), nat.ptr(codes),
                  nat.stream())
-        return scipy.sparse.csc_matrix(
-            (codes[: self.nnz].cpu().numpy().astype(np.int64), rows[: self.nnz].cpu().numpy(),
-             self.indptr.cpu().numpy()), shape=(self.N, self.P))
+        rows = rows[:n]
+        if self.cell_of_pos is not None:
+            rows = self.cell_of_pos[rows.long()].to(torch.int32)
+        X = scipy.sparse.csc_matrix(
+            (codes[:n].cpu().numpy().astype(np.int64), rows.cpu().numpy(), ip),
+            shape=(self.N, G))
+        X.sort_indices()
+        return X

@@ -174,7 +174,7 @@ class DiscretisedSpec:
         indptr = torch.zeros(Pl + 1, dtype=torch.int64, device="cuda")
         torch.cumsum(counts, 0, out=indptr[1:])
         nnz = int(indptr[-1].item())
-        packed = torch.empty(max(nnz, 1), dtype=torch.int32, device="cuda")
+        packed = torch.zeros(nnz + 4, dtype=torch.int32, device="cuda")  # engine.PACKED_PAD
         nat.call("prb_synth_fill", *args, nat.ptr(indptr), nat.ptr(packed), s)
         eng = Engine(indptr, packed, self.N, self.K, gene_lo=gene_lo, P_total=self.P, comm=comm)
         return eng, y

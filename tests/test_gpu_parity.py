@@ -287,3 +287,64 @@ def test_edge_cases(pr):
     a.set_y((y == 1).astype(np.int64))
     b.set_y((y == 1).astype(np.int64))
     assert np.array_equal(a.entropy_wrt([-1]), b.entropy_wrt(np.array([-1])))
+
+
+@pytest.mark.parametrize("tile_cells,swar", [(None, True), (4096, True), (256, True), (None, False)])
+def test_class_sorted_cells_and_register_counters(pr, O, monkeypatch, tile_cells, swar):
+    """csrc/swar.cu (K <= 5): class-sorted cells, class segments split and packed into
+    super-tiles of various sizes, label re-targeting (cells move again), export of X in
+    the original cell order — all bit-identical to the oracle; swar=False runs the same
+    checks through the generic shared-histogram kernel on the same re-ordered cells."""
+    import picturedrocks_b200.engine as E
+    from picturedrocks_b200.synth import DiscretisedSpec
+
+    monkeypatch.setattr(E, "USE_SWAR", swar)
+    if tile_cells:
+        monkeypatch.setenv("PRB_SWAR_TILE_CELLS", str(tile_cells))
+    spec = DiscretisedSpec(N=30011, P=257, C=7, K=5, mean_density=0.09, seed=11)
+    eng, yd = spec.device_engine()
+    assert eng.swar == swar
+    inf = pr.markers.SparseInformationSet._from_engine(eng, yd)
+    y = spec.cpu_labels()
+    Xs = spec.cpu_csc(range(spec.P), y)
+    Xg = eng.to_scipy_csc()  # cells were re-ordered by set_y: export must undo it
+    assert eng.cell_of_pos is not None
+    assert np.array_equal(Xg.indptr, Xs.indptr) and np.array_equal(Xg.indices, Xs.indices)
+    assert np.array_equal(Xg.data, Xs.data)
+    ora = O.SparseInformationSet(Xs, y)
+    rng = np.random.RandomState(5)
+    y_skew = np.where(rng.rand(spec.N) < 0.8, 0, rng.randint(1, 13, spec.N)).astype(np.int64)
+    for labels in (None, y_skew, (y == 3).astype(np.int64)):
+        if labels is not None:
+            inf.set_y(labels)
+            ora.set_y(labels)
+        for cols in ([], [-1], [5], [-1, 5], [200], [-1, 200], [5, 9], [-1, 5, 9]):
+            c = np.array(cols, dtype=np.int64)
+            assert np.array_equal(inf.entropy_wrt(c), ora.entropy_wrt(c)), cols
+            assert inf.entropy(c) == ora.entropy(c), cols
+        for kind in ("CIFE", "JMI", "CIFEUnsup"):
+            a, b = getattr(pr.markers, kind)(inf), getattr(O, kind)(ora)
+            a.autoselect(9)  # crosses GRAPH_MIN_STEPS: eager step, capture, replays
+            b.autoselect(9)
+            assert a.S == [int(s) for s in b.S], kind
+            assert np.array_equal(a.score, b.score), kind
+    Xg = eng.to_scipy_csc()
+    assert np.array_equal(Xg.indices, Xs.indices) and np.array_equal(Xg.data, Xs.data)
+
+
+@pytest.mark.parametrize("K", [2, 3, 4])
+def test_register_counters_fewer_bins(pr, O, K):
+    from picturedrocks_b200.synth import DiscretisedSpec
+
+    spec = DiscretisedSpec(N=9001, P=130, C=5, K=K, mean_density=0.2, seed=K)
+    eng, yd = spec.device_engine()
+    assert eng.swar
+    inf = pr.markers.SparseInformationSet._from_engine(eng, yd)
+    ora = O.SparseInformationSet(inf.X, spec.cpu_labels())
+    for cols in ([], [-1], [3], [-1, 3]):
+        c = np.array(cols, dtype=np.int64)
+        assert np.array_equal(inf.entropy_wrt(c), ora.entropy_wrt(c)), cols
+    a, b = pr.markers.CIFE(inf), O.CIFE(ora)
+    a.autoselect(5)
+    b.autoselect(5)
+    assert a.S == [int(s) for s in b.S] and np.array_equal(a.score, b.score)
