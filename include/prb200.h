@@ -106,10 +106,11 @@ int prb_stream_swar(const uint32_t *packed, const int64_t *indptr, const int32_t
                     int64_t P, int64_t nnz, const int32_t *st_seg0, const int32_t *seg_cell0,
                     const int32_t *seg_class, int n_st, int64_t max_tile_cells, const int8_t *sx,
                     int K1, int C, int32_t *out, int32_t *counters, prb_stream_t stream);
-/* per-cell shift code of the selected gene for prb_stream_swar (sx int8[N]) plus the
- * same hsize / hs_begin / hs_y / hs_ysum / ha tables as prb_state_direct. */
-int prb_state_swar(const uint8_t *xj, const int32_t *y, int64_t N, int C, int K, int8_t *sx,
-                   int32_t *hsize, int32_t *hs_begin, int32_t *hs_y, int32_t *hs_ysum,
+/* per-cell shift code of the selected gene (sx int8[N]; enc 0 for prb_stream_swar, enc 1
+ * for prb_stream_v) plus the same hsize / hs_begin / hs_y / hs_ysum / ha tables as
+ * prb_state_direct. */
+int prb_state_swar(const uint8_t *xj, const int32_t *y, int64_t N, int C, int K, int enc,
+                   int8_t *sx, int32_t *hsize, int32_t *hs_begin, int32_t *hs_y, int32_t *hs_ysum,
                    int32_t *ha, prb_stream_t stream);
 /* relabel cells and keep every gene's entries ascending: out word = code | newpos[row],
  * entries of a gene stably partitioned by cls[row] (int32[N], class of the CURRENT cell
@@ -117,6 +118,37 @@ int prb_state_swar(const uint8_t *xj, const int32_t *y, int64_t N, int C, int K,
 int prb_class_sort(const uint32_t *packed_in, const int64_t *indptr, int64_t P,
                    const int32_t *newpos, const int32_t *cls, int C, uint32_t *packed_out,
                    int32_t *queue, prb_stream_t stream);
+
+/* ---- the hot loop for K <= 5 on the V layout (vstream.cu): 4 instructions per entry ----
+ * Same job as prb_stream_swar.  The V layout re-orders the class-sorted packed CSC once
+ * (prb_v_count -> caller's scan -> prb_v_scatter): every gene g becomes K-1 virtual genes
+ * (g, v), one per non-zero code v; a RUN (vg, s) holds the entries of virtual gene vg in
+ * segment s (seg_of_cell int32[N] = segment of every cell), ascending, padded to a multiple
+ * of 32 entries (one 128-byte row); runs are stored TILE-MAJOR: by (super-tile of s, vg, s).
+ *   seglen    int32[P*(K-1)][n_seg]  true run lengths (= the class-conditional count
+ *                                    tables behind entropy_wrt([]) / ([-1]), ITER:30, 32)
+ *   run_end   int32[P*(K-1)][n_seg]  row just past each run (inclusive scan of
+ *                                    ceil(seglen/32) in storage order, done by the caller)
+ *   tile_row0 int32[n_st+1]          first row of every super-tile's block
+ *   vpacked   uint32[32 * rows]      words code<<24 | cell; the padding words of segment s
+ *             are seg_pad[s] = 0xFF000000 | ((first cell after the segment's super-tile)
+ *             mod tile span): a slot the kernel keeps at "x_j = 0"
+ * prb_stream_v adds to hits int32[P][C][K-1][K-1]; sx = prb_state_swar(enc = 1). */
+int prb_v_tile_capacity(int64_t *max_cells, int *max_segs);
+int prb_v_count(const uint32_t *packed, const int64_t *indptr, int64_t P,
+                const int32_t *seg_of_cell, int n_seg, int K1, int32_t *seglen, int32_t *queue,
+                prb_stream_t stream);
+int prb_v_scatter(const uint32_t *packed, const int64_t *indptr, int64_t P,
+                  const int32_t *seg_of_cell, int n_seg, int K1, const int32_t *seglen,
+                  const int32_t *run_end, const uint32_t *seg_pad, uint32_t *vpacked,
+                  int32_t *queue, prb_stream_t stream);
+int prb_stream_v(const uint32_t *vpacked, const int32_t *run_end, const int32_t *tile_row0,
+                 int n_seg, int64_t P, int K1, int64_t v_rows, const int32_t *st_seg0,
+                 const int32_t *seg_cell0, const int32_t *seg_class, int n_st,
+                 int64_t max_tile_cells, const uint8_t *sx, int C, int32_t *hits,
+                 int32_t *counters, prb_stream_t stream);
+/* cells per super-tile modulus (power of two) of the active kernel configuration */
+int prb_v_tile_span(void);
 
 /* ---- joint-state build ("master column", _sparse_make_master_col INFOSET:431-442) */
 /* dense uint8 x_j[N] (zeroed by caller) <- codes of gene *gene_ptr (device int32;

@@ -96,11 +96,13 @@ __global__ void k_state_direct_sums(const int32_t *__restrict__ hsize, int C, in
 }
 
 // Per-cell shift code of the selected gene (x_j in the class-sorted cell order):
-//   sx = 16*(x_j-1) - 4  (so that sx + 4*x_i is the 4-bit field offset), PRB_SX_NONE for x_j = 0
+//   enc 0 (swar.cu):    sx = 16*(x_j-1) - 4  (sx + 4*x_i = 4-bit field offset), PRB_SX_NONE for x_j = 0
+//   enc 1 (vstream.cu): sx = 8*(x_j-1)       (8-bit field offset),          64 for x_j = 0
 // and hsize[y*(K-1) + x_j-1] = #cells (the sizes of the hit states).
 __global__ void __launch_bounds__(256)
 k_state_swar(const uint8_t *__restrict__ xj, const int32_t *__restrict__ y, int64_t N, int K1,
-             int C, int8_t *__restrict__ sx, int32_t *__restrict__ hsize, int use_smem_hist)
+             int C, int enc, int8_t *__restrict__ sx, int32_t *__restrict__ hsize,
+             int use_smem_hist)
 {
     extern __shared__ int sh_hist[];
     const int n_hs = C * K1;
@@ -111,10 +113,10 @@ k_state_swar(const uint8_t *__restrict__ xj, const int32_t *__restrict__ y, int6
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t cell = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; cell < N; cell += stride) {
         const int a = xj[cell];
-        int s = PRB_SX_NONE;
+        int s = enc ? 64 : PRB_SX_NONE;
         if (a) {
             const int yy = y ? y[cell] : 0;
-            s = 16 * (a - 1) - 4;
+            s = enc ? 8 * (a - 1) : 16 * (a - 1) - 4;
             atomicAdd(use_smem_hist ? sh_hist + yy * K1 + a - 1 : hsize + yy * K1 + a - 1, 1);
         }
         sx[cell] = (int8_t)s;
@@ -304,7 +306,7 @@ extern "C" int prb_state_direct(const uint8_t *xj, const int32_t *y, int64_t N, 
 }
 
 extern "C" int prb_state_swar(const uint8_t *xj, const int32_t *y, int64_t N, int C, int K,
-                              int8_t *sx, int32_t *hsize, int32_t *hs_begin, int32_t *hs_y,
+                              int enc, int8_t *sx, int32_t *hsize, int32_t *hs_begin, int32_t *hs_y,
                               int32_t *hs_ysum, int32_t *ha, prb_stream_t stream)
 {
     PRB_REQUIRE(N > 0 && N <= PRB_MAX_ROWS, "N out of range");
@@ -314,7 +316,7 @@ extern "C" int prb_state_swar(const uint8_t *xj, const int32_t *y, int64_t N, in
     PRB_CUDA(cudaMemsetAsync(hsize, 0, sizeof(int32_t) * n_hs, S(stream)));
     const int use_smem = n_hs <= 8192;
     k_state_swar<<<cell_grid(N, 256), 256, use_smem ? n_hs * 4 : 0, S(stream)>>>(
-        xj, y, N, K1, C, sx, hsize, use_smem);
+        xj, y, N, K1, C, enc, sx, hsize, use_smem);
     PRB_LAUNCH_CHECK("k_state_swar");
     k_state_direct_sums<<<1, 256, 0, S(stream)>>>(hsize, C, K1, hs_begin, hs_y, hs_ysum, ha,
                                                   nullptr);

@@ -20,6 +20,8 @@
 // of 1 KB TMA bulk copies (cp.async.bulk + mbarrier, 3 blocks in flight per warp, 96 KB
 // per SM); one persistent CTA per SM; (super-tile, gene-chunk) work items claimed
 // dynamically per warp.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace prb {
@@ -106,29 +108,33 @@ __device__ __forceinline__ void flush(Counters &c, int32_t *out, int K1, int lan
     }
 }
 
-// The super-tile's shift codes live in shared memory at index (cell id mod SW_TILE_SPAN):
-// a super-tile spans at most SW_TILE_SPAN consecutive cells, so the mapping is injective
-// and a probe is one AND plus one LDS from a constant base.
-constexpr int SW_TILE_SPAN = 1 << 17;
-
-template <bool COUNT, bool MASKED>
+// The super-tile's shift codes live in shared memory at index (cell id mod SPAN), SPAN a
+// power of two: a super-tile spans at most SPAN consecutive cells, so the mapping is
+// injective and a probe is one AND plus one LDS from a constant base.
+template <bool COUNT, bool MASKED, int SPAN>
 __device__ __forceinline__ void acc(uint32_t w, bool ok, const int8_t *__restrict__ st, Counters &c)
 {
-    uint32_t sh = ((w >> 24) << 2) - 4u;
-    if (!COUNT) sh += 4u + (uint32_t)(int)st[w & (SW_TILE_SPAN - 1)];
+    // field offset = 4*code - 4 (+ 16*(x_j-1), folded into the shift code); multiply-adds
+    // keep this off the (busier) shift/logic pipe
+    uint32_t sh = (w >> 24) * 4u + (COUNT ? 0xFFFFFFFCu : (uint32_t)(int)st[w & (SPAN - 1)]);
     if (MASKED) sh = ok ? sh : 127u;  // >= 64: counts nothing
     c.A += shl1(sh);
     if (!COUNT) c.B += shl1(sh - 32u);
 }
 
 // ---- per-warp TMA ring: the packed stream goes global -> shared with 1-D bulk copies ----
-// (cp.async.bulk, one instruction per 1 KB block, completion on an mbarrier), SW_STAGES
-// blocks in flight per warp without holding registers or LSU issue slots.
+// (cp.async.bulk, one instruction per stage, completion on an mbarrier), STAGES stages of
+// UNITS x 1 KB in flight per warp without holding registers or LSU issue slots.
 constexpr int SW_WARPS = SW_THREADS / 32;
-constexpr int SW_STAGES = 3;
-constexpr int SW_STAGE_BYTES = SW_BLOCK * 4;
-constexpr int SW_RING_BYTES = SW_WARPS * SW_STAGES * SW_STAGE_BYTES;
-constexpr int SW_SMEM_BYTES = SW_TILE_SPAN + SW_RING_BYTES + SW_WARPS * SW_STAGES * 8;
+
+template <int SPAN, int UNITS, int STAGES>
+struct SwarCfg {
+    static constexpr int span = SPAN, units = UNITS, stages = STAGES;
+    static constexpr int stage_entries = UNITS * SW_BLOCK;
+    static constexpr int stage_bytes = stage_entries * 4;
+    static constexpr int ring_bytes = SW_WARPS * STAGES * stage_bytes;
+    static constexpr int smem_bytes = SPAN + ring_bytes + SW_WARPS * STAGES * 8;
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
@@ -172,10 +178,10 @@ struct Walk {
     bool dirty;
 };
 
-// Count one block of 256 entries starting at position blk (16-byte aligned in memory, so the
-// first block of a gene may start below the gene's first entry of this super-tile and the
+// Count one unit of 256 entries starting at position blk (16-byte aligned in memory, so the
+// first unit of a gene may start below the gene's first entry of this super-tile and the
 // last one may run past its end).  Lane l holds entries blk + 128*h + 4*l + j in w[4*h + j].
-template <bool COUNT>
+template <bool COUNT, int SPAN>
 __device__ __forceinline__ void process_block(const uint32_t (&w)[SW_U], int blk,
                                               const int8_t *__restrict__ st, Counters &c,
                                               Walk &k, const int *s_cls, int out_stride, int K1,
@@ -183,9 +189,9 @@ __device__ __forceinline__ void process_block(const uint32_t (&w)[SW_U], int blk
 {
     const int nxt = blk + SW_BLOCK;
     if (k.lo <= blk && k.seg_end > nxt) {
-        // the whole block lies inside the current class segment
+        // the whole unit lies inside the current class segment
 #pragma unroll
-        for (int u = 0; u < SW_U; ++u) acc<COUNT, false>(w[u], true, st, c);
+        for (int u = 0; u < SW_U; ++u) acc<COUNT, false, SPAN>(w[u], true, st, c);
         k.dirty = true;
     } else {
         const int blk_end = min(nxt, k.gend);
@@ -196,13 +202,13 @@ __device__ __forceinline__ void process_block(const uint32_t (&w)[SW_U], int blk
 #pragma unroll
                 for (int u = 0; u < SW_U; ++u) {
                     const int off = (u >> 2) * 128 + (u & 3);
-                    acc<COUNT, true>(w[u], off >= rlo && off < rhi, st, c);
+                    acc<COUNT, true, SPAN>(w[u], off >= rlo && off < rhi, st, c);
                 }
                 k.dirty = true;
                 k.lo = hi;
             }
             if (k.seg_end > blk_end) break;
-            // the segment ends inside (or at the end of) this block
+            // the segment ends inside (or at the end of) this unit
             if (k.dirty) {
                 c.spill4();
                 flush(c, k.oseg, K1, lane);
@@ -221,12 +227,12 @@ __device__ __forceinline__ void process_block(const uint32_t (&w)[SW_U], int blk
 //   seg_cell0 int32[n_seg+1] : cell boundaries of the class segments (ascending, last = N)
 //   seg_class int32[n_seg]   : class of each segment, or NULL (everything counts as class 0)
 //   st_seg0   int32[n_st+1]  : super-tile t = segments [st_seg0[t], st_seg0[t+1]), <= 31 of
-//                              them, spanning <= SW_TILE_SPAN - 16 cells
+//                              them, spanning <= SPAN - 16 cells
 //   tpf       int32[P][n_seg+1] : first stored entry of gene g (relative to indptr[g]) whose
 //                                 cell id is >= seg_cell0[s]
 // packed must be readable up to the next multiple of 16 bytes past its last entry.
 // out: hits int32[P][C][K1][K1]  (COUNT: cnt int32[P][C][K1], every cell has x_j = 1)
-template <bool COUNT>
+template <bool COUNT, typename CFG>
 __global__ void __launch_bounds__(SW_THREADS, 1)
 k_stream_swar(const uint32_t *__restrict__ packed, const int64_t *__restrict__ indptr,
               const int32_t *__restrict__ tpf, int n_seg, int64_t P,
@@ -234,22 +240,24 @@ k_stream_swar(const uint32_t *__restrict__ packed, const int64_t *__restrict__ i
               const int32_t *__restrict__ seg_class, int n_st, const int8_t *__restrict__ sx,
               int K1, int C, int32_t *__restrict__ out, int *counters, int genes_per_item)
 {
+    constexpr int SPAN = CFG::span, UNITS = CFG::units, STAGES = CFG::stages;
+    constexpr int STAGE_ENTRIES = CFG::stage_entries, STAGE_BYTES = CFG::stage_bytes;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ int s_flag;
     __shared__ int s_cls[SW_MAX_SEGS + 1];
     const int8_t *st = (const int8_t *)smem_raw;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    unsigned char *ring = smem_raw + SW_TILE_SPAN + warp * (SW_STAGES * SW_STAGE_BYTES);
+    unsigned char *ring = smem_raw + SPAN + warp * (STAGES * STAGE_BYTES);
     const uint32_t ring_s = smem_u32(ring);
-    const uint32_t bar_s = smem_u32(smem_raw + SW_TILE_SPAN + SW_RING_BYTES) + warp * (SW_STAGES * 8);
+    const uint32_t bar_s = smem_u32(smem_raw + SPAN + CFG::ring_bytes) + warp * (STAGES * 8);
     if (lane == 0) {
 #pragma unroll
-        for (int i = 0; i < SW_STAGES; ++i) mbar_init(bar_s + 8 * i, 1);
+        for (int i = 0; i < STAGES; ++i) mbar_init(bar_s + 8 * i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    int stage = 0;          // next stage to consume (== next to fill once the ring is primed)
-    uint32_t parity = 0;    // bit i: phase parity to wait for on stage i
+    int stage = 0;        // next stage to consume (== next to fill once the ring is primed)
+    uint32_t parity = 0;  // bit i: phase parity to wait for on stage i
     const int n_items = (int)((P + genes_per_item - 1) / genes_per_item);
     const int out_stride = COUNT ? K1 : K1 * K1;
     const int nb = n_seg + 1;
@@ -268,7 +276,7 @@ k_stream_swar(const uint32_t *__restrict__ packed, const int64_t *__restrict__ i
         if (!COUNT) {
             // per-cell shift codes of the super-tile: global -> shared in 16-byte chunks, from
             // the aligned address below its first cell (the buffer is padded), placed at
-            // (cell id mod SW_TILE_SPAN)
+            // (cell id mod SPAN)
             const int64_t c0 = seg_cell0[s0], c1 = seg_cell0[s1];
             const int64_t a0 = c0 & ~int64_t(15);
             const int nvec = (int)((c1 - a0 + 15) >> 4);
@@ -276,7 +284,7 @@ k_stream_swar(const uint32_t *__restrict__ packed, const int64_t *__restrict__ i
             const int v0 = (int)(a0 >> 4);
             uint4 *dst = (uint4 *)smem_raw;
             for (int i = tid; i < nvec; i += SW_THREADS)
-                dst[(v0 + i) & (SW_TILE_SPAN / 16 - 1)] = __ldg(src + i);
+                dst[(v0 + i) & (SPAN / 16 - 1)] = __ldg(src + i);
         }
         __syncthreads();
         for (;;) {
@@ -300,32 +308,45 @@ k_stream_swar(const uint32_t *__restrict__ packed, const int64_t *__restrict__ i
                 k.lo = gpos;
                 k.dirty = false;
                 const int64_t base = __ldg(indptr + g);
-                // blocks are 16-byte aligned in memory: start at or below the first entry
+                // stages are 16-byte aligned in memory: start at or below the first entry
                 const int ea = gpos - (int)((base + gpos) & 3);
                 const uint32_t *src = packed + base + ea;
-                const int nblk = (k.gend - ea + SW_BLOCK - 1) / SW_BLOCK;
+                const int n_ent = k.gend - ea;
+                const int nstg = (n_ent + STAGE_ENTRIES - 1) / STAGE_ENTRIES;
                 auto issue = [&](int b, int s) {
-                    const int rem = k.gend - (ea + b * SW_BLOCK);
-                    const uint32_t bytes = rem >= SW_BLOCK ? SW_STAGE_BYTES : ((rem * 4 + 15) & ~15);
-                    bulk_load(ring_s + s * SW_STAGE_BYTES, src + (int64_t)b * SW_BLOCK, bytes,
+                    const int rem = n_ent - b * STAGE_ENTRIES;
+                    const uint32_t bytes =
+                        rem >= STAGE_ENTRIES ? STAGE_BYTES : ((rem * 4 + 15) & ~15);
+                    bulk_load(ring_s + s * STAGE_BYTES, src + (int64_t)b * STAGE_ENTRIES, bytes,
                               bar_s + 8 * s);
                 };
+                // all copies of the previous gene were consumed: stages [stage, stage + STAGES)
                 if (lane == 0) {
 #pragma unroll
-                    for (int i = 0; i < SW_STAGES; ++i)
-                        if (i < nblk) issue(i, (stage + i) % SW_STAGES);
+                    for (int i = 0; i < STAGES; ++i)
+                        if (i < nstg) issue(i, (stage + i) % STAGES);
                 }
-                for (int b = 0; b < nblk; ++b) {
+                // one copy of the counting code (runtime stage / unit indices): the body is
+                // large and must stay inside the instruction cache
+#pragma unroll 1
+                for (int b = 0; b < nstg; ++b) {
                     mbar_wait(bar_s + 8 * stage, (parity >> stage) & 1u);
                     parity ^= 1u << stage;
-                    const uint4 *rb = (const uint4 *)(ring + stage * SW_STAGE_BYTES);
-                    const uint4 q0 = rb[lane], q1 = rb[32 + lane];
-                    const uint32_t w[SW_U] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-                    __syncwarp();  // every lane has read the stage: refill it
-                    if (lane == 0 && b + SW_STAGES < nblk) issue(b + SW_STAGES, stage);
-                    stage = stage + 1 == SW_STAGES ? 0 : stage + 1;
-                    process_block<COUNT>(w, ea + b * SW_BLOCK, st, c, k, s_cls, out_stride, K1,
-                                         lane);
+                    const int rem = n_ent - b * STAGE_ENTRIES;  // > 0
+                    const int nu = min(UNITS, (rem + SW_BLOCK - 1) / SW_BLOCK);
+                    const uint4 *rb = (const uint4 *)(ring + stage * STAGE_BYTES);
+#pragma unroll 1
+                    for (int h = 0; h < nu; ++h) {
+                        const uint4 q0 = rb[h * 64 + lane], q1 = rb[h * 64 + 32 + lane];
+                        const uint32_t w[SW_U] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+                        if (h == nu - 1) {
+                            __syncwarp();  // every lane has read the stage: refill it
+                            if (lane == 0 && b + STAGES < nstg) issue(b + STAGES, stage);
+                        }
+                        process_block<COUNT, SPAN>(w, ea + b * STAGE_ENTRIES + h * SW_BLOCK, st, c,
+                                                   k, s_cls, out_stride, K1, lane);
+                    }
+                    stage = stage + 1 == STAGES ? 0 : stage + 1;
                 }
                 if (k.dirty) flush(c, k.oseg, K1, lane);
             }
@@ -426,11 +447,38 @@ k_class_sort(const uint32_t *__restrict__ in, const int64_t *__restrict__ indptr
 
 using namespace prb;
 
+// Kernel configurations (cells per super-tile, 1 KB units per stage, stages per warp); all fit
+// the 227 KB of shared memory.  PRB_SWAR_CFG selects one for tuning runs.
+using Cfg0 = SwarCfg<1 << 17, 1, 3>;  // 128 KB of shift codes + 32 warps x 3 x 1 KB
+using Cfg1 = SwarCfg<1 << 16, 2, 2>;  //  64 KB + 32 x 2 x 2 KB
+using Cfg2 = SwarCfg<1 << 16, 1, 5>;  //  64 KB + 32 x 5 x 1 KB
+using Cfg3 = SwarCfg<1 << 16, 1, 3>;  //  64 KB + 32 x 3 x 1 KB (tile-size probe)
+
+static int swar_cfg()
+{
+    static const int cfg = [] {
+        const char *e = getenv("PRB_SWAR_CFG");
+        const int v = e ? atoi(e) : 1;  // measured best on config 4: 64 KB tile, 2 x 2 KB ring
+        return v >= 0 && v <= 3 ? v : 1;
+    }();
+    return cfg;
+}
+
+static int swar_span()
+{
+    switch (swar_cfg()) {
+        case 1: return Cfg1::span;
+        case 2: return Cfg2::span;
+        case 3: return Cfg3::span;
+        default: return Cfg0::span;
+    }
+}
+
 extern "C" int prb_swar_tile_capacity(int64_t *max_cells, int *max_segs)
 {
-    // a super-tile's shift codes sit in shared memory at (cell id mod SW_TILE_SPAN); 16 cells
-    // of slack for the aligned 16-byte copies
-    if (max_cells) *max_cells = SW_TILE_SPAN - 16;
+    // a super-tile's shift codes sit in shared memory at (cell id mod SPAN); 16 cells of
+    // slack for the aligned 16-byte copies
+    if (max_cells) *max_cells = swar_span() - 16;
     if (max_segs) *max_segs = SW_MAX_SEGS;
     return 0;
 }
@@ -456,28 +504,33 @@ extern "C" int prb_stream_swar(const uint32_t *packed, const int64_t *indptr, co
     PRB_REQUIRE(K1 >= 1 && K1 <= 4, "the register-counter path needs K <= 5");
     PRB_REQUIRE(n_seg >= 1 && n_st >= 1 && C >= 1, "bad segment plan");
     const bool count = sx == nullptr;
-    PRB_REQUIRE(max_tile_cells <= SW_TILE_SPAN - 16, "super-tile spans too many cells");
-    const int64_t smem = SW_SMEM_BYTES;
-    PRB_REQUIRE(smem + 256 <= devinfo().smem_optin, "not enough shared memory per block");
+    PRB_REQUIRE(max_tile_cells <= swar_span() - 16, "super-tile spans too many cells");
     PRB_CUDA(cudaMemsetAsync(counters, 0, sizeof(int32_t) * n_st, S(stream)));
     // ~16 work items per warp and super-tile
-    const int64_t warps_per_tile = hmax(1, (int64_t)devinfo().sm_count * (SW_THREADS / 32) / n_st);
+    const int64_t warps_per_tile = hmax(1, (int64_t)devinfo().sm_count * SW_WARPS / n_st);
     const int gpi = (int)hmin(64, hmax(1, P / (warps_per_tile * 16)));
     const int64_t n_items = ceil_div(P, gpi) * n_st;
-    const int grid = (int)hmax(1, hmin(devinfo().sm_count, ceil_div(n_items, SW_THREADS / 32)));
-    if (count) {
-        PRB_CUDA(cudaFuncSetAttribute(k_stream_swar<true>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_stream_swar<true><<<grid, SW_THREADS, smem, S(stream)>>>(
-            packed, indptr, tpf, n_seg, P, st_seg0, seg_cell0, seg_class, n_st, nullptr, K1, C, out,
-            counters, gpi);
-    } else {
-        PRB_CUDA(cudaFuncSetAttribute(k_stream_swar<false>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_stream_swar<false><<<grid, SW_THREADS, smem, S(stream)>>>(
-            packed, indptr, tpf, n_seg, P, st_seg0, seg_cell0, seg_class, n_st, sx, K1, C, out,
-            counters, gpi);
+    const int grid = (int)hmax(1, hmin(devinfo().sm_count, ceil_div(n_items, SW_WARPS)));
+    auto launch = [&](auto kern, int smem) -> int {
+        PRB_REQUIRE(smem + 512 <= devinfo().smem_optin, "not enough shared memory per block");
+        PRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        kern<<<grid, SW_THREADS, smem, S(stream)>>>(packed, indptr, tpf, n_seg, P, st_seg0,
+                                                    seg_cell0, seg_class, n_st, sx, K1, C, out,
+                                                    counters, gpi);
+        return 0;
+    };
+#define PRB_SW(CFG)                                                                    \
+    if (count ? launch(k_stream_swar<true, CFG>, CFG::smem_bytes)                      \
+              : launch(k_stream_swar<false, CFG>, CFG::smem_bytes))                    \
+        return 1;                                                                      \
+    break
+    switch (swar_cfg()) {
+        case 1: PRB_SW(Cfg1);
+        case 2: PRB_SW(Cfg2);
+        case 3: PRB_SW(Cfg3);
+        default: PRB_SW(Cfg0);
     }
+#undef PRB_SW
     PRB_LAUNCH_CHECK("k_stream_swar");
     return 0;
 }

@@ -1,0 +1,468 @@
+// vstream.cu — the hot loop for K <= 5 bins on the "V layout": 4 instructions per entry.
+//
+// Replaces the per-gene two-pointer merge of _sparse_entropy_wrt
+// (picturedrocks/markers/mutualinformation/infoset.py:365-391) for the selectors' calls
+// entropy_wrt([j]) and entropy_wrt([-1, j]) (iterative.py:53, 55); the class-conditional
+// count tables behind entropy_wrt([]) / entropy_wrt([-1]) (iterative.py:30, 32) fall out
+// of the layout's own segment lengths (no streaming pass at all).
+//
+// V layout (a private re-ordering of the packed by-gene CSC; a histogram does not depend
+// on the order in which cells are visited).  Cells are sorted by class (prb_class_sort)
+// and cut into SEGMENTS (a class, or a piece of one that fits a shared-memory tile).
+// Every gene g is split into K-1 VIRTUAL GENES (g, v), one per non-zero code v; the
+// entries of a virtual gene are grouped by segment, ascending inside a segment, and every
+// (g, v, segment) run is padded to a multiple of 32 entries (one 128-byte ROW, one entry
+// per lane).  Inside a run the class AND the candidate's code are known, so the joint
+// histogram of (y, x_j, x_i) restricted to it has only K-1 <= 4 bins (the value of the
+// selected gene x_j): they live in ONE register as four 8-bit fields, and an entry costs
+//     AND (cell id mod tile)  ->  LDS.U8 (shift code of x_j)  ->  SHL  ->  ADD.
+// At the end of a run the fields are summed over the warp (5 shuffles) and added to
+// hits[g][class][x_j-1][v-1].  No shared-memory atomics, no per-entry decode of the code.
+//
+// HBM-bound by design: 4 bytes per stored entry (+ the row padding), read exactly once
+// through a per-warp ring of TMA bulk copies (cp.async.bulk + mbarrier); one persistent
+// CTA per SM; (super-tile, virtual-gene chunk) work items claimed dynamically per warp.
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace prb {
+
+constexpr int V_THREADS = 1024;
+constexpr int V_WARPS = V_THREADS / 32;
+constexpr int V_MAX_SEGS = 31;  // segments per super-tile (32 boundaries = one warp load)
+
+template <int SPAN, int STAGE_ROWS, int STAGES>
+struct VCfg {
+    static constexpr int span = SPAN, stage_rows = STAGE_ROWS, stages = STAGES;
+    static constexpr int stage_bytes = STAGE_ROWS * 128;
+    static constexpr int ring_bytes = V_WARPS * STAGES * stage_bytes;
+    static constexpr int smem_bytes = SPAN + ring_bytes + V_WARPS * STAGES * 8;
+};
+
+__device__ __forceinline__ uint32_t v_smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void v_mbar_init(uint32_t bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void v_bulk_load(uint32_t dst, const void *src, uint32_t bytes,
+                                            uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void v_mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+
+// PTX shl clamps: a shift amount >= 32 gives 0 (the shift code of a cell with x_j = 0).
+__device__ __forceinline__ uint32_t v_shl1(uint32_t s)
+{
+    uint32_t r;
+    asm("shl.b32 %0, 1, %1;" : "=r"(r) : "r"(s));
+    return r;
+}
+
+// Sum the four 8-bit fields of acc over the warp and add them to out[a*K1], a = field.
+// Per-lane fields are <= 255, so 32 lanes fit 16 bits.  woff = a*K1 for the four writer
+// lanes (0, 1, 16, 17 <-> fields 0, 2, 1, 3), -1 elsewhere.
+__device__ __forceinline__ void v_flush(uint32_t &acc, int32_t *out, int woff, int lane)
+{
+    const uint32_t r0 = acc & 0x00FF00FFu;         // fields 0 (low half) and 2 (high half)
+    const uint32_t r1 = (acc >> 8) & 0x00FF00FFu;  // fields 1 and 3
+    acc = 0;
+    const bool hi = lane & 16;
+    uint32_t r = (hi ? r1 : r0) + __shfl_xor_sync(0xffffffffu, hi ? r0 : r1, 16);
+    r += __shfl_xor_sync(0xffffffffu, r, 8);
+    r += __shfl_xor_sync(0xffffffffu, r, 4);
+    r += __shfl_xor_sync(0xffffffffu, r, 2);
+    r += __shfl_xor_sync(0xffffffffu, r, 1);
+    const uint32_t cnt = (lane & 1) ? (r >> 16) : (r & 0xFFFFu);
+    if (woff >= 0 && cnt) atomicAdd(out + woff, (int)cnt);
+}
+
+// Segment plan (host-built, see engine.py):
+//   seg_cell0 int32[n_seg+1] : cell boundaries of the segments (ascending, last = N)
+//   seg_class int32[n_seg]   : class of each segment, or NULL (everything counts as class 0)
+//   st_seg0   int32[n_st+1]  : super-tile t = segments [st_seg0[t], st_seg0[t+1]), <= 31 of
+//                              them, spanning <= SPAN - 32 cells
+// V layout, TILE-MAJOR: rows (32 entries, 128 bytes) ordered by (super-tile, virtual gene,
+// segment), so the virtual genes of one work item are ONE contiguous row range:
+//   run_end   int32[PV][n_seg] : row just past run (vg, s);  PV = P*K1
+//   tile_row0 int32[n_st+1]    : first row of every super-tile's block
+// Padding words of a run point at the cell slot just past their super-tile, which the tile
+// loader sets to "x_j = 0", so every row is counted the same way (no lane masks).
+// sx: uint8[N] shift codes 8*(x_j-1), >= 32 where x_j = 0 (prb_state_swar, enc = 1).
+// hits: int32[P][C][K1][K1], added to.
+template <typename CFG>
+__global__ void __launch_bounds__(V_THREADS, 1)
+k_stream_v(const uint32_t *__restrict__ vpacked, const int32_t *__restrict__ run_end,
+           const int32_t *__restrict__ tile_row0, int n_seg, int64_t PV, int K1,
+           const int32_t *__restrict__ st_seg0, const int32_t *__restrict__ seg_cell0,
+           const int32_t *__restrict__ seg_class, int n_st, const uint8_t *__restrict__ sx, int C,
+           int32_t *__restrict__ hits, int *counters, int vg_per_item)
+{
+    constexpr int SPAN = CFG::span, SR = CFG::stage_rows, STAGES = CFG::stages;
+    constexpr int STAGE_BYTES = CFG::stage_bytes;
+    constexpr int RING_ROWS = SR * STAGES;
+    static_assert((RING_ROWS & (RING_ROWS - 1)) == 0, "ring rows must be a power of two");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ int s_flag;
+    __shared__ int s_cls[V_MAX_SEGS + 1];
+    uint8_t *st = (uint8_t *)smem_raw;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t *ring = (const uint32_t *)(smem_raw + SPAN + warp * (STAGES * STAGE_BYTES)) + lane;
+    const uint32_t ring_s = v_smem_u32(smem_raw + SPAN + warp * (STAGES * STAGE_BYTES));
+    const uint32_t bar_s = v_smem_u32(smem_raw + SPAN + CFG::ring_bytes) + warp * (STAGES * 8);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < STAGES; ++i) v_mbar_init(bar_s + 8 * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    uint32_t parity = 0;  // bit i: phase parity to wait for on barrier i
+    const int n_items = (int)((PV + vg_per_item - 1) / vg_per_item);
+    const int KK = K1 * K1;
+    // writer lanes of v_flush: lanes 0, 1, 16, 17 <-> x_j - 1 = 0, 2, 1, 3
+    const int wa = ((lane >> 4) & 1) + 2 * (lane & 1);
+    const int woff = ((lane & 14) == 0 && wa < K1) ? wa * K1 : -1;
+    uint32_t acc = 0;
+
+    for (int tt = 0; tt < n_st; ++tt) {
+        const int t = (int)((blockIdx.x + tt) % (unsigned)n_st);
+        __syncthreads();  // every warp has left the previous super-tile
+        if (tid == 0) s_flag = *(volatile int *)(counters + t) < n_items;
+        __syncthreads();
+        if (!s_flag) continue;  // already drained by other CTAs
+        const int s0 = st_seg0[t], s1 = st_seg0[t + 1];
+        const int nsg = s1 - s0;
+        if (tid < nsg) s_cls[tid] = (seg_class ? seg_class[s0 + tid] : 0) * KK;
+        const int c1 = seg_cell0[s1];
+        {
+            // shift codes of the super-tile: global -> shared in 16-byte chunks from the aligned
+            // address below its first cell (the buffer is padded), at (cell id mod SPAN)
+            const int64_t c0 = seg_cell0[s0];
+            const int64_t a0 = c0 & ~int64_t(15);
+            const int nvec = (int)((c1 - a0 + 15) >> 4);
+            const uint4 *src = (const uint4 *)(sx + a0);
+            const int v0 = (int)(a0 >> 4);
+            uint4 *dst = (uint4 *)smem_raw;
+            for (int i = tid; i < nvec; i += V_THREADS)
+                dst[(v0 + i) & (SPAN / 16 - 1)] = __ldg(src + i);
+        }
+        __syncthreads();
+        if (tid == 0) st[c1 & (SPAN - 1)] = 64;  // the slot padding words point at: x_j = 0
+        __syncthreads();
+        const int32_t tile_first_row = tile_row0[t];
+        for (;;) {
+            int item = 0;
+            if (lane == 0) item = atomicAdd(counters + t, 1);
+            item = __shfl_sync(0xffffffffu, item, 0);
+            if (item >= n_items) break;
+            const int64_t vg_a = (int64_t)item * vg_per_item;
+            const int64_t vg_b = min(vg_a + vg_per_item, PV);
+            // the item's rows are contiguous: [row_begin, row_begin + nrows)
+            const int row_begin = vg_a ? __ldg(run_end + (vg_a - 1) * n_seg + (s1 - 1)) : tile_first_row;
+            const int nrows = __ldg(run_end + (vg_b - 1) * n_seg + (s1 - 1)) - row_begin;
+            if (nrows <= 0) continue;
+            const uint32_t *src = vpacked + (int64_t)row_begin * 32;
+            const int nstg = (nrows + SR - 1) / SR;
+            auto issue = [&](int b) {  // stage b of this item -> ring slot b % STAGES
+                const int rows = min(SR, nrows - b * SR);
+                const int s = b % STAGES;
+                v_bulk_load(ring_s + s * STAGE_BYTES, src + (int64_t)b * (SR * 32),
+                            (uint32_t)rows * 128u, bar_s + 8 * s);
+            };
+            // all copies of the previous item were consumed: row 0 <-> ring slot 0
+            if (lane == 0) {
+#pragma unroll
+                for (int i = 0; i < STAGES; ++i)
+                    if (i < nstg) issue(i);
+            }
+            int waited = 0, released = 0;  // stages waited for / handed back
+            int r = 0;                     // next row to count (relative to row_begin)
+            int limit = 0;                 // rows below it can be counted without a ring event
+            int r_flush = 0;               // row at which acc was last flushed
+            int64_t g = vg_a / K1;
+            int v = (int)(vg_a - g * K1);
+            int32_t ends_next = lane < nsg ? __ldg(run_end + vg_a * n_seg + s0 + lane) : 0;
+#pragma unroll 1
+            for (int64_t vg = vg_a; vg < vg_b; ++vg) {
+                const int32_t ends = ends_next - row_begin;
+                if (vg + 1 < vg_b && lane < nsg)
+                    ends_next = __ldg(run_end + (vg + 1) * n_seg + s0 + lane);
+                int32_t *og = hits + g * (int64_t)C * KK + v;
+                if (++v == K1) {
+                    v = 0;
+                    ++g;
+                }
+#pragma unroll 1
+                for (int seg = 0; seg < nsg; ++seg) {
+                    const int e = __shfl_sync(0xffffffffu, ends, seg);
+                    if (e == r) continue;  // empty run
+                    for (;;) {
+                        const int stop = min(min(e, limit), r_flush + 255);
+                        const uint32_t *rp = ring + (r & (RING_ROWS - 1)) * 32;
+                        const uint32_t *rp_end = rp + (stop - r) * 32;
+#pragma unroll 1
+                        for (; rp + 96 < rp_end; rp += 128) {
+                            const uint32_t w0 = rp[0], w1 = rp[32], w2 = rp[64], w3 = rp[96];
+                            const uint32_t x0 = st[w0 & (SPAN - 1)], x1 = st[w1 & (SPAN - 1)];
+                            const uint32_t x2 = st[w2 & (SPAN - 1)], x3 = st[w3 & (SPAN - 1)];
+                            acc += v_shl1(x0) + v_shl1(x1) + v_shl1(x2) + v_shl1(x3);
+                        }
+#pragma unroll 1
+                        for (; rp < rp_end; rp += 32) acc += v_shl1(st[rp[0] & (SPAN - 1)]);
+                        r = stop;
+                        if (r == e) break;
+                        if (r == r_flush + 255) {  // the 8-bit fields are full
+                            v_flush(acc, og + s_cls[seg], woff, lane);
+                            r_flush = r;
+                        }
+                        if (r == limit) {
+                            // ring event: hand fully counted stages back to the copy engine,
+                            // wait for the stage that holds row r
+                            while ((released + 1) * SR <= r) {
+                                __syncwarp();  // every lane has read the stage
+                                if (lane == 0 && released + STAGES < nstg) issue(released + STAGES);
+                                ++released;
+                            }
+                            while (waited * SR <= r) {
+                                const int s = waited % STAGES;
+                                v_mbar_wait(bar_s + 8 * s, (parity >> s) & 1u);
+                                parity ^= 1u << s;
+                                ++waited;
+                            }
+                            limit = min(min(nrows, waited * SR), (r | (RING_ROWS - 1)) + 1);
+                        }
+                    }
+                    v_flush(acc, og + s_cls[seg], woff, lane);
+                    r_flush = r;
+                }
+            }
+            __syncwarp();  // the ring is free for the next item
+        }
+    }
+}
+
+// ---- building the V layout -------------------------------------------------------------
+// pass 1: per gene, entries per (code, segment) -> seglen[P*K1][n_seg].  One warp per gene
+// (dynamic queue), shared-memory histogram per warp.
+constexpr int VB_WARPS = 8;
+
+__global__ void __launch_bounds__(VB_WARPS * 32)
+k_vcount(const uint32_t *__restrict__ packed, const int64_t *__restrict__ indptr, int64_t P,
+         const int32_t *__restrict__ seg_of_cell, int n_seg, int K1,
+         int32_t *__restrict__ seglen, int *queue)
+{
+    extern __shared__ int vb_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nk = K1 * n_seg;
+    int *cnt = vb_smem + warp * nk;
+    for (;;) {
+        int gi = 0;
+        if (lane == 0) gi = atomicAdd(queue, 1);
+        const int64_t g = __shfl_sync(0xffffffffu, gi, 0);
+        if (g >= P) break;
+        const int64_t b = indptr[g], e = indptr[g + 1];
+        for (int i = lane; i < nk; i += 32) cnt[i] = 0;
+        __syncwarp();
+        for (int64_t i = b + lane; i < e; i += 32) {
+            const uint32_t w = packed[i];
+            atomicAdd(cnt + ((w >> 24) - 1u) * n_seg + seg_of_cell[w & ROW_MASK], 1);
+        }
+        __syncwarp();
+        for (int i = lane; i < nk; i += 32) seglen[g * nk + i] = cnt[i];
+        __syncwarp();
+    }
+}
+
+// pass 2: ordered scatter into the padded runs (rank inside a 32-entry group by
+// __match_any_sync keeps the ascending cell order inside a run); run (vg, s) occupies rows
+// [run_end - ceil(len/32), run_end); the padding words of segment s are
+// seg_pad[s] = 0xFF000000 | (a cell slot the kernel keeps at "x_j = 0").
+__global__ void __launch_bounds__(VB_WARPS * 32)
+k_vscatter(const uint32_t *__restrict__ packed, const int64_t *__restrict__ indptr, int64_t P,
+           const int32_t *__restrict__ seg_of_cell, int n_seg, int K1,
+           const int32_t *__restrict__ seglen, const int32_t *__restrict__ run_end,
+           const uint32_t *__restrict__ seg_pad, uint32_t *__restrict__ vpacked, int *queue)
+{
+    extern __shared__ int64_t vb_smem64[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nk = K1 * n_seg;
+    int64_t *off = vb_smem64 + warp * nk;  // next free slot of every run
+    for (;;) {
+        int gi = 0;
+        if (lane == 0) gi = atomicAdd(queue, 1);
+        const int64_t g = __shfl_sync(0xffffffffu, gi, 0);
+        if (g >= P) break;
+        const int64_t b = indptr[g], e = indptr[g + 1];
+        for (int i = lane; i < nk; i += 32) {
+            const int nr = (seglen[g * nk + i] + 31) >> 5;
+            off[i] = (int64_t)(run_end[g * nk + i] - nr) * 32;
+        }
+        __syncwarp();
+        for (int64_t i0 = b; i0 < e; i0 += 32) {
+            const int64_t i = i0 + lane;
+            const bool valid = i < e;
+            const unsigned act = __ballot_sync(0xffffffffu, valid);
+            if (valid) {
+                const uint32_t w = packed[i];
+                const int key = (int)((w >> 24) - 1u) * n_seg + seg_of_cell[w & ROW_MASK];
+                const unsigned m = __match_any_sync(act, key);
+                const int rank = __popc(m & ((1u << lane) - 1u));
+                const int64_t base = off[key];
+                vpacked[base + rank] = w;
+                __syncwarp(act);
+                if (rank == 0) off[key] = base + __popc(m);
+            }
+            __syncwarp();
+        }
+        // padding up to the end of the run's last row
+        for (int i = lane; i < nk; i += 32) {
+            const int s = i % n_seg;
+            const int64_t end = (int64_t)run_end[g * nk + i] * 32;
+            const uint32_t padw = seg_pad[s];
+            for (int64_t p = off[i]; p < end; ++p) vpacked[p] = padw;
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace prb
+
+using namespace prb;
+
+// Kernel configurations (cells per super-tile, rows per stage, stages per warp); all fit the
+// 227 KB of shared memory.  PRB_V_CFG selects one for tuning runs.
+using VCfg0 = VCfg<1 << 16, 16, 2>;  //  64 KB of shift codes + 32 warps x 2 x 2 KB
+using VCfg1 = VCfg<1 << 16, 8, 4>;   //  64 KB + 32 x 4 x 1 KB
+using VCfg2 = VCfg<1 << 17, 8, 2>;   // 128 KB + 32 x 2 x 1 KB
+using VCfg3 = VCfg<1 << 16, 8, 2>;   //  64 KB + 32 x 2 x 1 KB
+
+static int v_cfg()
+{
+    static const int cfg = [] {
+        const char *e = getenv("PRB_V_CFG");
+        const int v = e ? atoi(e) : 0;
+        return v >= 0 && v <= 3 ? v : 0;
+    }();
+    return cfg;
+}
+
+static int v_span()
+{
+    switch (v_cfg()) {
+        case 1: return VCfg1::span;
+        case 2: return VCfg2::span;
+        case 3: return VCfg3::span;
+        default: return VCfg0::span;
+    }
+}
+
+extern "C" int prb_v_tile_span(void) { return v_span(); }
+
+extern "C" int prb_v_tile_capacity(int64_t *max_cells, int *max_segs)
+{
+    // a super-tile's shift codes sit in shared memory at (cell id mod SPAN); 16 cells of
+    // slack for the aligned 16-byte copies + the slot the padding words point at
+    if (max_cells) *max_cells = v_span() - 32;
+    if (max_segs) *max_segs = V_MAX_SEGS;
+    return 0;
+}
+
+extern "C" int prb_v_count(const uint32_t *packed, const int64_t *indptr, int64_t P,
+                           const int32_t *seg_of_cell, int n_seg, int K1, int32_t *seglen,
+                           int32_t *queue, prb_stream_t stream)
+{
+    if (P == 0) return 0;
+    PRB_REQUIRE(K1 >= 1 && K1 <= 4 && n_seg >= 1, "bad arguments");
+    const size_t smem = (size_t)VB_WARPS * K1 * n_seg * 4;
+    PRB_REQUIRE((int64_t)smem <= devinfo().smem_optin - 1024, "too many segments");
+    PRB_CUDA(cudaFuncSetAttribute(k_vcount, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PRB_CUDA(cudaMemsetAsync(queue, 0, sizeof(int32_t), S(stream)));
+    const int grid = (int)hmin(ceil_div(P, VB_WARPS), (int64_t)devinfo().sm_count * 8);
+    k_vcount<<<grid, VB_WARPS * 32, smem, S(stream)>>>(packed, indptr, P, seg_of_cell, n_seg, K1,
+                                                       seglen, queue);
+    PRB_LAUNCH_CHECK("k_vcount");
+    return 0;
+}
+
+extern "C" int prb_v_scatter(const uint32_t *packed, const int64_t *indptr, int64_t P,
+                             const int32_t *seg_of_cell, int n_seg, int K1, const int32_t *seglen,
+                             const int32_t *run_end, const uint32_t *seg_pad, uint32_t *vpacked,
+                             int32_t *queue, prb_stream_t stream)
+{
+    if (P == 0) return 0;
+    PRB_REQUIRE(K1 >= 1 && K1 <= 4 && n_seg >= 1, "bad arguments");
+    const size_t smem = (size_t)VB_WARPS * K1 * n_seg * 8;
+    PRB_REQUIRE((int64_t)smem <= devinfo().smem_optin - 1024, "too many segments");
+    PRB_CUDA(cudaFuncSetAttribute(k_vscatter, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    PRB_CUDA(cudaMemsetAsync(queue, 0, sizeof(int32_t), S(stream)));
+    const int grid = (int)hmin(ceil_div(P, VB_WARPS), (int64_t)devinfo().sm_count * 8);
+    k_vscatter<<<grid, VB_WARPS * 32, smem, S(stream)>>>(packed, indptr, P, seg_of_cell, n_seg, K1,
+                                                         seglen, run_end, seg_pad, vpacked, queue);
+    PRB_LAUNCH_CHECK("k_vscatter");
+    return 0;
+}
+
+extern "C" int prb_stream_v(const uint32_t *vpacked, const int32_t *run_end,
+                            const int32_t *tile_row0, int n_seg, int64_t P, int K1,
+                            int64_t v_rows, const int32_t *st_seg0, const int32_t *seg_cell0,
+                            const int32_t *seg_class, int n_st, int64_t max_tile_cells,
+                            const uint8_t *sx, int C, int32_t *hits, int32_t *counters,
+                            prb_stream_t stream)
+{
+    if (P == 0 || v_rows == 0) return 0;
+    PRB_REQUIRE(K1 >= 1 && K1 <= 4, "the register-counter path needs K <= 5");
+    PRB_REQUIRE(n_seg >= 1 && n_st >= 1 && C >= 1 && sx != nullptr, "bad segment plan");
+    PRB_REQUIRE(max_tile_cells <= v_span() - 32, "super-tile spans too many cells");
+    PRB_CUDA(cudaMemsetAsync(counters, 0, sizeof(int32_t) * n_st, S(stream)));
+    const int64_t PV = P * K1;
+    // ~16 work items per warp and super-tile
+    const int64_t warps_per_tile = hmax(1, (int64_t)devinfo().sm_count * V_WARPS / n_st);
+    const int gpi = (int)hmin(1024, hmax(1, PV / (warps_per_tile * 16)));
+    const int64_t n_items = ceil_div(PV, gpi) * n_st;
+    const int grid = (int)hmax(1, hmin(devinfo().sm_count, ceil_div(n_items, V_WARPS)));
+    auto launch = [&](auto kern, int smem) -> int {
+        PRB_REQUIRE(smem + 512 <= devinfo().smem_optin, "not enough shared memory per block");
+        PRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        kern<<<grid, V_THREADS, smem, S(stream)>>>(vpacked, run_end, tile_row0, n_seg, PV, K1,
+                                                   st_seg0, seg_cell0, seg_class, n_st, sx, C, hits,
+                                                   counters, gpi);
+        return 0;
+    };
+    switch (v_cfg()) {
+        case 1:
+            if (launch(k_stream_v<VCfg1>, VCfg1::smem_bytes)) return 1;
+            break;
+        case 2:
+            if (launch(k_stream_v<VCfg2>, VCfg2::smem_bytes)) return 1;
+            break;
+        case 3:
+            if (launch(k_stream_v<VCfg3>, VCfg3::smem_bytes)) return 1;
+            break;
+        default:
+            if (launch(k_stream_v<VCfg0>, VCfg0::smem_bytes)) return 1;
+    }
+    PRB_LAUNCH_CHECK("k_stream_v");
+    return 0;
+}

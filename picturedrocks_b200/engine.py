@@ -26,6 +26,8 @@ _I16_MAX_BINS = 65536
 # K <= 5: class-sorted cells + register counters (csrc/swar.cu); PRB_NO_SWAR=1 forces the
 # generic shared-histogram kernel (csrc/stream.cu) everywhere
 USE_SWAR = os.environ.get("PRB_NO_SWAR", "0") != "1"
+# which register-counter kernel: "v" = csrc/vstream.cu (V layout, default), "16" = csrc/swar.cu
+SWAR_MODE = os.environ.get("PRB_SWAR_MODE", "v")
 PACKED_PAD = 4  # words of slack after the last stored entry
 
 
@@ -87,6 +89,8 @@ class Engine:
         self._tps = {}
         self._swar = {}
         self.swar = USE_SWAR and self.K1 <= 4
+        self.vmode = self.swar and SWAR_MODE == "v"
+        self.v = None  # V layout (csrc/vstream.cu): dict(vpacked, vindptr, tpf2, seglen, nnz)
         self.cell_of_pos = None  # int64[N]: original cell id at each position (None = identity)
         self.classsizes_host = None
         self.gene_ptr = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -140,6 +144,8 @@ class Engine:
         which every cell is a "master row" whose state is its class)."""
         if C * self.K1 > _I16_MAX_BINS:
             raise NotImplementedError("classes x codes exceeds 65536 histogram bins")
+        if self.vmode:
+            return self._count_table_v(y is not None, C)
         cnt = torch.zeros(max(self.P * C * self.K1, 1), dtype=torch.int32, device=self.device)
         if self.swar:
             self._stream_swar(y is not None, None, C, cnt)
@@ -178,11 +184,12 @@ class Engine:
             self.packed = out
             self.cell_of_pos = order if self.cell_of_pos is None else self.cell_of_pos[order]
             y_cur = y_cur[order]
-            self._tps, self._swar = {}, {}
+            self._tps, self._swar, self.v = {}, {}, None
         self.has_y, self.y, self.C = True, y_cur.contiguous(), C
         self.classsizes = torch.bincount(self.y, minlength=C).to(torch.int64)
         self.classsizes_host = [int(v) for v in self.classsizes.cpu().numpy()]
         self._swar.pop(True, None)
+        self.v = None
         self.cnt_y = self._count_table(self.y, C)
 
     # ------------------------------------------------ register-counter path (K <= 5)
@@ -193,7 +200,8 @@ class Engine:
         if pl is not None:
             return pl
         cap, max_segs = ctypes.c_int64(), ctypes.c_int()
-        nat.call("prb_swar_tile_capacity", ctypes.byref(cap), ctypes.byref(max_segs))
+        nat.call("prb_v_tile_capacity" if self.vmode else "prb_swar_tile_capacity",
+                 ctypes.byref(cap), ctypes.byref(max_segs))
         cap = max(128, min(int(os.environ.get("PRB_SWAR_TILE_CELLS", cap.value)), cap.value))
         sizes = self.classsizes_host if classes else [self.N]
         cell0, cls, pos = [], [], 0
@@ -222,10 +230,13 @@ class Engine:
             raise NotImplementedError("too many cell tiles")
         max_cells = max(cell0[st[t + 1]] - cell0[st[t]] for t in range(n_st))
         i32 = dict(dtype=torch.int32, device=self.device)
-        pl = dict(n_seg=n_seg, n_st=n_st, max_cells=max_cells,
+        pl = dict(n_seg=n_seg, n_st=n_st, max_cells=max_cells, classes=classes,
                   seg_cell0=torch.tensor(cell0, **i32), st_seg0=torch.tensor(st, **i32),
-                  seg_class=torch.tensor(cls, **i32) if classes else None,
-                  tpf=torch.empty(max(self.P, 1) * (n_seg + 1), **i32))
+                  seg_class=torch.tensor(cls, **i32) if classes else None)
+        if self.vmode:
+            self._swar[classes] = pl
+            return pl
+        pl["tpf"] = torch.empty(max(self.P, 1) * (n_seg + 1), **i32)
         if self.P:
             nat.call("prb_seg_ptrs", nat.ptr(self.packed), nat.ptr(self.indptr), self.P,
                      nat.ptr(pl["seg_cell0"]), n_seg, nat.ptr(pl["tpf"]), nat.stream())
@@ -250,6 +261,88 @@ class Engine:
                  pl["n_seg"], self.P, self.nnz, nat.ptr(pl["st_seg0"]), nat.ptr(pl["seg_cell0"]),
                  nat.ptr(pl["seg_class"]), pl["n_st"], pl["max_cells"], nat.ptr(sx), self.K1, C,
                  nat.ptr(out), nat.ptr(self.counters), nat.stream())
+
+    # ------------------------------------------------ V layout (csrc/vstream.cu)
+    def _build_v(self):
+        """Re-order the (class-sorted) packed CSC into the V layout for the current segment
+        plan: (gene, code) virtual genes, runs per segment padded to 32-entry rows."""
+        classes = self.has_y
+        pl = self._swar_plan(classes)
+        P, K1, n_seg, dev = self.P, self.K1, pl["n_seg"], self.device
+        seg_of_cell = torch.bucketize(torch.arange(self.N, dtype=torch.int32, device=dev),
+                                      pl["seg_cell0"][1:-1].contiguous(), right=True).to(torch.int32)
+        PV = max(P * K1, 1)
+        seglen = torch.zeros(PV * n_seg, dtype=torch.int32, device=dev)
+        nat.call("prb_v_count", nat.ptr(self.packed), nat.ptr(self.indptr), P,
+                 nat.ptr(seg_of_cell), n_seg, K1, nat.ptr(seglen), nat.ptr(self.counters),
+                 nat.stream())
+        # rows of every run, scanned in storage order: (super-tile, virtual gene, segment)
+        span = nat.load().prb_v_tile_span()
+        cell0, st = pl["seg_cell0"].cpu().tolist(), pl["st_seg0"].cpu().tolist()
+        nr = (seglen.view(PV, n_seg) + 31) >> 5
+        run_end = torch.empty((PV, n_seg), dtype=torch.int32, device=dev)
+        tile_row0, base = [0], 0
+        pad = np.zeros(n_seg, dtype=np.int64)
+        for t in range(pl["n_st"]):
+            a, b = st[t], st[t + 1]
+            cs = torch.cumsum(nr[:, a:b].reshape(-1), 0, dtype=torch.int64) + base
+            base = int(cs[-1].item())
+            if base >= (1 << 31):
+                raise NotImplementedError("more than 2^31 rows in the V layout")
+            run_end[:, a:b] = cs.view(PV, b - a).to(torch.int32)
+            tile_row0.append(base)
+            # padding words point at the cell slot just past the run's super-tile
+            pad[a:b] = 0xFF000000 | (cell0[b] & (span - 1))
+        v_rows = base
+        seg_pad = torch.from_numpy(pad.astype(np.uint32).view(np.int32)).to(dev)
+        vpacked = torch.empty(v_rows * 32 + PACKED_PAD, dtype=torch.int32, device=dev)
+        nat.call("prb_v_scatter", nat.ptr(self.packed), nat.ptr(self.indptr), P,
+                 nat.ptr(seg_of_cell), n_seg, K1, nat.ptr(seglen), nat.ptr(run_end),
+                 nat.ptr(seg_pad), nat.ptr(vpacked), nat.ptr(self.counters), nat.stream())
+        self.v = dict(plan=pl, vpacked=vpacked, run_end=run_end, seglen=seglen, rows=v_rows,
+                      tile_row0=torch.tensor(tile_row0, dtype=torch.int32, device=dev))
+        self.epoch += 1
+        return self.v
+
+    def _v(self):
+        return self.v if self.v is not None else self._build_v()
+
+    def _count_table_v(self, with_classes, C):
+        """cnt[g][c][v-1] from the run lengths of the V layout (no streaming pass)."""
+        v = self._v()
+        pl = v["plan"]
+        L = v["seglen"].view(max(self.P * self.K1, 1), pl["n_seg"])[: self.P * self.K1]
+        L = L.view(self.P, self.K1, pl["n_seg"])
+        if not with_classes or pl["seg_class"] is None:
+            cnt = L.sum(2, dtype=torch.int32).view(self.P, 1, self.K1)
+        else:
+            cnt = torch.zeros((self.P, self.K1, C), dtype=torch.int32, device=self.device)
+            cnt.index_add_(2, pl["seg_class"].long(), L)
+            cnt = cnt.permute(0, 2, 1)
+        cnt = cnt.contiguous().view(-1)
+        return cnt if cnt.numel() else torch.zeros(1, dtype=torch.int32, device=self.device)
+
+    def _stream_v(self, with_y, sx, C, hits):
+        ev = getattr(self, "profile_events", None)
+        if ev is not None:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            self._stream_v_launch(with_y, sx, C, hits)
+            e1.record()
+            ev.append((e0, e1))
+        else:
+            self._stream_v_launch(with_y, sx, C, hits)
+
+    def _stream_v_launch(self, with_y, sx, C, hits):
+        v = self._v()
+        pl = v["plan"]
+        nat.call("prb_stream_v", nat.ptr(v["vpacked"]), nat.ptr(v["run_end"]),
+                 nat.ptr(v["tile_row0"]), pl["n_seg"], self.P, self.K1, v["rows"],
+                 nat.ptr(pl["st_seg0"]),
+                 nat.ptr(pl["seg_cell0"]), nat.ptr(pl["seg_class"]) if with_y else None,
+                 pl["n_st"], pl["max_cells"], nat.ptr(sx), C, nat.ptr(hits),
+                 nat.ptr(self.counters), nat.stream())
 
     # --------------------------------------------------------------- primitives
     def hits_buffer(self, n_bins):
@@ -320,10 +413,14 @@ class Engine:
         self.scatter_selected_gene()
         if self.swar:
             nat.call("prb_state_swar", nat.ptr(self.xj), nat.ptr(y), self.N, C, self.K,
-                     nat.ptr(self.state_buf), nat.ptr(self.hsize), nat.ptr(self.hs_begin),
-                     nat.ptr(self.hs_y), nat.ptr(self.hs_ysum), nat.ptr(self.ha), nat.stream())
+                     1 if self.vmode else 0, nat.ptr(self.state_buf), nat.ptr(self.hsize),
+                     nat.ptr(self.hs_begin), nat.ptr(self.hs_y), nat.ptr(self.hs_ysum),
+                     nat.ptr(self.ha), nat.stream())
             hits = self.hits_buffer(n_bins)
-            self._stream_swar(with_y, self.state_buf, C, hits)
+            if self.vmode:
+                self._stream_v(with_y, self.state_buf, C, hits)
+            else:
+                self._stream_swar(with_y, self.state_buf, C, hits)
             self._finalize(hits, cnt, clsz, C, n_hs, None, out_full, out_marg, True)
             return
         sb = self._plan(n_hs)[3]
