@@ -28,16 +28,15 @@
 
 namespace prb {
 
-constexpr int V_THREADS = 1024;
-constexpr int V_WARPS = V_THREADS / 32;
 constexpr int V_MAX_SEGS = 31;  // segments per super-tile (32 boundaries = one warp load)
 
-template <int SPAN, int STAGE_ROWS, int STAGES>
+template <int SPAN, int STAGE_ROWS, int STAGES, int WARPS>
 struct VCfg {
-    static constexpr int span = SPAN, stage_rows = STAGE_ROWS, stages = STAGES;
+    static constexpr int span = SPAN, stage_rows = STAGE_ROWS, stages = STAGES, warps = WARPS;
+    static constexpr int threads = WARPS * 32;
     static constexpr int stage_bytes = STAGE_ROWS * 128;
-    static constexpr int ring_bytes = V_WARPS * STAGES * stage_bytes;
-    static constexpr int smem_bytes = SPAN + ring_bytes + V_WARPS * STAGES * 8;
+    static constexpr int ring_bytes = WARPS * STAGES * stage_bytes;
+    static constexpr int smem_bytes = SPAN + ring_bytes + WARPS * STAGES * 8;
 };
 
 __device__ __forceinline__ uint32_t v_smem_u32(const void *p)
@@ -80,21 +79,16 @@ __device__ __forceinline__ uint32_t v_shl1(uint32_t s)
     return r;
 }
 
-// Sum the four 8-bit fields of acc over the warp and add them to out[a*K1], a = field.
-// Per-lane fields are <= 255, so 32 lanes fit 16 bits.  woff = a*K1 for the four writer
-// lanes (0, 1, 16, 17 <-> fields 0, 2, 1, 3), -1 elsewhere.
+// Sum the four 8-bit fields of acc over the warp (two REDUX.SUM on 16-bit field pairs: a
+// per-lane field is <= 255, so 32 lanes fit 16 bits) and add field a to out[a*K1].
+// woff = lane*K1 for the writer lanes 0..K1-1, -1 elsewhere.
 __device__ __forceinline__ void v_flush(uint32_t &acc, int32_t *out, int woff, int lane)
 {
-    const uint32_t r0 = acc & 0x00FF00FFu;         // fields 0 (low half) and 2 (high half)
-    const uint32_t r1 = (acc >> 8) & 0x00FF00FFu;  // fields 1 and 3
+    const uint32_t s02 = __reduce_add_sync(0xffffffffu, acc & 0x00FF00FFu);         // fields 0, 2
+    const uint32_t s13 = __reduce_add_sync(0xffffffffu, (acc >> 8) & 0x00FF00FFu);  // fields 1, 3
     acc = 0;
-    const bool hi = lane & 16;
-    uint32_t r = (hi ? r1 : r0) + __shfl_xor_sync(0xffffffffu, hi ? r0 : r1, 16);
-    r += __shfl_xor_sync(0xffffffffu, r, 8);
-    r += __shfl_xor_sync(0xffffffffu, r, 4);
-    r += __shfl_xor_sync(0xffffffffu, r, 2);
-    r += __shfl_xor_sync(0xffffffffu, r, 1);
-    const uint32_t cnt = (lane & 1) ? (r >> 16) : (r & 0xFFFFu);
+    const uint32_t sv = (lane & 1) ? s13 : s02;
+    const uint32_t cnt = (lane & 2) ? (sv >> 16) : (sv & 0xFFFFu);
     if (woff >= 0 && cnt) atomicAdd(out + woff, (int)cnt);
 }
 
@@ -112,7 +106,7 @@ __device__ __forceinline__ void v_flush(uint32_t &acc, int32_t *out, int woff, i
 // sx: uint8[N] shift codes 8*(x_j-1), >= 32 where x_j = 0 (prb_state_swar, enc = 1).
 // hits: int32[P][C][K1][K1], added to.
 template <typename CFG>
-__global__ void __launch_bounds__(V_THREADS, 1)
+__global__ void __launch_bounds__(CFG::threads, 1)
 k_stream_v(const uint32_t *__restrict__ vpacked, const int32_t *__restrict__ run_end,
            const int32_t *__restrict__ tile_row0, int n_seg, int64_t PV, int K1,
            const int32_t *__restrict__ st_seg0, const int32_t *__restrict__ seg_cell0,
@@ -120,7 +114,7 @@ k_stream_v(const uint32_t *__restrict__ vpacked, const int32_t *__restrict__ run
            int32_t *__restrict__ hits, int *counters, int vg_per_item)
 {
     constexpr int SPAN = CFG::span, SR = CFG::stage_rows, STAGES = CFG::stages;
-    constexpr int STAGE_BYTES = CFG::stage_bytes;
+    constexpr int STAGE_BYTES = CFG::stage_bytes, THREADS = CFG::threads;
     constexpr int RING_ROWS = SR * STAGES;
     static_assert((RING_ROWS & (RING_ROWS - 1)) == 0, "ring rows must be a power of two");
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -140,9 +134,7 @@ k_stream_v(const uint32_t *__restrict__ vpacked, const int32_t *__restrict__ run
     uint32_t parity = 0;  // bit i: phase parity to wait for on barrier i
     const int n_items = (int)((PV + vg_per_item - 1) / vg_per_item);
     const int KK = K1 * K1;
-    // writer lanes of v_flush: lanes 0, 1, 16, 17 <-> x_j - 1 = 0, 2, 1, 3
-    const int wa = ((lane >> 4) & 1) + 2 * (lane & 1);
-    const int woff = ((lane & 14) == 0 && wa < K1) ? wa * K1 : -1;
+    const int woff = lane < K1 ? lane * K1 : -1;  // writer lanes of v_flush
     uint32_t acc = 0;
 
     for (int tt = 0; tt < n_st; ++tt) {
@@ -164,7 +156,7 @@ k_stream_v(const uint32_t *__restrict__ vpacked, const int32_t *__restrict__ run
             const uint4 *src = (const uint4 *)(sx + a0);
             const int v0 = (int)(a0 >> 4);
             uint4 *dst = (uint4 *)smem_raw;
-            for (int i = tid; i < nvec; i += V_THREADS)
+            for (int i = tid; i < nvec; i += THREADS)
                 dst[(v0 + i) & (SPAN / 16 - 1)] = __ldg(src + i);
         }
         __syncthreads();
@@ -182,24 +174,30 @@ k_stream_v(const uint32_t *__restrict__ vpacked, const int32_t *__restrict__ run
             const int row_begin = vg_a ? __ldg(run_end + (vg_a - 1) * n_seg + (s1 - 1)) : tile_first_row;
             const int nrows = __ldg(run_end + (vg_b - 1) * n_seg + (s1 - 1)) - row_begin;
             if (nrows <= 0) continue;
-            const uint32_t *src = vpacked + (int64_t)row_begin * 32;
             const int nstg = (nrows + SR - 1) / SR;
-            auto issue = [&](int b) {  // stage b of this item -> ring slot b % STAGES
-                const int rows = min(SR, nrows - b * SR);
-                const int s = b % STAGES;
-                v_bulk_load(ring_s + s * STAGE_BYTES, src + (int64_t)b * (SR * 32),
-                            (uint32_t)rows * 128u, bar_s + 8 * s);
+            // stage b of the item lives in ring slot b % STAGES; row 0 <-> ring slot 0 (all
+            // copies of the previous item were consumed)
+            const uint32_t *src_next = vpacked + (int64_t)row_begin * 32;  // next stage to issue
+            int rows_unissued = nrows;
+            int issue_slot = 0;
+            auto issue = [&]() {
+                const int rows = min(SR, rows_unissued);
+                v_bulk_load(ring_s + issue_slot * STAGE_BYTES, src_next, (uint32_t)rows * 128u,
+                            bar_s + 8 * issue_slot);
+                src_next += SR * 32;
+                rows_unissued -= SR;
+                issue_slot = issue_slot + 1 == STAGES ? 0 : issue_slot + 1;
             };
-            // all copies of the previous item were consumed: row 0 <-> ring slot 0
             if (lane == 0) {
 #pragma unroll
                 for (int i = 0; i < STAGES; ++i)
-                    if (i < nstg) issue(i);
+                    if (i < nstg) issue();
             }
-            int waited = 0, released = 0;  // stages waited for / handed back
-            int r = 0;                     // next row to count (relative to row_begin)
-            int limit = 0;                 // rows below it can be counted without a ring event
-            int r_flush = 0;               // row at which acc was last flushed
+            int wait_slot = 0;  // ring slot of the next stage to wait for
+            int r = 0;          // next row to count (relative to row_begin)
+            int limit = 0;      // rows below it are in shared memory (next stage boundary)
+            int fb = 255;       // row at which the 8-bit fields could overflow
+            const uint32_t *rp = ring;  // lane's word of row r
             int64_t g = vg_a / K1;
             int v = (int)(vg_a - g * K1);
             int32_t ends_next = lane < nsg ? __ldg(run_end + vg_a * n_seg + s0 + lane) : 0;
@@ -217,9 +215,9 @@ k_stream_v(const uint32_t *__restrict__ vpacked, const int32_t *__restrict__ run
                 for (int seg = 0; seg < nsg; ++seg) {
                     const int e = __shfl_sync(0xffffffffu, ends, seg);
                     if (e == r) continue;  // empty run
+                    int32_t *oseg = og + s_cls[seg];
                     for (;;) {
-                        const int stop = min(min(e, limit), r_flush + 255);
-                        const uint32_t *rp = ring + (r & (RING_ROWS - 1)) * 32;
+                        const int stop = min(min(e, limit), fb);
                         const uint32_t *rp_end = rp + (stop - r) * 32;
 #pragma unroll 1
                         for (; rp + 96 < rp_end; rp += 128) {
@@ -232,29 +230,26 @@ k_stream_v(const uint32_t *__restrict__ vpacked, const int32_t *__restrict__ run
                         for (; rp < rp_end; rp += 32) acc += v_shl1(st[rp[0] & (SPAN - 1)]);
                         r = stop;
                         if (r == e) break;
-                        if (r == r_flush + 255) {  // the 8-bit fields are full
-                            v_flush(acc, og + s_cls[seg], woff, lane);
-                            r_flush = r;
+                        if (r == fb) {  // the 8-bit fields are full
+                            v_flush(acc, oseg, woff, lane);
+                            fb = r + 255;
                         }
                         if (r == limit) {
-                            // ring event: hand fully counted stages back to the copy engine,
-                            // wait for the stage that holds row r
-                            while ((released + 1) * SR <= r) {
+                            // ring event at a stage boundary: hand the stage just counted back
+                            // to the copy engine, wait for the stage that holds row r
+                            if (r) {
                                 __syncwarp();  // every lane has read the stage
-                                if (lane == 0 && released + STAGES < nstg) issue(released + STAGES);
-                                ++released;
+                                if (lane == 0 && rows_unissued > 0) issue();
                             }
-                            while (waited * SR <= r) {
-                                const int s = waited % STAGES;
-                                v_mbar_wait(bar_s + 8 * s, (parity >> s) & 1u);
-                                parity ^= 1u << s;
-                                ++waited;
-                            }
-                            limit = min(min(nrows, waited * SR), (r | (RING_ROWS - 1)) + 1);
+                            v_mbar_wait(bar_s + 8 * wait_slot, (parity >> wait_slot) & 1u);
+                            parity ^= 1u << wait_slot;
+                            wait_slot = wait_slot + 1 == STAGES ? 0 : wait_slot + 1;
+                            limit = min(nrows, r + SR);
+                            rp = ring + (r & (RING_ROWS - 1)) * 32;
                         }
                     }
-                    v_flush(acc, og + s_cls[seg], woff, lane);
-                    r_flush = r;
+                    v_flush(acc, oseg, woff, lane);
+                    fb = r + 255;
                 }
             }
             __syncwarp();  // the ring is free for the next item
@@ -350,12 +345,12 @@ k_vscatter(const uint32_t *__restrict__ packed, const int64_t *__restrict__ indp
 
 using namespace prb;
 
-// Kernel configurations (cells per super-tile, rows per stage, stages per warp); all fit the
-// 227 KB of shared memory.  PRB_V_CFG selects one for tuning runs.
-using VCfg0 = VCfg<1 << 16, 16, 2>;  //  64 KB of shift codes + 32 warps x 2 x 2 KB
-using VCfg1 = VCfg<1 << 16, 8, 4>;   //  64 KB + 32 x 4 x 1 KB
-using VCfg2 = VCfg<1 << 17, 8, 2>;   // 128 KB + 32 x 2 x 1 KB
-using VCfg3 = VCfg<1 << 16, 8, 2>;   //  64 KB + 32 x 2 x 1 KB
+// Kernel configurations (cells per super-tile, rows per stage, stages per warp, warps per
+// CTA); all fit the 227 KB of shared memory.  PRB_V_CFG selects one for tuning runs.
+using VCfg0 = VCfg<1 << 16, 16, 2, 32>;  //  64 KB of shift codes + 32 warps x 2 x 2 KB
+using VCfg1 = VCfg<1 << 15, 32, 2, 24>;  //  32 KB + 24 x 2 x 4 KB
+using VCfg2 = VCfg<1 << 16, 32, 2, 16>;  //  64 KB + 16 x 2 x 4 KB
+using VCfg3 = VCfg<1 << 15, 16, 4, 24>;  //  32 KB + 24 x 4 x 2 KB
 
 static int v_cfg()
 {
@@ -437,31 +432,31 @@ extern "C" int prb_stream_v(const uint32_t *vpacked, const int32_t *run_end,
     PRB_REQUIRE(max_tile_cells <= v_span() - 32, "super-tile spans too many cells");
     PRB_CUDA(cudaMemsetAsync(counters, 0, sizeof(int32_t) * n_st, S(stream)));
     const int64_t PV = P * K1;
-    // ~16 work items per warp and super-tile
-    const int64_t warps_per_tile = hmax(1, (int64_t)devinfo().sm_count * V_WARPS / n_st);
-    const int gpi = (int)hmin(1024, hmax(1, PV / (warps_per_tile * 16)));
-    const int64_t n_items = ceil_div(PV, gpi) * n_st;
-    const int grid = (int)hmax(1, hmin(devinfo().sm_count, ceil_div(n_items, V_WARPS)));
-    auto launch = [&](auto kern, int smem) -> int {
+    auto launch = [&](auto kern, int smem, int warps) -> int {
+        // ~16 work items per warp and super-tile
+        const int64_t warps_per_tile = hmax(1, (int64_t)devinfo().sm_count * warps / n_st);
+        const int gpi = (int)hmin(1024, hmax(1, PV / (warps_per_tile * 16)));
+        const int64_t n_items = ceil_div(PV, gpi) * n_st;
+        const int grid = (int)hmax(1, hmin(devinfo().sm_count, ceil_div(n_items, warps)));
         PRB_REQUIRE(smem + 512 <= devinfo().smem_optin, "not enough shared memory per block");
         PRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        kern<<<grid, V_THREADS, smem, S(stream)>>>(vpacked, run_end, tile_row0, n_seg, PV, K1,
-                                                   st_seg0, seg_cell0, seg_class, n_st, sx, C, hits,
-                                                   counters, gpi);
+        kern<<<grid, warps * 32, smem, S(stream)>>>(vpacked, run_end, tile_row0, n_seg, PV, K1,
+                                                    st_seg0, seg_cell0, seg_class, n_st, sx, C, hits,
+                                                    counters, gpi);
         return 0;
     };
     switch (v_cfg()) {
         case 1:
-            if (launch(k_stream_v<VCfg1>, VCfg1::smem_bytes)) return 1;
+            if (launch(k_stream_v<VCfg1>, VCfg1::smem_bytes, VCfg1::warps)) return 1;
             break;
         case 2:
-            if (launch(k_stream_v<VCfg2>, VCfg2::smem_bytes)) return 1;
+            if (launch(k_stream_v<VCfg2>, VCfg2::smem_bytes, VCfg2::warps)) return 1;
             break;
         case 3:
-            if (launch(k_stream_v<VCfg3>, VCfg3::smem_bytes)) return 1;
+            if (launch(k_stream_v<VCfg3>, VCfg3::smem_bytes, VCfg3::warps)) return 1;
             break;
         default:
-            if (launch(k_stream_v<VCfg0>, VCfg0::smem_bytes)) return 1;
+            if (launch(k_stream_v<VCfg0>, VCfg0::smem_bytes, VCfg0::warps)) return 1;
     }
     PRB_LAUNCH_CHECK("k_stream_v");
     return 0;
