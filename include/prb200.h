@@ -83,57 +83,41 @@ int prb_stream_hits(const uint32_t *packed, const int64_t *tp, int64_t P, int64_
                     const void *state, int64_t N, int64_t n_states, int K1, int direct_C,
                     int32_t *hits, int32_t *counters, prb_stream_t stream);
 
-/* ---- the hot loop for K <= 5: class-sorted cells + register counters (swar.cu) ----
+/* ---- the hot loop for K <= 5 on the V layout (vstream.cu): 4 instructions per entry ----
  * Same job as prb_stream_hits for the direct single-gene layout — the merge of
- * INFOSET:365-391 for entropy_wrt([j]) / entropy_wrt([-1, j]) (ITER:53, 55) and the
- * class-conditional count tables behind entropy_wrt([]) / ([-1]) (ITER:30, 32) — on a
- * matrix whose cells have been relabelled so that classes are contiguous
- * (prb_class_sort; entropies do not depend on the order of cells).
- * Segment plan (host-built, device arrays): seg_cell0 int32[n_seg+1] ascending cell
- * boundaries of the class segments (last = N); seg_class int32[n_seg] or NULL (= all
- * class 0); st_seg0 int32[n_st+1]: super-tile t = segments [st_seg0[t], st_seg0[t+1]),
- * at most max_segs of them and at most max_cells cells (prb_swar_tile_capacity);
- * tpf int32[P][n_seg+1] from prb_seg_ptrs: first entry of gene g, relative to
- * indptr[g], whose cell id is >= seg_cell0[s].
- *   sx  : int8[N] (+16 bytes padding) from prb_state_swar, or NULL = count-table mode
- *   out : hits int32[P][C][K-1][K-1] (added to; bin = (x_j-1)*(K-1) + x_g-1), or in
- *         count-table mode cnt int32[P][C][K-1].
- *   counters : int32[n_st] scratch (reset by the call). */
-int prb_swar_tile_capacity(int64_t *max_cells, int *max_segs);
-int prb_seg_ptrs(const uint32_t *packed, const int64_t *indptr, int64_t P,
-                 const int32_t *seg_cell0, int n_seg, int32_t *tpf, prb_stream_t stream);
-int prb_stream_swar(const uint32_t *packed, const int64_t *indptr, const int32_t *tpf, int n_seg,
-                    int64_t P, int64_t nnz, const int32_t *st_seg0, const int32_t *seg_cell0,
-                    const int32_t *seg_class, int n_st, int64_t max_tile_cells, const int8_t *sx,
-                    int K1, int C, int32_t *out, int32_t *counters, prb_stream_t stream);
-/* per-cell shift code of the selected gene (sx int8[N]; enc 0 for prb_stream_swar, enc 1
- * for prb_stream_v) plus the same hsize / hs_begin / hs_y / hs_ysum / ha tables as
- * prb_state_direct. */
-int prb_state_swar(const uint8_t *xj, const int32_t *y, int64_t N, int C, int K, int enc,
-                   int8_t *sx, int32_t *hsize, int32_t *hs_begin, int32_t *hs_y, int32_t *hs_ysum,
-                   int32_t *ha, prb_stream_t stream);
-/* relabel cells and keep every gene's entries ascending: out word = code | newpos[row],
- * entries of a gene stably partitioned by cls[row] (int32[N], class of the CURRENT cell
- * id; newpos must be increasing inside a class).  queue: device int32 scratch. */
+ * INFOSET:365-391 for entropy_wrt([j]) / entropy_wrt([-1, j]) (ITER:53, 55) — and, through
+ * its run lengths, the class-conditional count tables behind entropy_wrt([]) / ([-1])
+ * (ITER:30, 32), on a private re-ordering of the matrix (a histogram does not depend on the
+ * order in which cells are visited):
+ *  1. prb_class_sort relabels the cells so that classes are contiguous (out word =
+ *     code | newpos[row], every gene's entries stably partitioned by cls[row] — int32[N],
+ *     class of the CURRENT cell id; newpos must be increasing inside a class).
+ *  2. A host-built segment plan cuts the cells into SEGMENTS (a class, or a piece of one)
+ *     and packs consecutive segments into SUPER-TILES of at most max_cells cells and
+ *     max_segs segments (prb_v_tile_capacity): seg_cell0 int32[n_seg+1] ascending cell
+ *     boundaries (last = N); seg_class int32[n_seg] or NULL (= all class 0);
+ *     st_seg0 int32[n_st+1]: super-tile t = segments [st_seg0[t], st_seg0[t+1]).
+ *  3. prb_v_count -> caller's scan -> prb_v_scatter build the V layout: every gene g
+ *     becomes K-1 virtual genes (g, v), one per non-zero code v; a RUN (vg, s) holds the
+ *     entries of virtual gene vg in segment s (seg_of_cell int32[N] = segment of every
+ *     cell), ascending, padded to a multiple of 32 entries (one 128-byte row); runs are
+ *     stored TILE-MAJOR: by (super-tile of s, vg, s).
+ *       seglen    int32[P*(K-1)][n_seg]  true run lengths
+ *       run_end   int32[P*(K-1)][n_seg]  row just past each run (inclusive scan of
+ *                                        ceil(seglen/32) in storage order, by the caller)
+ *       tile_row0 int32[n_st+1]          first row of every super-tile's block
+ *       vpacked   uint32[32 * rows]      words code<<24 | cell; the padding words of segment
+ *                 s are seg_pad[s] = 0xFF000000 | ((first cell after the segment's
+ *                 super-tile) mod tile span): a slot the kernel keeps at "x_j = 0"
+ *  4. prb_state_v: per-cell shift code of the selected gene, sx uint8[N] (+16 bytes of
+ *     padding) = 8*(x_j-1), 64 where x_j = 0, plus the same hsize / hs_begin / hs_y /
+ *     hs_ysum / ha tables as prb_state_direct.
+ *  5. prb_stream_v adds the joint counts to hits int32[P][C][K-1][K-1]
+ *     (bin = (x_j-1)*(K-1) + x_g-1).  counters: int32[n_st] scratch (reset by the call);
+ *     queue: device int32 scratch. */
 int prb_class_sort(const uint32_t *packed_in, const int64_t *indptr, int64_t P,
                    const int32_t *newpos, const int32_t *cls, int C, uint32_t *packed_out,
                    int32_t *queue, prb_stream_t stream);
-
-/* ---- the hot loop for K <= 5 on the V layout (vstream.cu): 4 instructions per entry ----
- * Same job as prb_stream_swar.  The V layout re-orders the class-sorted packed CSC once
- * (prb_v_count -> caller's scan -> prb_v_scatter): every gene g becomes K-1 virtual genes
- * (g, v), one per non-zero code v; a RUN (vg, s) holds the entries of virtual gene vg in
- * segment s (seg_of_cell int32[N] = segment of every cell), ascending, padded to a multiple
- * of 32 entries (one 128-byte row); runs are stored TILE-MAJOR: by (super-tile of s, vg, s).
- *   seglen    int32[P*(K-1)][n_seg]  true run lengths (= the class-conditional count
- *                                    tables behind entropy_wrt([]) / ([-1]), ITER:30, 32)
- *   run_end   int32[P*(K-1)][n_seg]  row just past each run (inclusive scan of
- *                                    ceil(seglen/32) in storage order, done by the caller)
- *   tile_row0 int32[n_st+1]          first row of every super-tile's block
- *   vpacked   uint32[32 * rows]      words code<<24 | cell; the padding words of segment s
- *             are seg_pad[s] = 0xFF000000 | ((first cell after the segment's super-tile)
- *             mod tile span): a slot the kernel keeps at "x_j = 0"
- * prb_stream_v adds to hits int32[P][C][K-1][K-1]; sx = prb_state_swar(enc = 1). */
 int prb_v_tile_capacity(int64_t *max_cells, int *max_segs);
 int prb_v_count(const uint32_t *packed, const int64_t *indptr, int64_t P,
                 const int32_t *seg_of_cell, int n_seg, int K1, int32_t *seglen, int32_t *queue,
@@ -142,6 +126,9 @@ int prb_v_scatter(const uint32_t *packed, const int64_t *indptr, int64_t P,
                   const int32_t *seg_of_cell, int n_seg, int K1, const int32_t *seglen,
                   const int32_t *run_end, const uint32_t *seg_pad, uint32_t *vpacked,
                   int32_t *queue, prb_stream_t stream);
+int prb_state_v(const uint8_t *xj, const int32_t *y, int64_t N, int C, int K, uint8_t *sx,
+                int32_t *hsize, int32_t *hs_begin, int32_t *hs_y, int32_t *hs_ysum, int32_t *ha,
+                prb_stream_t stream);
 int prb_stream_v(const uint32_t *vpacked, const int32_t *run_end, const int32_t *tile_row0,
                  int n_seg, int64_t P, int K1, int64_t v_rows, const int32_t *st_seg0,
                  const int32_t *seg_cell0, const int32_t *seg_class, int n_st,

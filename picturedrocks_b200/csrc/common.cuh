@@ -46,8 +46,8 @@ inline int64_t hmin(int64_t a, int64_t b) { return a < b ? a : b; }
 inline int64_t hmax(int64_t a, int64_t b) { return a > b ? a : b; }
 
 constexpr uint32_t ROW_MASK = 0x00FFFFFFu;
-// swar.cu: shift code of a cell whose selected-gene code is 0 (>= 64: counts nothing)
-constexpr int PRB_SX_NONE = 100;
+// vstream.cu: shift code of a cell whose selected-gene code is 0 (>= 32: 1 << it == 0)
+constexpr int PRB_SX_NONE = 64;
 
 // np.argmax ordering: NaN is maximal; first index wins ties.
 __device__ __forceinline__ bool better(double sa, int64_t ia, double sb, int64_t ib)

@@ -95,14 +95,12 @@ __global__ void k_state_direct_sums(const int32_t *__restrict__ hsize, int C, in
     (void)work_counter;
 }
 
-// Per-cell shift code of the selected gene (x_j in the class-sorted cell order):
-//   enc 0 (swar.cu):    sx = 16*(x_j-1) - 4  (sx + 4*x_i = 4-bit field offset), PRB_SX_NONE for x_j = 0
-//   enc 1 (vstream.cu): sx = 8*(x_j-1)       (8-bit field offset),          64 for x_j = 0
+// Per-cell shift code of the selected gene (x_j in the class-sorted cell order) for
+// vstream.cu:  sx = 8*(x_j-1) (offset of x_j's 8-bit counter field), PRB_SX_NONE for x_j = 0,
 // and hsize[y*(K-1) + x_j-1] = #cells (the sizes of the hit states).
 __global__ void __launch_bounds__(256)
-k_state_swar(const uint8_t *__restrict__ xj, const int32_t *__restrict__ y, int64_t N, int K1,
-             int C, int enc, int8_t *__restrict__ sx, int32_t *__restrict__ hsize,
-             int use_smem_hist)
+k_state_v(const uint8_t *__restrict__ xj, const int32_t *__restrict__ y, int64_t N, int K1,
+             int C, uint8_t *__restrict__ sx, int32_t *__restrict__ hsize, int use_smem_hist)
 {
     extern __shared__ int sh_hist[];
     const int n_hs = C * K1;
@@ -113,13 +111,13 @@ k_state_swar(const uint8_t *__restrict__ xj, const int32_t *__restrict__ y, int6
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t cell = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; cell < N; cell += stride) {
         const int a = xj[cell];
-        int s = enc ? 64 : PRB_SX_NONE;
+        int s = PRB_SX_NONE;
         if (a) {
             const int yy = y ? y[cell] : 0;
-            s = enc ? 8 * (a - 1) : 16 * (a - 1) - 4;
+            s = 8 * (a - 1);
             atomicAdd(use_smem_hist ? sh_hist + yy * K1 + a - 1 : hsize + yy * K1 + a - 1, 1);
         }
-        sx[cell] = (int8_t)s;
+        sx[cell] = (uint8_t)s;
     }
     if (use_smem_hist) {
         __syncthreads();
@@ -305,19 +303,19 @@ extern "C" int prb_state_direct(const uint8_t *xj, const int32_t *y, int64_t N, 
     return 0;
 }
 
-extern "C" int prb_state_swar(const uint8_t *xj, const int32_t *y, int64_t N, int C, int K,
-                              int enc, int8_t *sx, int32_t *hsize, int32_t *hs_begin, int32_t *hs_y,
+extern "C" int prb_state_v(const uint8_t *xj, const int32_t *y, int64_t N, int C, int K,
+                           uint8_t *sx, int32_t *hsize, int32_t *hs_begin, int32_t *hs_y,
                               int32_t *hs_ysum, int32_t *ha, prb_stream_t stream)
 {
     PRB_REQUIRE(N > 0 && N <= PRB_MAX_ROWS, "N out of range");
-    PRB_REQUIRE(C >= 1 && K >= 2 && K <= 5, "the register-counter path needs 2 <= K <= 5");
+    PRB_REQUIRE(C >= 1 && K >= 2 && K <= 5, "the V-layout path needs 2 <= K <= 5");
     const int K1 = K - 1;
     const int64_t n_hs = (int64_t)C * K1;
     PRB_CUDA(cudaMemsetAsync(hsize, 0, sizeof(int32_t) * n_hs, S(stream)));
     const int use_smem = n_hs <= 8192;
-    k_state_swar<<<cell_grid(N, 256), 256, use_smem ? n_hs * 4 : 0, S(stream)>>>(
-        xj, y, N, K1, C, enc, sx, hsize, use_smem);
-    PRB_LAUNCH_CHECK("k_state_swar");
+    k_state_v<<<cell_grid(N, 256), 256, use_smem ? n_hs * 4 : 0, S(stream)>>>(
+        xj, y, N, K1, C, sx, hsize, use_smem);
+    PRB_LAUNCH_CHECK("k_state_v");
     k_state_direct_sums<<<1, 256, 0, S(stream)>>>(hsize, C, K1, hs_begin, hs_y, hs_ysum, ha,
                                                   nullptr);
     PRB_LAUNCH_CHECK("k_state_direct_sums");

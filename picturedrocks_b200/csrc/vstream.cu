@@ -103,7 +103,7 @@ __device__ __forceinline__ void v_flush(uint32_t &acc, int32_t *out, int woff, i
 //   tile_row0 int32[n_st+1]    : first row of every super-tile's block
 // Padding words of a run point at the cell slot just past their super-tile, which the tile
 // loader sets to "x_j = 0", so every row is counted the same way (no lane masks).
-// sx: uint8[N] shift codes 8*(x_j-1), >= 32 where x_j = 0 (prb_state_swar, enc = 1).
+// sx: uint8[N] shift codes 8*(x_j-1), >= 32 where x_j = 0 (prb_state_v).
 // hits: int32[P][C][K1][K1], added to.
 template <typename CFG>
 __global__ void __launch_bounds__(CFG::threads, 1)
@@ -160,7 +160,7 @@ k_stream_v(const uint32_t *__restrict__ vpacked, const int32_t *__restrict__ run
                 dst[(v0 + i) & (SPAN / 16 - 1)] = __ldg(src + i);
         }
         __syncthreads();
-        if (tid == 0) st[c1 & (SPAN - 1)] = 64;  // the slot padding words point at: x_j = 0
+        if (tid == 0) st[c1 & (SPAN - 1)] = PRB_SX_NONE;  // the slot padding words point at: x_j = 0
         __syncthreads();
         const int32_t tile_first_row = tile_row0[t];
         for (;;) {
@@ -258,6 +258,64 @@ k_stream_v(const uint32_t *__restrict__ vpacked, const int32_t *__restrict__ run
 }
 
 // ---- building the V layout -------------------------------------------------------------
+// Stable partition of every gene's entries by the class of their cell, with the cell ids
+// relabelled: out word = code | newpos[row].  One warp per gene (dynamic queue), two passes:
+// class counts -> exclusive offsets -> ordered scatter (rank inside a 32-entry group by
+// __match_any_sync, so the ascending order inside a class is kept).
+constexpr int CS_WARPS = 8;
+
+__global__ void __launch_bounds__(CS_WARPS * 32)
+k_class_sort(const uint32_t *__restrict__ in, const int64_t *__restrict__ indptr, int64_t P,
+             const int32_t *__restrict__ newpos, const int32_t *__restrict__ cls, int C,
+             uint32_t *__restrict__ out, int *queue)
+{
+    extern __shared__ int off_all[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int *off = off_all + warp * C;
+    for (;;) {
+        int gi = 0;
+        if (lane == 0) gi = atomicAdd(queue, 1);
+        const int64_t g = __shfl_sync(0xffffffffu, gi, 0);
+        if (g >= P) break;
+        const int64_t b = indptr[g], e = indptr[g + 1];
+        for (int i = lane; i < C; i += 32) off[i] = 0;
+        __syncwarp();
+        for (int64_t i = b + lane; i < e; i += 32) atomicAdd(off + cls[in[i] & ROW_MASK], 1);
+        __syncwarp();
+        int carry = 0;
+        for (int c0 = 0; c0 < C; c0 += 32) {
+            const int i = c0 + lane;
+            const int v = i < C ? off[i] : 0;
+            int incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (i < C) off[i] = carry + incl - v;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        __syncwarp();
+        for (int64_t i0 = b; i0 < e; i0 += 32) {
+            const int64_t i = i0 + lane;
+            const bool valid = i < e;
+            const unsigned act = __ballot_sync(0xffffffffu, valid);
+            if (valid) {
+                const uint32_t w = in[i];
+                const uint32_t row = w & ROW_MASK;
+                const int cc = cls[row];
+                const unsigned m = __match_any_sync(act, cc);
+                const int rank = __popc(m & ((1u << lane) - 1u));
+                const int base = off[cc];
+                out[b + base + rank] = (w & ~ROW_MASK) | (uint32_t)newpos[row];
+                __syncwarp(act);
+                if (rank == 0) off[cc] = base + __popc(m);
+            }
+            __syncwarp();
+        }
+    }
+}
+
 // pass 1: per gene, entries per (code, segment) -> seglen[P*K1][n_seg].  One warp per gene
 // (dynamic queue), shared-memory histogram per warp.
 constexpr int VB_WARPS = 8;
@@ -459,5 +517,19 @@ extern "C" int prb_stream_v(const uint32_t *vpacked, const int32_t *run_end,
             if (launch(k_stream_v<VCfg0>, VCfg0::smem_bytes, VCfg0::warps)) return 1;
     }
     PRB_LAUNCH_CHECK("k_stream_v");
+    return 0;
+}
+
+extern "C" int prb_class_sort(const uint32_t *packed_in, const int64_t *indptr, int64_t P,
+                              const int32_t *newpos, const int32_t *cls, int C,
+                              uint32_t *packed_out, int32_t *queue, prb_stream_t stream)
+{
+    if (P == 0) return 0;
+    PRB_REQUIRE(C >= 1 && C <= 4096, "class count out of range");
+    PRB_CUDA(cudaMemsetAsync(queue, 0, sizeof(int32_t), S(stream)));
+    const int grid = (int)hmin(ceil_div(P, CS_WARPS), (int64_t)devinfo().sm_count * 8);
+    k_class_sort<<<grid, CS_WARPS * 32, (size_t)CS_WARPS * C * 4, S(stream)>>>(
+        packed_in, indptr, P, newpos, cls, C, packed_out, queue);
+    PRB_LAUNCH_CHECK("k_class_sort");
     return 0;
 }

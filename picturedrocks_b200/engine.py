@@ -23,11 +23,9 @@ import torch
 from . import _native as nat
 
 _I16_MAX_BINS = 65536
-# K <= 5: class-sorted cells + register counters (csrc/swar.cu); PRB_NO_SWAR=1 forces the
-# generic shared-histogram kernel (csrc/stream.cu) everywhere
-USE_SWAR = os.environ.get("PRB_NO_SWAR", "0") != "1"
-# which register-counter kernel: "v" = csrc/vstream.cu (V layout, default), "16" = csrc/swar.cu
-SWAR_MODE = os.environ.get("PRB_SWAR_MODE", "v")
+# K <= 5: class-sorted cells + the V layout + register counters (csrc/vstream.cu);
+# PRB_NO_VLAYOUT=1 forces the generic shared-histogram kernel (csrc/stream.cu) everywhere
+USE_VLAYOUT = os.environ.get("PRB_NO_VLAYOUT", "0") != "1"
 PACKED_PAD = 4  # words of slack after the last stored entry
 
 
@@ -61,7 +59,7 @@ class Engine:
         self.K1 = self.K - 1
         self.shift = (self.K - 1).bit_length()  # infoset.py:199  int(log2(max)+1)
         self.nnz = int(indptr[-1].item())
-        if packed.numel() < self.nnz + PACKED_PAD:  # csrc/swar.cu reads whole 16-byte chunks
+        if packed.numel() < self.nnz + PACKED_PAD:  # keep 16 bytes of slack behind the stream
             packed = torch.cat([packed[: self.nnz], packed.new_zeros(PACKED_PAD)])
             self.packed = packed
         sm = ctypes.c_int()
@@ -87,10 +85,8 @@ class Engine:
         self.counters = torch.zeros(8192, dtype=torch.int32, device=dev)
         self._plans = {}
         self._tps = {}
-        self._swar = {}
-        self.swar = USE_SWAR and self.K1 <= 4
-        self.vmode = self.swar and SWAR_MODE == "v"
-        self.v = None  # V layout (csrc/vstream.cu): dict(vpacked, vindptr, tpf2, seglen, nnz)
+        self.vmode = USE_VLAYOUT and self.K1 <= 4
+        self.v = None  # V layout (csrc/vstream.cu), built lazily for the current labels
         self.cell_of_pos = None  # int64[N]: original cell id at each position (None = identity)
         self.classsizes_host = None
         self.gene_ptr = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -140,16 +136,14 @@ class Engine:
             self.state_buf[: 2 * self.N] = values.to(torch.int16).view(torch.uint8)
 
     def _count_table(self, y, C):
-        """cnt[g][c][v-1] = #cells of class c with code v in gene g (one streaming pass in
-        which every cell is a "master row" whose state is its class)."""
+        """cnt[g][c][v-1] = #cells of class c with code v in gene g.  V layout: the run
+        lengths; generic path: one streaming pass in which every cell is a "master row"
+        whose state is its class."""
         if C * self.K1 > _I16_MAX_BINS:
             raise NotImplementedError("classes x codes exceeds 65536 histogram bins")
         if self.vmode:
             return self._count_table_v(y is not None, C)
         cnt = torch.zeros(max(self.P * C * self.K1, 1), dtype=torch.int32, device=self.device)
-        if self.swar:
-            self._stream_swar(y is not None, None, C, cnt)
-            return cnt
         sb = self._plan(C)[3]
         if y is None:
             self._store_state(torch.ones(self.N, dtype=torch.int32, device=self.device), sb)
@@ -162,7 +156,7 @@ class Engine:
         """y: int32 device tensor [N] of labels in 0..C-1 (original cell order), or None
         (infoset.py:202-216).  The cells are re-ordered so that classes are contiguous
         (stable, so every gene's entries stay ascending): entropies do not depend on the
-        order of cells, and csrc/swar.cu needs class-contiguous cells."""
+        order of cells, and csrc/vstream.cu needs class-contiguous cells."""
         self.epoch += 1
         if y is None:
             self.has_y, self.y, self.C, self.classsizes, self.cnt_y = False, None, 1, None, None
@@ -184,25 +178,21 @@ class Engine:
             self.packed = out
             self.cell_of_pos = order if self.cell_of_pos is None else self.cell_of_pos[order]
             y_cur = y_cur[order]
-            self._tps, self._swar, self.v = {}, {}, None
+            self._tps = {}
         self.has_y, self.y, self.C = True, y_cur.contiguous(), C
         self.classsizes = torch.bincount(self.y, minlength=C).to(torch.int64)
         self.classsizes_host = [int(v) for v in self.classsizes.cpu().numpy()]
-        self._swar.pop(True, None)
-        self.v = None
+        self.v = None  # new labels: new segments
         self.cnt_y = self._count_table(self.y, C)
 
-    # ------------------------------------------------ register-counter path (K <= 5)
-    def _swar_plan(self, classes):
-        """Segment plan of csrc/swar.cu: class segments (split when a class exceeds the
-        shared-memory capacity) packed into super-tiles; cached until the cells move."""
-        pl = self._swar.get(classes)
-        if pl is not None:
-            return pl
+    # ------------------------------------------------ V layout (csrc/vstream.cu), K <= 5
+    def _v_plan(self):
+        """Segment plan: one segment per class (split when a class exceeds the shared-memory
+        tile; a single class [0, N) without labels) packed into super-tiles."""
+        classes = self.has_y
         cap, max_segs = ctypes.c_int64(), ctypes.c_int()
-        nat.call("prb_v_tile_capacity" if self.vmode else "prb_swar_tile_capacity",
-                 ctypes.byref(cap), ctypes.byref(max_segs))
-        cap = max(128, min(int(os.environ.get("PRB_SWAR_TILE_CELLS", cap.value)), cap.value))
+        nat.call("prb_v_tile_capacity", ctypes.byref(cap), ctypes.byref(max_segs))
+        cap = max(128, min(int(os.environ.get("PRB_V_TILE_CELLS", cap.value)), cap.value))
         sizes = self.classsizes_host if classes else [self.N]
         cell0, cls, pos = [], [], 0
         for c, n in enumerate(sizes):
@@ -230,44 +220,14 @@ class Engine:
             raise NotImplementedError("too many cell tiles")
         max_cells = max(cell0[st[t + 1]] - cell0[st[t]] for t in range(n_st))
         i32 = dict(dtype=torch.int32, device=self.device)
-        pl = dict(n_seg=n_seg, n_st=n_st, max_cells=max_cells, classes=classes,
-                  seg_cell0=torch.tensor(cell0, **i32), st_seg0=torch.tensor(st, **i32),
-                  seg_class=torch.tensor(cls, **i32) if classes else None)
-        if self.vmode:
-            self._swar[classes] = pl
-            return pl
-        pl["tpf"] = torch.empty(max(self.P, 1) * (n_seg + 1), **i32)
-        if self.P:
-            nat.call("prb_seg_ptrs", nat.ptr(self.packed), nat.ptr(self.indptr), self.P,
-                     nat.ptr(pl["seg_cell0"]), n_seg, nat.ptr(pl["tpf"]), nat.stream())
-        self._swar[classes] = pl
-        return pl
+        return dict(n_seg=n_seg, n_st=n_st, max_cells=max_cells, cell0=cell0, st=st,
+                    seg_cell0=torch.tensor(cell0, **i32), st_seg0=torch.tensor(st, **i32),
+                    seg_class=torch.tensor(cls, **i32) if classes else None)
 
-    def _stream_swar(self, classes, sx, C, out):
-        ev = getattr(self, "profile_events", None)
-        if ev is not None:
-            e0 = torch.cuda.Event(enable_timing=True)
-            e1 = torch.cuda.Event(enable_timing=True)
-            e0.record()
-            self._stream_swar_launch(classes, sx, C, out)
-            e1.record()
-            ev.append((e0, e1))
-        else:
-            self._stream_swar_launch(classes, sx, C, out)
-
-    def _stream_swar_launch(self, classes, sx, C, out):
-        pl = self._swar_plan(classes)
-        nat.call("prb_stream_swar", nat.ptr(self.packed), nat.ptr(self.indptr), nat.ptr(pl["tpf"]),
-                 pl["n_seg"], self.P, self.nnz, nat.ptr(pl["st_seg0"]), nat.ptr(pl["seg_cell0"]),
-                 nat.ptr(pl["seg_class"]), pl["n_st"], pl["max_cells"], nat.ptr(sx), self.K1, C,
-                 nat.ptr(out), nat.ptr(self.counters), nat.stream())
-
-    # ------------------------------------------------ V layout (csrc/vstream.cu)
     def _build_v(self):
         """Re-order the (class-sorted) packed CSC into the V layout for the current segment
         plan: (gene, code) virtual genes, runs per segment padded to 32-entry rows."""
-        classes = self.has_y
-        pl = self._swar_plan(classes)
+        pl = self._v_plan()
         P, K1, n_seg, dev = self.P, self.K1, pl["n_seg"], self.device
         seg_of_cell = torch.bucketize(torch.arange(self.N, dtype=torch.int32, device=dev),
                                       pl["seg_cell0"][1:-1].contiguous(), right=True).to(torch.int32)
@@ -278,7 +238,7 @@ class Engine:
                  nat.stream())
         # rows of every run, scanned in storage order: (super-tile, virtual gene, segment)
         span = nat.load().prb_v_tile_span()
-        cell0, st = pl["seg_cell0"].cpu().tolist(), pl["st_seg0"].cpu().tolist()
+        cell0, st = pl["cell0"], pl["st"]
         nr = (seglen.view(PV, n_seg) + 31) >> 5
         run_end = torch.empty((PV, n_seg), dtype=torch.int32, device=dev)
         tile_row0, base = [0], 0
@@ -308,19 +268,23 @@ class Engine:
         return self.v if self.v is not None else self._build_v()
 
     def _count_table_v(self, with_classes, C):
-        """cnt[g][c][v-1] from the run lengths of the V layout (no streaming pass)."""
+        """cnt[g][c][v-1] from run lengths (no streaming pass over the hot kernel).  Without
+        labels only the per-(gene, code) totals are needed: one counting pass with a single
+        segment; the V layout itself is built when the labels (or the first step) arrive."""
+        dev, P, K1 = self.device, self.P, self.K1
+        if not with_classes:
+            seglen = torch.zeros(max(P * K1, 1), dtype=torch.int32, device=dev)
+            seg0 = torch.zeros(self.N, dtype=torch.int32, device=dev)
+            nat.call("prb_v_count", nat.ptr(self.packed), nat.ptr(self.indptr), P, nat.ptr(seg0),
+                     1, K1, nat.ptr(seglen), nat.ptr(self.counters), nat.stream())
+            return seglen
         v = self._v()
         pl = v["plan"]
-        L = v["seglen"].view(max(self.P * self.K1, 1), pl["n_seg"])[: self.P * self.K1]
-        L = L.view(self.P, self.K1, pl["n_seg"])
-        if not with_classes or pl["seg_class"] is None:
-            cnt = L.sum(2, dtype=torch.int32).view(self.P, 1, self.K1)
-        else:
-            cnt = torch.zeros((self.P, self.K1, C), dtype=torch.int32, device=self.device)
-            cnt.index_add_(2, pl["seg_class"].long(), L)
-            cnt = cnt.permute(0, 2, 1)
-        cnt = cnt.contiguous().view(-1)
-        return cnt if cnt.numel() else torch.zeros(1, dtype=torch.int32, device=self.device)
+        L = v["seglen"][: P * K1 * pl["n_seg"]].view(P, K1, pl["n_seg"])
+        cnt = torch.zeros((P, K1, C), dtype=torch.int32, device=dev)
+        cnt.index_add_(2, pl["seg_class"].long(), L)
+        cnt = cnt.permute(0, 2, 1).contiguous().view(-1)
+        return cnt if cnt.numel() else torch.zeros(1, dtype=torch.int32, device=dev)
 
     def _stream_v(self, with_y, sx, C, hits):
         ev = getattr(self, "profile_events", None)
@@ -411,16 +375,12 @@ class Engine:
         if n_bins > _I16_MAX_BINS:
             raise NotImplementedError("C*(K-1)^2 exceeds 65536 histogram bins")
         self.scatter_selected_gene()
-        if self.swar:
-            nat.call("prb_state_swar", nat.ptr(self.xj), nat.ptr(y), self.N, C, self.K,
-                     1 if self.vmode else 0, nat.ptr(self.state_buf), nat.ptr(self.hsize),
-                     nat.ptr(self.hs_begin), nat.ptr(self.hs_y), nat.ptr(self.hs_ysum),
-                     nat.ptr(self.ha), nat.stream())
+        if self.vmode:
+            nat.call("prb_state_v", nat.ptr(self.xj), nat.ptr(y), self.N, C, self.K,
+                     nat.ptr(self.state_buf), nat.ptr(self.hsize), nat.ptr(self.hs_begin),
+                     nat.ptr(self.hs_y), nat.ptr(self.hs_ysum), nat.ptr(self.ha), nat.stream())
             hits = self.hits_buffer(n_bins)
-            if self.vmode:
-                self._stream_v(with_y, self.state_buf, C, hits)
-            else:
-                self._stream_swar(with_y, self.state_buf, C, hits)
+            self._stream_v(with_y, self.state_buf, C, hits)
             self._finalize(hits, cnt, clsz, C, n_hs, None, out_full, out_marg, True)
             return
         sb = self._plan(n_hs)[3]

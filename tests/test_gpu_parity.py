@@ -289,21 +289,23 @@ def test_edge_cases(pr):
     assert np.array_equal(a.entropy_wrt([-1]), b.entropy_wrt(np.array([-1])))
 
 
-@pytest.mark.parametrize("tile_cells,swar", [(None, True), (4096, True), (256, True), (None, False)])
-def test_class_sorted_cells_and_register_counters(pr, O, monkeypatch, tile_cells, swar):
-    """csrc/swar.cu (K <= 5): class-sorted cells, class segments split and packed into
-    super-tiles of various sizes, label re-targeting (cells move again), export of X in
-    the original cell order — all bit-identical to the oracle; swar=False runs the same
-    checks through the generic shared-histogram kernel on the same re-ordered cells."""
+@pytest.mark.parametrize("tile_cells,vlayout", [(None, True), (4096, True), (256, True),
+                                                 (None, False)])
+def test_class_sorted_cells_and_v_layout(pr, O, monkeypatch, tile_cells, vlayout):
+    """csrc/vstream.cu (K <= 5): class-sorted cells, class segments split and packed into
+    super-tiles of various sizes, tile-major padded runs, label re-targeting (cells move
+    again, layout rebuilt), export of X in the original cell order — all bit-identical to
+    the oracle; vlayout=False runs the same checks through the generic shared-histogram
+    kernel on the same re-ordered cells."""
     import picturedrocks_b200.engine as E
     from picturedrocks_b200.synth import DiscretisedSpec
 
-    monkeypatch.setattr(E, "USE_SWAR", swar)
+    monkeypatch.setattr(E, "USE_VLAYOUT", vlayout)
     if tile_cells:
-        monkeypatch.setenv("PRB_SWAR_TILE_CELLS", str(tile_cells))
+        monkeypatch.setenv("PRB_V_TILE_CELLS", str(tile_cells))
     spec = DiscretisedSpec(N=30011, P=257, C=7, K=5, mean_density=0.09, seed=11)
     eng, yd = spec.device_engine()
-    assert eng.swar == swar
+    assert eng.vmode == vlayout
     inf = pr.markers.SparseInformationSet._from_engine(eng, yd)
     y = spec.cpu_labels()
     Xs = spec.cpu_csc(range(spec.P), y)
@@ -333,12 +335,12 @@ def test_class_sorted_cells_and_register_counters(pr, O, monkeypatch, tile_cells
 
 
 @pytest.mark.parametrize("K", [2, 3, 4])
-def test_register_counters_fewer_bins(pr, O, K):
+def test_v_layout_fewer_bins(pr, O, K):
     from picturedrocks_b200.synth import DiscretisedSpec
 
     spec = DiscretisedSpec(N=9001, P=130, C=5, K=K, mean_density=0.2, seed=K)
     eng, yd = spec.device_engine()
-    assert eng.swar
+    assert eng.vmode
     inf = pr.markers.SparseInformationSet._from_engine(eng, yd)
     ora = O.SparseInformationSet(inf.X, spec.cpu_labels())
     for cols in ([], [-1], [3], [-1, 3]):
