@@ -31,6 +31,9 @@ WORKLOADS = {
     # BASELINE.json configs[2]: PBMC-68k-shaped sparse
     "c3": dict(N=68579, P=32738, C=10, K=5, mean_density=0.02, seed=3,
                name="PBMC-68k-shaped synthetic sparse 68,579 x 32,738, 10 clusters, 2% nnz"),
+    # one eighth of the genes of c4: what each rank streams in the 8-GPU run (tuning aid)
+    "c4_shard8": dict(N=1306127, P=3500, C=60, K=5, mean_density=0.07, seed=4,
+                      name="c4 gene shard: 1,306,127 x 3,500, 60 clusters, 7% nnz"),
     # small case for quick functional runs
     "small": dict(N=20000, P=2000, C=12, K=5, mean_density=0.06, seed=7,
                   name="small synthetic sparse 20,000 x 2,000, 12 clusters"),

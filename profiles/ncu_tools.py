@@ -2,6 +2,7 @@
 
     python profiles/ncu_tools.py launches gpurun_out/launches.csv
     python profiles/ncu_tools.py raw gpurun_out/prof.ncu-rep
+    python profiles/ncu_tools.py hot gpurun_out/prof.ncu-rep    # where the instructions go
 """
 import collections
 import csv
@@ -25,6 +26,7 @@ KEYS = [
     "smsp__issue_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
     "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic",
     "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
     "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
@@ -73,5 +75,32 @@ def raw(path):
                 print("  %-88s %16s %s" % (k, r[i], units[i]))
 
 
+def hot(path):
+    """Executed-instruction shares of contiguous SASS regions (source page of the FIRST
+    kernel in the report): regions are runs of instructions with the same execution count."""
+    out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv"], capture_output=True,
+                         text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    print("# " + rows[0][1][:100])
+    hdr, data = rows[1], rows[2:]
+    isrc, ie, iss = (hdr.index("Source"), hdr.index("Instructions Executed"),
+                     hdr.index("# Samples"))
+    data = [r for r in data if len(r) > ie and r[ie].isdigit()]
+    tot = sum(int(r[ie]) for r in data)
+    runs = []
+    for i, r in enumerate(data):
+        n = int(r[ie])
+        if runs and abs(runs[-1][2] - n) <= 0.02 * max(n, 1):
+            runs[-1][1], runs[-1][3], runs[-1][4] = i, runs[-1][3] + int(r[iss]), runs[-1][4] + n
+        else:
+            runs.append([i, i, n, int(r[iss]), n, r[isrc].strip()[:40]])
+    print("total warp instructions executed: %.0f M" % (tot / 1e6))
+    print("%-11s %4s %10s %6s %8s  %s" % ("sass", "len", "exec(M)", "share", "samples", "first"))
+    for a, b, n, smp, t, first in runs:
+        if t > tot * 0.004:
+            print("%4d-%-6d %4d %10.2f %5.1f%% %8d  %s" % (a, b, b - a + 1, n / 1e6,
+                                                        100.0 * t / tot, smp, first))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "raw": raw}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "raw": raw, "hot": hot}[sys.argv[1]](sys.argv[2])
