@@ -111,10 +111,16 @@ int prb_stream_hits(const uint32_t *packed, const int64_t *tp, int64_t P, int64_
  *                 super-tile) mod tile span): a slot the kernel keeps at "x_j = 0"
  *  4. prb_state_v: per-cell shift code of the selected gene, sx uint8[N] (+16 bytes of
  *     padding) = 8*(x_j-1), 64 where x_j = 0, plus the same hsize / hs_begin / hs_y /
- *     hs_ysum / ha tables as prb_state_direct.
+ *     hs_ysum / ha tables as prb_state_direct (derived by the last block to finish;
+ *     ticket: device int32, zero on entry and on exit).  x_j is read and RESET to zero,
+ *     so the next prb_scatter_gene_u8 needs no memset.
  *  5. prb_stream_v adds the joint counts to hits int32[P][C][K-1][K-1]
- *     (bin = (x_j-1)*(K-1) + x_g-1).  counters: int32[n_st] scratch (reset by the call);
- *     queue: device int32 scratch. */
+ *     (bin = (x_j-1)*(K-1) + x_g-1).  Work items are fixed-size row ranges: item k of
+ *     super-tile t = rows [k*rows_per_item, (k+1)*rows_per_item) of its block;
+ *     item_off int32[n_st+1] = first item id of every super-tile; item_vg0 int32[n_items]
+ *     = first virtual gene with a run ending past the item's first row (a searchsorted of
+ *     run_end, by the caller; prb_v_warps() = warps of one launch, to size the items).
+ *     counters: int32[n_st] scratch (reset by the call); queue: device int32 scratch. */
 int prb_class_sort(const uint32_t *packed_in, const int64_t *indptr, int64_t P,
                    const int32_t *newpos, const int32_t *cls, int C, uint32_t *packed_out,
                    int32_t *queue, prb_stream_t stream);
@@ -126,14 +132,16 @@ int prb_v_scatter(const uint32_t *packed, const int64_t *indptr, int64_t P,
                   const int32_t *seg_of_cell, int n_seg, int K1, const int32_t *seglen,
                   const int32_t *run_end, const uint32_t *seg_pad, uint32_t *vpacked,
                   int32_t *queue, prb_stream_t stream);
-int prb_state_v(const uint8_t *xj, const int32_t *y, int64_t N, int C, int K, uint8_t *sx,
+int prb_state_v(uint8_t *xj, const int32_t *y, int64_t N, int C, int K, uint8_t *sx,
                 int32_t *hsize, int32_t *hs_begin, int32_t *hs_y, int32_t *hs_ysum, int32_t *ha,
-                prb_stream_t stream);
+                int32_t *ticket, prb_stream_t stream);
 int prb_stream_v(const uint32_t *vpacked, const int32_t *run_end, const int32_t *tile_row0,
                  int n_seg, int64_t P, int K1, int64_t v_rows, const int32_t *st_seg0,
                  const int32_t *seg_cell0, const int32_t *seg_class, int n_st,
                  int64_t max_tile_cells, const uint8_t *sx, int C, int32_t *hits,
-                 int32_t *counters, prb_stream_t stream);
+                 int32_t *counters, int rows_per_item, const int32_t *item_off,
+                 const int32_t *item_vg0, int64_t n_items, prb_stream_t stream);
+int prb_v_warps(void);
 /* cells per super-tile modulus (power of two) of the active kernel configuration */
 int prb_v_tile_span(void);
 
@@ -218,6 +226,11 @@ int prb_argmax_blocks(const double *score, int64_t P, int32_t gene_lo, double *c
 int prb_argmax_final(const double *cand_score, const int64_t *cand_idx, int64_t n_cand,
                      int64_t stride, double *best_score, int64_t *best_idx,
                      prb_stream_t stream);
+/* prb_argmax_final followed by prb_commit_add, one launch. */
+int prb_argmax_commit(const double *cand_score, const int64_t *cand_idx, int64_t n_cand,
+                      int64_t stride, double *best_score, int64_t *best_idx, int32_t *gene_ptr,
+                      int32_t *S, int32_t *n_sel_ptr, uint8_t *selected, int32_t gene_lo, int64_t P,
+                      prb_stream_t stream);
 /* commit a winner: gene_ptr <- idx, S[n_sel++] <- idx, selected[idx-gene_lo] <- 1,
  * score[idx-gene_lo] untouched (the update masks it).  idx is read from best_idx. */
 int prb_commit_add(const int64_t *best_idx, int32_t *gene_ptr, int32_t *S, int32_t *n_sel_ptr,

@@ -15,6 +15,8 @@
 //   (y, m>0, 0)   = hsize[state] - Σ_v hits
 //   (y, 0,   v>0) = cnt[g][y][v] - Σ_{states of y} hits[.][v]
 //   (y, 0,   0)   = classsize[y] - Σ hsize(states of y) - Σ_v (y,0,v)
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace prb {
@@ -533,10 +535,26 @@ static int launch_direct(int32_t *hits, int64_t stride, const int32_t *cnt, cons
                          double *out_marg, cudaStream_t st)
 {
     if constexpr (TK1 > 0) {
-        constexpr int L = 8;  // lanes per gene
+        // lanes per gene: 8 when there are enough genes to fill the GPU, more for small
+        // gene counts (a multi-GPU shard), where the kernel is bound by the per-gene chain
+        static const int forced = [] {
+            const char *e = getenv("PRB_FINALIZE_L");
+            return e ? atoi(e) : 0;
+        }();
         const int threads = 256;
-        k_finalize_direct_grp<TK1, L><<<(unsigned)ceil_div(P * L, threads), threads, 0, st>>>(
-            hits, stride, cnt, clsz, hsize, hs_ysum, ha, C, table, N, P, out_full, out_marg);
+        int L = P * 8 >= (int64_t)devinfo().sm_count * threads * 3 ? 8 : 16;
+        if (forced == 8 || forced == 16 || forced == 32) L = forced;
+        if (C <= 8) L = 8;
+#define PRB_FG(LL)                                                                            \
+    k_finalize_direct_grp<TK1, LL><<<(unsigned)ceil_div(P * LL, threads), threads, 0, st>>>(  \
+        hits, stride, cnt, clsz, hsize, hs_ysum, ha, C, table, N, P, out_full, out_marg)
+        if (L == 32)
+            PRB_FG(32);
+        else if (L == 16)
+            PRB_FG(16);
+        else
+            PRB_FG(8);
+#undef PRB_FG
         PRB_LAUNCH_CHECK("k_finalize_direct_grp");
         return 0;
     }

@@ -134,6 +134,36 @@ k_argmax_final(const double *__restrict__ cand_score, const int64_t *__restrict_
     }
 }
 
+// k_argmax_final followed by k_commit_add in one launch (the greedy step's first kernel).
+__global__ void __launch_bounds__(SEL_BLOCK)
+k_argmax_commit(const double *__restrict__ cand_score, const int64_t *__restrict__ cand_idx,
+                int64_t n_cand, int64_t stride, double *__restrict__ best_score,
+                int64_t *__restrict__ best_idx, int32_t *gene_ptr, int32_t *S, int32_t *n_sel_ptr,
+                uint8_t *selected, int32_t gene_lo, int64_t P)
+{
+    double sc = 0.0;
+    int64_t idx = -1;
+    for (int64_t c = threadIdx.x; c < n_cand; c += SEL_BLOCK) {
+        const double s2 = cand_score[c * stride];
+        const int64_t i2 = cand_idx[c * stride];
+        if (i2 >= 0 && (idx < 0 || better(s2, i2, sc, idx))) {
+            sc = s2;
+            idx = i2;
+        }
+    }
+    block_argmax(sc, idx);
+    if (threadIdx.x == 0) {
+        *best_score = sc;
+        *best_idx = idx;
+        *gene_ptr = (int32_t)idx;
+        const int n = *n_sel_ptr;
+        S[n] = (int32_t)idx;
+        *n_sel_ptr = n + 1;
+        const int64_t l = idx - gene_lo;
+        if (l >= 0 && l < P) selected[l] = 1;
+    }
+}
+
 __global__ void k_commit_add(const int64_t *__restrict__ best_idx, int32_t *gene_ptr, int32_t *S,
                              int32_t *n_sel_ptr, uint8_t *selected, int32_t gene_lo, int64_t P)
 {
@@ -195,6 +225,20 @@ extern "C" int prb_argmax_final(const double *cand_score, const int64_t *cand_id
     k_argmax_final<<<1, SEL_BLOCK, 0, S(stream)>>>(cand_score, cand_idx, n_cand, stride,
                                                    best_score, best_idx);
     PRB_LAUNCH_CHECK("k_argmax_final");
+    return 0;
+}
+
+extern "C" int prb_argmax_commit(const double *cand_score, const int64_t *cand_idx, int64_t n_cand,
+                                 int64_t stride, double *best_score, int64_t *best_idx,
+                                 int32_t *gene_ptr, int32_t *S_out, int32_t *n_sel_ptr,
+                                 uint8_t *selected, int32_t gene_lo, int64_t P,
+                                 prb_stream_t stream)
+{
+    PRB_REQUIRE(stride >= 1, "stride must be >= 1");
+    k_argmax_commit<<<1, SEL_BLOCK, 0, prb::S(stream)>>>(cand_score, cand_idx, n_cand, stride,
+                                                         best_score, best_idx, gene_ptr, S_out,
+                                                         n_sel_ptr, selected, gene_lo, P);
+    PRB_LAUNCH_CHECK("k_argmax_commit");
     return 0;
 }
 

@@ -99,10 +99,13 @@ __global__ void k_state_direct_sums(const int32_t *__restrict__ hsize, int C, in
 // vstream.cu:  sx = 8*(x_j-1) (offset of x_j's 8-bit counter field), PRB_SX_NONE for x_j = 0,
 // and hsize[y*(K-1) + x_j-1] = #cells (the sizes of the hit states).
 __global__ void __launch_bounds__(256)
-k_state_v(const uint8_t *__restrict__ xj, const int32_t *__restrict__ y, int64_t N, int K1,
-             int C, uint8_t *__restrict__ sx, int32_t *__restrict__ hsize, int use_smem_hist)
+k_state_v(uint8_t *__restrict__ xj, const int32_t *__restrict__ y, int64_t N, int K1, int C,
+          uint8_t *__restrict__ sx, int32_t *__restrict__ hsize, int use_smem_hist,
+          int32_t *__restrict__ hs_begin, int32_t *__restrict__ hs_y,
+          int32_t *__restrict__ hs_ysum, int32_t *__restrict__ ha, int *ticket)
 {
     extern __shared__ int sh_hist[];
+    __shared__ int s_last;
     const int n_hs = C * K1;
     if (use_smem_hist) {
         for (int i = threadIdx.x; i < n_hs; i += blockDim.x) sh_hist[i] = 0;
@@ -116,6 +119,7 @@ k_state_v(const uint8_t *__restrict__ xj, const int32_t *__restrict__ y, int64_t
             const int yy = y ? y[cell] : 0;
             s = 8 * (a - 1);
             atomicAdd(use_smem_hist ? sh_hist + yy * K1 + a - 1 : hsize + yy * K1 + a - 1, 1);
+            xj[cell] = 0;  // leave the scatter buffer clean for the next selected gene
         }
         sx[cell] = (uint8_t)s;
     }
@@ -124,6 +128,27 @@ k_state_v(const uint8_t *__restrict__ xj, const int32_t *__restrict__ y, int64_t
         for (int i = threadIdx.x; i < n_hs; i += blockDim.x)
             if (sh_hist[i]) atomicAdd(hsize + i, sh_hist[i]);
     }
+    // the last block to finish derives the per-class / per-value sums (k_state_direct_sums)
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int t = threadIdx.x, nt = blockDim.x;
+    for (int yy = t; yy <= C; yy += nt) hs_begin[yy] = yy * K1;
+    for (int h = t; h < n_hs; h += nt) hs_y[h] = h / K1;
+    for (int yy = t; yy < C; yy += nt) {
+        int sum = 0;
+        for (int a = 0; a < K1; ++a) sum += __ldcg(hsize + yy * K1 + a);
+        hs_ysum[yy] = sum;
+    }
+    for (int a = t; a < K1; a += nt) {
+        int sum = 0;
+        for (int yy = 0; yy < C; ++yy) sum += __ldcg(hsize + yy * K1 + a);
+        ha[a] = sum;
+    }
+    if (t == 0) *ticket = 0;
 }
 
 // ---- generic multi-column state through a presence table --------------------
@@ -303,9 +328,9 @@ extern "C" int prb_state_direct(const uint8_t *xj, const int32_t *y, int64_t N, 
     return 0;
 }
 
-extern "C" int prb_state_v(const uint8_t *xj, const int32_t *y, int64_t N, int C, int K,
-                           uint8_t *sx, int32_t *hsize, int32_t *hs_begin, int32_t *hs_y,
-                              int32_t *hs_ysum, int32_t *ha, prb_stream_t stream)
+extern "C" int prb_state_v(uint8_t *xj, const int32_t *y, int64_t N, int C, int K, uint8_t *sx,
+                           int32_t *hsize, int32_t *hs_begin, int32_t *hs_y, int32_t *hs_ysum,
+                           int32_t *ha, int32_t *ticket, prb_stream_t stream)
 {
     PRB_REQUIRE(N > 0 && N <= PRB_MAX_ROWS, "N out of range");
     PRB_REQUIRE(C >= 1 && K >= 2 && K <= 5, "the V-layout path needs 2 <= K <= 5");
@@ -314,11 +339,8 @@ extern "C" int prb_state_v(const uint8_t *xj, const int32_t *y, int64_t N, int C
     PRB_CUDA(cudaMemsetAsync(hsize, 0, sizeof(int32_t) * n_hs, S(stream)));
     const int use_smem = n_hs <= 8192;
     k_state_v<<<cell_grid(N, 256), 256, use_smem ? n_hs * 4 : 0, S(stream)>>>(
-        xj, y, N, K1, C, sx, hsize, use_smem);
+        xj, y, N, K1, C, sx, hsize, use_smem, hs_begin, hs_y, hs_ysum, ha, ticket);
     PRB_LAUNCH_CHECK("k_state_v");
-    k_state_direct_sums<<<1, 256, 0, S(stream)>>>(hsize, C, K1, hs_begin, hs_y, hs_ysum, ha,
-                                                  nullptr);
-    PRB_LAUNCH_CHECK("k_state_direct_sums");
     return 0;
 }
 

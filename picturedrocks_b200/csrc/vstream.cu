@@ -21,7 +21,7 @@
 //
 // HBM-bound by design: 4 bytes per stored entry (+ the row padding), read exactly once
 // through a per-warp ring of TMA bulk copies (cp.async.bulk + mbarrier); one persistent
-// CTA per SM; (super-tile, virtual-gene chunk) work items claimed dynamically per warp.
+// CTA per SM; (super-tile, fixed-size row range) work items claimed dynamically per warp.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -101,6 +101,9 @@ __device__ __forceinline__ void v_flush(uint32_t &acc, int32_t *out, int woff, i
 // segment), so the virtual genes of one work item are ONE contiguous row range:
 //   run_end   int32[PV][n_seg] : row just past run (vg, s);  PV = P*K1
 //   tile_row0 int32[n_st+1]    : first row of every super-tile's block
+// Work items: rows [k*rows_per_item, (k+1)*rows_per_item) of a super-tile's block;
+//   item_off int32[n_st+1]     : first item id of every super-tile
+//   item_vg0 int32[n_items]    : first virtual gene with a run ending past the item's first row
 // Padding words of a run point at the cell slot just past their super-tile, which the tile
 // loader sets to "x_j = 0", so every row is counted the same way (no lane masks).
 // sx: uint8[N] shift codes 8*(x_j-1), >= 32 where x_j = 0 (prb_state_v).
@@ -111,7 +114,8 @@ k_stream_v(const uint32_t *__restrict__ vpacked, const int32_t *__restrict__ run
            const int32_t *__restrict__ tile_row0, int n_seg, int64_t PV, int K1,
            const int32_t *__restrict__ st_seg0, const int32_t *__restrict__ seg_cell0,
            const int32_t *__restrict__ seg_class, int n_st, const uint8_t *__restrict__ sx, int C,
-           int32_t *__restrict__ hits, int *counters, int vg_per_item)
+           int32_t *__restrict__ hits, int *counters, int rows_per_item,
+           const int32_t *__restrict__ item_off, const int32_t *__restrict__ item_vg0)
 {
     constexpr int SPAN = CFG::span, SR = CFG::stage_rows, STAGES = CFG::stages;
     constexpr int STAGE_BYTES = CFG::stage_bytes, THREADS = CFG::threads;
@@ -132,17 +136,47 @@ k_stream_v(const uint32_t *__restrict__ vpacked, const int32_t *__restrict__ run
     }
     __syncwarp();
     uint32_t parity = 0;  // bit i: phase parity to wait for on barrier i
-    const int n_items = (int)((PV + vg_per_item - 1) / vg_per_item);
     const int KK = K1 * K1;
     const int woff = lane < K1 ? lane * K1 : -1;  // writer lanes of v_flush
     uint32_t acc = 0;
 
-    for (int tt = 0; tt < n_st; ++tt) {
-        const int t = (int)((blockIdx.x + tt) % (unsigned)n_st);
+    // A CTA starts on its home super-tile (blockIdx mod n_st) and drains it together with the
+    // other CTAs that call it home.  Afterwards it helps the super-tile with the most
+    // unclaimed items — but only when that is worth staging another 64 KB tile for
+    // (>= HELP_MIN items left), or when the tile has no home CTA at all (small grids).
+    constexpr int HELP_MIN = 8 * CFG::warps;
+    for (bool first = true;; first = false) {
         __syncthreads();  // every warp has left the previous super-tile
-        if (tid == 0) s_flag = *(volatile int *)(counters + t) < n_items;
+        if (warp == 0) {
+            int best = -1, best_t = -1;
+            if (first) {
+                best_t = (int)(blockIdx.x % (unsigned)n_st);
+                best = 1;
+            } else {
+                for (int tt = lane; tt < n_st; tt += 32) {
+                    const int rem = item_off[tt + 1] - item_off[tt] - *(volatile int *)(counters + tt);
+                    const bool homeless = tt >= (int)gridDim.x;
+                    if (rem > 0 && (rem >= HELP_MIN || homeless) && rem > best) {
+                        best = rem;
+                        best_t = tt;
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const int b2 = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int t2 = __shfl_xor_sync(0xffffffffu, best_t, o);
+                    if (b2 > best || (b2 == best && t2 > best_t)) {
+                        best = b2;
+                        best_t = t2;
+                    }
+                }
+            }
+            if (lane == 0) s_flag = best > 0 ? best_t : -1;
+        }
         __syncthreads();
-        if (!s_flag) continue;  // already drained by other CTAs
+        const int t = s_flag;
+        if (t < 0) break;
+        const int item0 = item_off[t], n_items = item_off[t + 1] - item0;
         const int s0 = st_seg0[t], s1 = st_seg0[t + 1];
         const int nsg = s1 - s0;
         if (tid < nsg) s_cls[tid] = (seg_class ? seg_class[s0 + tid] : 0) * KK;
@@ -162,18 +196,17 @@ k_stream_v(const uint32_t *__restrict__ vpacked, const int32_t *__restrict__ run
         __syncthreads();
         if (tid == 0) st[c1 & (SPAN - 1)] = PRB_SX_NONE;  // the slot padding words point at: x_j = 0
         __syncthreads();
-        const int32_t tile_first_row = tile_row0[t];
+        const int32_t tile_first_row = tile_row0[t], tile_rows = tile_row0[t + 1] - tile_first_row;
+        // work items are fixed-size row ranges of the super-tile's block (balanced whatever
+        // the density of a gene); the next one is claimed while the current one is counted
+        int claim = lane == 0 ? atomicAdd(counters + t, 1) : 0;
         for (;;) {
-            int item = 0;
-            if (lane == 0) item = atomicAdd(counters + t, 1);
-            item = __shfl_sync(0xffffffffu, item, 0);
+            const int item = __shfl_sync(0xffffffffu, claim, 0);
             if (item >= n_items) break;
-            const int64_t vg_a = (int64_t)item * vg_per_item;
-            const int64_t vg_b = min(vg_a + vg_per_item, PV);
-            // the item's rows are contiguous: [row_begin, row_begin + nrows)
-            const int row_begin = vg_a ? __ldg(run_end + (vg_a - 1) * n_seg + (s1 - 1)) : tile_first_row;
-            const int nrows = __ldg(run_end + (vg_b - 1) * n_seg + (s1 - 1)) - row_begin;
-            if (nrows <= 0) continue;
+            if (lane == 0) claim = atomicAdd(counters + t, 1);
+            const int row_off = item * rows_per_item;  // rows [row_off, row_off + nrows) of the tile
+            const int nrows = min(rows_per_item, tile_rows - row_off);
+            const int row_begin = tile_first_row + row_off;
             const int nstg = (nrows + SR - 1) / SR;
             // stage b of the item lives in ring slot b % STAGES; row 0 <-> ring slot 0 (all
             // copies of the previous item were consumed)
@@ -193,6 +226,8 @@ k_stream_v(const uint32_t *__restrict__ vpacked, const int32_t *__restrict__ run
                 for (int i = 0; i < STAGES; ++i)
                     if (i < nstg) issue();
             }
+            // first virtual gene with a run that ends past the item's first row
+            const int64_t vg_a = __ldg(item_vg0 + item0 + item);
             int wait_slot = 0;  // ring slot of the next stage to wait for
             int r = 0;          // next row to count (relative to row_begin)
             int limit = 0;      // rows below it are in shared memory (next stage boundary)
@@ -202,9 +237,9 @@ k_stream_v(const uint32_t *__restrict__ vpacked, const int32_t *__restrict__ run
             int v = (int)(vg_a - g * K1);
             int32_t ends_next = lane < nsg ? __ldg(run_end + vg_a * n_seg + s0 + lane) : 0;
 #pragma unroll 1
-            for (int64_t vg = vg_a; vg < vg_b; ++vg) {
+            for (int64_t vg = vg_a; r < nrows; ++vg) {
                 const int32_t ends = ends_next - row_begin;
-                if (vg + 1 < vg_b && lane < nsg)
+                if (vg + 1 < PV && lane < nsg)
                     ends_next = __ldg(run_end + (vg + 1) * n_seg + s0 + lane);
                 int32_t *og = hits + g * (int64_t)C * KK + v;
                 if (++v == K1) {
@@ -213,8 +248,9 @@ k_stream_v(const uint32_t *__restrict__ vpacked, const int32_t *__restrict__ run
                 }
 #pragma unroll 1
                 for (int seg = 0; seg < nsg; ++seg) {
-                    const int e = __shfl_sync(0xffffffffu, ends, seg);
-                    if (e == r) continue;  // empty run
+                    // the part of run (vg, seg) inside the item: rows [r, e)
+                    const int e = min(__shfl_sync(0xffffffffu, ends, seg), nrows);
+                    if (e <= r) continue;  // empty, or entirely before the item
                     int32_t *oseg = og + s_cls[seg];
                     for (;;) {
                         const int stop = min(min(e, limit), fb);
@@ -248,7 +284,7 @@ k_stream_v(const uint32_t *__restrict__ vpacked, const int32_t *__restrict__ run
                             rp = ring + (r & (RING_ROWS - 1)) * 32;
                         }
                     }
-                    v_flush(acc, oseg, woff, lane);
+                    v_flush(acc, oseg, woff, lane);  // hits are added to: partial runs are fine
                     fb = r + 255;
                 }
             }
@@ -432,6 +468,18 @@ static int v_span()
 
 extern "C" int prb_v_tile_span(void) { return v_span(); }
 
+// warps of one launch of the active configuration (to size the work items)
+extern "C" int prb_v_warps(void)
+{
+    int w = VCfg0::warps;
+    switch (v_cfg()) {
+        case 1: w = VCfg1::warps; break;
+        case 2: w = VCfg2::warps; break;
+        case 3: w = VCfg3::warps; break;
+    }
+    return w * devinfo().sm_count;
+}
+
 extern "C" int prb_v_tile_capacity(int64_t *max_cells, int *max_segs)
 {
     // a super-tile's shift codes sit in shared memory at (cell id mod SPAN); 16 cells of
@@ -482,25 +530,23 @@ extern "C" int prb_stream_v(const uint32_t *vpacked, const int32_t *run_end,
                             int64_t v_rows, const int32_t *st_seg0, const int32_t *seg_cell0,
                             const int32_t *seg_class, int n_st, int64_t max_tile_cells,
                             const uint8_t *sx, int C, int32_t *hits, int32_t *counters,
-                            prb_stream_t stream)
+                            int rows_per_item, const int32_t *item_off, const int32_t *item_vg0,
+                            int64_t n_items, prb_stream_t stream)
 {
     if (P == 0 || v_rows == 0) return 0;
     PRB_REQUIRE(K1 >= 1 && K1 <= 4, "the register-counter path needs K <= 5");
     PRB_REQUIRE(n_seg >= 1 && n_st >= 1 && C >= 1 && sx != nullptr, "bad segment plan");
+    PRB_REQUIRE(rows_per_item >= 1 && item_off && item_vg0 && n_items >= 1, "bad item plan");
     PRB_REQUIRE(max_tile_cells <= v_span() - 32, "super-tile spans too many cells");
     PRB_CUDA(cudaMemsetAsync(counters, 0, sizeof(int32_t) * n_st, S(stream)));
     const int64_t PV = P * K1;
     auto launch = [&](auto kern, int smem, int warps) -> int {
-        // ~16 work items per warp and super-tile
-        const int64_t warps_per_tile = hmax(1, (int64_t)devinfo().sm_count * warps / n_st);
-        const int gpi = (int)hmin(1024, hmax(1, PV / (warps_per_tile * 16)));
-        const int64_t n_items = ceil_div(PV, gpi) * n_st;
         const int grid = (int)hmax(1, hmin(devinfo().sm_count, ceil_div(n_items, warps)));
         PRB_REQUIRE(smem + 512 <= devinfo().smem_optin, "not enough shared memory per block");
         PRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         kern<<<grid, warps * 32, smem, S(stream)>>>(vpacked, run_end, tile_row0, n_seg, PV, K1,
                                                     st_seg0, seg_cell0, seg_class, n_st, sx, C, hits,
-                                                    counters, gpi);
+                                                    counters, rows_per_item, item_off, item_vg0);
         return 0;
     };
     switch (v_cfg()) {

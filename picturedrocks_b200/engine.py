@@ -83,6 +83,7 @@ class Engine:
         self.ha = torch.zeros(256, dtype=torch.int32, device=dev)
         self.n_hs_dev = torch.zeros(1, dtype=torch.int32, device=dev)
         self.counters = torch.zeros(8192, dtype=torch.int32, device=dev)
+        self.ticket = torch.zeros(4, dtype=torch.int32, device=dev)
         self._plans = {}
         self._tps = {}
         self.vmode = USE_VLAYOUT and self.K1 <= 4
@@ -259,8 +260,23 @@ class Engine:
         nat.call("prb_v_scatter", nat.ptr(self.packed), nat.ptr(self.indptr), P,
                  nat.ptr(seg_of_cell), n_seg, K1, nat.ptr(seglen), nat.ptr(run_end),
                  nat.ptr(seg_pad), nat.ptr(vpacked), nat.ptr(self.counters), nat.stream())
+        # work items: fixed-size row ranges of every super-tile's block, ~16 per warp
+        warps = nat.load().prb_v_warps()
+        R = int(os.environ.get("PRB_V_ITEM_ROWS", 0)) or max(64, -(-v_rows // (16 * warps)))
+        R = (R + 31) & ~31
+        item_off, vg0 = [0], []
+        for t in range(pl["n_st"]):
+            n_it = -(-(tile_row0[t + 1] - tile_row0[t]) // R)
+            if n_it:
+                q = tile_row0[t] + R * torch.arange(n_it, dtype=torch.int32, device=dev)
+                vg0.append(torch.searchsorted(run_end[:, st[t + 1] - 1].contiguous(), q,
+                                              right=True).to(torch.int32))
+            item_off.append(item_off[-1] + n_it)
+        item_vg0 = (torch.cat(vg0) if vg0 else torch.zeros(1, dtype=torch.int32, device=dev))
         self.v = dict(plan=pl, vpacked=vpacked, run_end=run_end, seglen=seglen, rows=v_rows,
-                      tile_row0=torch.tensor(tile_row0, dtype=torch.int32, device=dev))
+                      tile_row0=torch.tensor(tile_row0, dtype=torch.int32, device=dev),
+                      item_rows=R, n_items=item_off[-1], item_vg0=item_vg0.contiguous(),
+                      item_off=torch.tensor(item_off, dtype=torch.int32, device=dev))
         self.epoch += 1
         return self.v
 
@@ -306,7 +322,8 @@ class Engine:
                  nat.ptr(pl["st_seg0"]),
                  nat.ptr(pl["seg_cell0"]), nat.ptr(pl["seg_class"]) if with_y else None,
                  pl["n_st"], pl["max_cells"], nat.ptr(sx), C, nat.ptr(hits),
-                 nat.ptr(self.counters), nat.stream())
+                 nat.ptr(self.counters), v["item_rows"], nat.ptr(v["item_off"]),
+                 nat.ptr(v["item_vg0"]), v["n_items"], nat.stream())
 
     # --------------------------------------------------------------- primitives
     def hits_buffer(self, n_bins):
@@ -358,8 +375,10 @@ class Engine:
         return 1, None, self.cnt_x, self.clsz_all
 
     def scatter_selected_gene(self):
-        """x_j[N] <- dense codes of gene *gene_ptr (owner rank), replicated to all ranks."""
-        self.xj.zero_()
+        """x_j[N] <- dense codes of gene *gene_ptr (owner rank), replicated to all ranks.
+        (V path: prb_state_v hands x_j back all-zero, so no memset is needed.)"""
+        if not self.vmode:
+            self.xj.zero_()
         nat.call("prb_scatter_gene_u8", nat.ptr(self.packed), nat.ptr(self.indptr),
                  nat.ptr(self.gene_ptr), _i32(self.gene_lo), self.P, nat.ptr(self.xj),
                  nat.stream())
@@ -378,7 +397,8 @@ class Engine:
         if self.vmode:
             nat.call("prb_state_v", nat.ptr(self.xj), nat.ptr(y), self.N, C, self.K,
                      nat.ptr(self.state_buf), nat.ptr(self.hsize), nat.ptr(self.hs_begin),
-                     nat.ptr(self.hs_y), nat.ptr(self.hs_ysum), nat.ptr(self.ha), nat.stream())
+                     nat.ptr(self.hs_y), nat.ptr(self.hs_ysum), nat.ptr(self.ha),
+                     nat.ptr(self.ticket), nat.stream())
             hits = self.hits_buffer(n_bins)
             self._stream_v(with_y, self.state_buf, C, hits)
             self._finalize(hits, cnt, clsz, C, n_hs, None, out_full, out_marg, True)

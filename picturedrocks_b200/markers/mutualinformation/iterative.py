@@ -96,23 +96,25 @@ class _DeviceScores:
         return v.cpu().numpy()
 
     # -- device steps ---------------------------------------------------------
-    def pick_best(self):
-        """best_idx <- argmax(score) (global index; lowest index on ties)."""
+    def pick_and_commit(self):
+        """best_idx <- argmax(score) (global index; lowest index on ties), then commit it:
+        gene_ptr <- best, S.append(best), selected[best] = 1."""
         s = nat.stream()
+        e = self.engine
         if not self.cand_valid:
             nat.call("prb_argmax_blocks", nat.ptr(self.score), self.P, ctypes.c_int32(self.gene_lo),
                      nat.ptr(self.cand_score), nat.ptr(self.cand_idx), s)
+        commit = (nat.ptr(e.gene_ptr), nat.ptr(self.S_dev), nat.ptr(self.n_sel),
+                  nat.ptr(self.selected), ctypes.c_int32(self.gene_lo), self.P, s)
+        if self.comm is None:
+            nat.call("prb_argmax_commit", nat.ptr(self.cand_score), nat.ptr(self.cand_idx),
+                     self.n_blocks, 1, nat.ptr(self.best_score), nat.ptr(self.best_idx), *commit)
+            return
         nat.call("prb_argmax_final", nat.ptr(self.cand_score), nat.ptr(self.cand_idx),
                  self.n_blocks, 1, nat.ptr(self.best_score), nat.ptr(self.best_idx), s)
-        if self.comm is not None:
-            g = self.comm.all_gather_cat(self.best)  # [world][score, idx]
-            nat.call("prb_argmax_final", nat.ptr(g), nat.ptr(g) + 8, self.comm.world, 2,
-                     nat.ptr(self.best_score), nat.ptr(self.best_idx), s)
-
-    def commit_best(self):
-        nat.call("prb_commit_add", nat.ptr(self.best_idx), nat.ptr(self.engine.gene_ptr),
-                 nat.ptr(self.S_dev), nat.ptr(self.n_sel), nat.ptr(self.selected),
-                 ctypes.c_int32(self.gene_lo), self.P, nat.stream())
+        g = self.comm.all_gather_cat(self.best)  # [world][score, idx]
+        nat.call("prb_argmax_commit", nat.ptr(g), nat.ptr(g) + 8, self.comm.world, 2,
+                 nat.ptr(self.best_score), nat.ptr(self.best_idx), *commit)
 
     def apply(self, kind, is_remove, host_ind=None):
         """penalty/score update for the gene in engine.gene_ptr."""
@@ -207,8 +209,7 @@ class _GreedyDevice(IterativeFeatureSelection):
 
     def _one_step(self):
         d = self._d
-        d.pick_best()
-        d.commit_best()
+        d.pick_and_commit()
         d.apply(self._kind, False)
 
     def _capture(self):
