@@ -350,3 +350,59 @@ def test_v_layout_fewer_bins(pr, O, K):
     a.autoselect(5)
     b.autoselect(5)
     assert a.S == [int(s) for s in b.S] and np.array_equal(a.score, b.score)
+
+
+@pytest.mark.timeout(900)
+def test_full_size_config4_sampled_genes(pr, O):
+    """BASELINE.json configs[3] at FULL size (1,306,127 x 27,998, 60 classes) on the GPU; the
+    CPU oracle recomputes the same quantities for a sample of candidate genes (the synthetic
+    matrix is a counter-based hash, so any column can be regenerated on the host):
+    entropy_wrt([]) / ([-1]) / ([j]) / ([-1, j]) bit-identical on the sample, plus
+    size-independent properties of the full vectors."""
+    import torch
+    from picturedrocks_b200.synth import DiscretisedSpec
+
+    import gc
+
+    gc.collect()
+    torch.cuda.empty_cache()
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40 << 30:
+        pytest.skip("needs ~30 GB of free device memory")
+    spec = DiscretisedSpec(N=1306127, P=27998, C=60, K=5, mean_density=0.07, seed=4)
+    eng, yd = spec.device_engine()
+    inf = pr.markers.SparseInformationSet._from_engine(eng, yd)
+    y = spec.cpu_labels()
+    assert np.array_equal(yd.cpu().numpy(), y)
+    j = 24255  # the first gene CIFE selects on this matrix
+    sample = [0, 1, 17, 18, 29, 4018, 11955, 12806, 13999, 20000, 27997, j]
+    Xs = spec.cpu_csc(sample, y)
+    ora = O.SparseInformationSet(Xs, y, nthreads=O.max_threads())
+    jj = len(sample) - 1
+    got = {c: inf.entropy_wrt(np.array(c, dtype=np.int64)) for c in ((), (-1,), (j,), (-1, j))}
+    want = {(): ora.entropy_wrt(np.arange(0)), (-1,): ora.entropy_wrt(np.array([-1])),
+            (j,): ora.entropy_wrt(np.array([jj])), (-1, j): ora.entropy_wrt(np.array([-1, jj]))}
+    for c in got:
+        assert got[c].shape == (spec.P,)
+        assert np.array_equal(got[c][sample], want[c]), c
+    Hx, Hyx, Hjx, Hyjx = got[()], got[(-1,)], got[(j,)], got[(-1, j)]
+    Hy, Hj, Hyj = inf.entropy([-1]), inf.entropy([j]), inf.entropy([-1, j])
+    assert Hy == ora.entropy(np.array([-1])) and Hj == ora.entropy(np.array([jj]))
+    assert Hyj == ora.entropy(np.array([-1, jj]))
+    eps = 1e-9
+    # H(A,B) >= max(H(A), H(B)) and <= H(A) + H(B), for every candidate gene
+    assert np.all(Hyx >= np.maximum(Hx, Hy) - eps) and np.all(Hyx <= Hx + Hy + eps)
+    assert np.all(Hjx >= np.maximum(Hx, Hj) - eps) and np.all(Hjx <= Hx + Hj + eps)
+    assert np.all(Hyjx >= np.maximum(Hyx, Hjx) - eps) and np.all(Hyjx <= Hyx + Hj + eps)
+    # x_i = x_j: the joint with itself adds nothing; planted duplicate / all-zero genes
+    assert Hjx[j] == Hj and Hyjx[j] == Hyj
+    assert Hx[4018] == Hx[4017] and Hyjx[4018] == Hyjx[4017]  # planted duplicate
+    assert Hx[29] == 0.0 and Hjx[29] == Hj and Hyjx[29] == Hyj  # planted all-zero gene
+    # exported matrix (original cell order) equals the host regeneration on the sample
+    Xg = eng.to_scipy_csc(30)
+    Xh = spec.cpu_csc(range(30), y)
+    assert np.array_equal(Xg.indptr, Xh.indptr) and np.array_equal(Xg.indices, Xh.indices)
+    assert np.array_equal(Xg.data, Xh.data)
+    fs = pr.markers.CIFE(inf)
+    fs.autoselect(3)
+    assert fs.S[0] == j and len(set(fs.S)) == 3
