@@ -115,11 +115,13 @@ int prb_stream_hits(const uint32_t *packed, const int64_t *tp, int64_t P, int64_
  *     ticket: device int32, zero on entry and on exit).  x_j is read and RESET to zero,
  *     so the next prb_scatter_gene_u8 needs no memset.
  *  5. prb_stream_v adds the joint counts to hits int32[P][C][K-1][K-1]
- *     (bin = (x_j-1)*(K-1) + x_g-1).  Work items are fixed-size row ranges: item k of
- *     super-tile t = rows [k*rows_per_item, (k+1)*rows_per_item) of its block;
- *     item_off int32[n_st+1] = first item id of every super-tile; item_vg0 int32[n_items]
- *     = first virtual gene with a run ending past the item's first row (a searchsorted of
- *     run_end, by the caller; prb_v_warps() = warps of one launch, to size the items).
+ *     (bin = (x_j-1)*(K-1) + x_g-1).  Work items are consecutive row ranges of a
+ *     super-tile's block (large first, small last): item_off int32[n_st+1] = first item id
+ *     of every super-tile; item_row0 int32[n_items + n_st] = first row of every item, the
+ *     items of tile t followed by one sentinel (end of its block), i.e. item k of tile t is
+ *     entry item_off[t] + t + k; item_vg0 int32[n_items] = first virtual gene with a run
+ *     ending past the item's first row (a searchsorted of run_end, by the caller;
+ *     prb_v_warps() = warps of one launch, to size the items).
  *     counters: int32[n_st] scratch (reset by the call); queue: device int32 scratch. */
 int prb_class_sort(const uint32_t *packed_in, const int64_t *indptr, int64_t P,
                    const int32_t *newpos, const int32_t *cls, int C, uint32_t *packed_out,
@@ -139,7 +141,7 @@ int prb_stream_v(const uint32_t *vpacked, const int32_t *run_end, const int32_t 
                  int n_seg, int64_t P, int K1, int64_t v_rows, const int32_t *st_seg0,
                  const int32_t *seg_cell0, const int32_t *seg_class, int n_st,
                  int64_t max_tile_cells, const uint8_t *sx, int C, int32_t *hits,
-                 int32_t *counters, int rows_per_item, const int32_t *item_off,
+                 int32_t *counters, const int32_t *item_off, const int32_t *item_row0,
                  const int32_t *item_vg0, int64_t n_items, prb_stream_t stream);
 int prb_v_warps(void);
 /* cells per super-tile modulus (power of two) of the active kernel configuration */

@@ -40,7 +40,7 @@ _SIGS = {
     "prb_v_scatter": [_vp, _vp, _i64, _vp, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp],
     "prb_v_tile_span": [],
     "prb_stream_v": [_vp, _vp, _vp, _int, _i64, _int, _i64, _vp, _vp, _vp, _int, _i64, _vp, _int,
-                     _vp, _vp, _int, _vp, _vp, _i64, _vp],
+                     _vp, _vp, _vp, _vp, _vp, _i64, _vp],
     "prb_v_warps": [],
     "prb_scatter_gene_u8": [_vp, _vp, _vp, _i32, _i64, _vp, _vp],
     "prb_scatter_gene_or32": [_vp, _vp, _i64, _int, _vp, _vp],

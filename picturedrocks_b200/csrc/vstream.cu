@@ -101,9 +101,13 @@ __device__ __forceinline__ void v_flush(uint32_t &acc, int32_t *out, int woff, i
 // segment), so the virtual genes of one work item are ONE contiguous row range:
 //   run_end   int32[PV][n_seg] : row just past run (vg, s);  PV = P*K1
 //   tile_row0 int32[n_st+1]    : first row of every super-tile's block
-// Work items: rows [k*rows_per_item, (k+1)*rows_per_item) of a super-tile's block;
-//   item_off int32[n_st+1]     : first item id of every super-tile
-//   item_vg0 int32[n_items]    : first virtual gene with a run ending past the item's first row
+// Work items: consecutive row ranges of a super-tile's block, large first and small last
+// (the tail of a launch is one item long);
+//   item_off  int32[n_st+1]        : first item id of every super-tile
+//   item_row0 int32[n_items+n_st]  : first row of every item; after the items of tile t comes
+//                                    one sentinel (= end of the block), i.e. item k of tile t
+//                                    is entry item_off[t] + t + k
+//   item_vg0  int32[n_items]       : first virtual gene with a run ending past the item's first row
 // Padding words of a run point at the cell slot just past their super-tile, which the tile
 // loader sets to "x_j = 0", so every row is counted the same way (no lane masks).
 // sx: uint8[N] shift codes 8*(x_j-1), >= 32 where x_j = 0 (prb_state_v).
@@ -114,8 +118,8 @@ k_stream_v(const uint32_t *__restrict__ vpacked, const int32_t *__restrict__ run
            const int32_t *__restrict__ tile_row0, int n_seg, int64_t PV, int K1,
            const int32_t *__restrict__ st_seg0, const int32_t *__restrict__ seg_cell0,
            const int32_t *__restrict__ seg_class, int n_st, const uint8_t *__restrict__ sx, int C,
-           int32_t *__restrict__ hits, int *counters, int rows_per_item,
-           const int32_t *__restrict__ item_off, const int32_t *__restrict__ item_vg0)
+           int32_t *__restrict__ hits, int *counters, const int32_t *__restrict__ item_off,
+           const int32_t *__restrict__ item_row0, const int32_t *__restrict__ item_vg0)
 {
     constexpr int SPAN = CFG::span, SR = CFG::stage_rows, STAGES = CFG::stages;
     constexpr int STAGE_BYTES = CFG::stage_bytes, THREADS = CFG::threads;
@@ -196,7 +200,6 @@ k_stream_v(const uint32_t *__restrict__ vpacked, const int32_t *__restrict__ run
         __syncthreads();
         if (tid == 0) st[c1 & (SPAN - 1)] = PRB_SX_NONE;  // the slot padding words point at: x_j = 0
         __syncthreads();
-        const int32_t tile_first_row = tile_row0[t], tile_rows = tile_row0[t + 1] - tile_first_row;
         // work items are fixed-size row ranges of the super-tile's block (balanced whatever
         // the density of a gene); the next one is claimed while the current one is counted
         int claim = lane == 0 ? atomicAdd(counters + t, 1) : 0;
@@ -204,9 +207,10 @@ k_stream_v(const uint32_t *__restrict__ vpacked, const int32_t *__restrict__ run
             const int item = __shfl_sync(0xffffffffu, claim, 0);
             if (item >= n_items) break;
             if (lane == 0) claim = atomicAdd(counters + t, 1);
-            const int row_off = item * rows_per_item;  // rows [row_off, row_off + nrows) of the tile
-            const int nrows = min(rows_per_item, tile_rows - row_off);
-            const int row_begin = tile_first_row + row_off;
+            // rows [row_begin, row_begin + nrows) of the layout (item t's own entry of
+            // item_row0 is followed by a sentinel = end of the tile's block)
+            const int row_begin = __ldg(item_row0 + item0 + t + item);
+            const int nrows = __ldg(item_row0 + item0 + t + item + 1) - row_begin;
             const int nstg = (nrows + SR - 1) / SR;
             // stage b of the item lives in ring slot b % STAGES; row 0 <-> ring slot 0 (all
             // copies of the previous item were consumed)
@@ -530,13 +534,13 @@ extern "C" int prb_stream_v(const uint32_t *vpacked, const int32_t *run_end,
                             int64_t v_rows, const int32_t *st_seg0, const int32_t *seg_cell0,
                             const int32_t *seg_class, int n_st, int64_t max_tile_cells,
                             const uint8_t *sx, int C, int32_t *hits, int32_t *counters,
-                            int rows_per_item, const int32_t *item_off, const int32_t *item_vg0,
-                            int64_t n_items, prb_stream_t stream)
+                            const int32_t *item_off, const int32_t *item_row0,
+                            const int32_t *item_vg0, int64_t n_items, prb_stream_t stream)
 {
     if (P == 0 || v_rows == 0) return 0;
     PRB_REQUIRE(K1 >= 1 && K1 <= 4, "the register-counter path needs K <= 5");
     PRB_REQUIRE(n_seg >= 1 && n_st >= 1 && C >= 1 && sx != nullptr, "bad segment plan");
-    PRB_REQUIRE(rows_per_item >= 1 && item_off && item_vg0 && n_items >= 1, "bad item plan");
+    PRB_REQUIRE(item_off && item_row0 && item_vg0 && n_items >= 1, "bad item plan");
     PRB_REQUIRE(max_tile_cells <= v_span() - 32, "super-tile spans too many cells");
     PRB_CUDA(cudaMemsetAsync(counters, 0, sizeof(int32_t) * n_st, S(stream)));
     const int64_t PV = P * K1;
@@ -546,7 +550,7 @@ extern "C" int prb_stream_v(const uint32_t *vpacked, const int32_t *run_end,
         PRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         kern<<<grid, warps * 32, smem, S(stream)>>>(vpacked, run_end, tile_row0, n_seg, PV, K1,
                                                     st_seg0, seg_cell0, seg_class, n_st, sx, C, hits,
-                                                    counters, rows_per_item, item_off, item_vg0);
+                                                    counters, item_off, item_row0, item_vg0);
         return 0;
     };
     switch (v_cfg()) {

@@ -260,22 +260,33 @@ class Engine:
         nat.call("prb_v_scatter", nat.ptr(self.packed), nat.ptr(self.indptr), P,
                  nat.ptr(seg_of_cell), n_seg, K1, nat.ptr(seglen), nat.ptr(run_end),
                  nat.ptr(seg_pad), nat.ptr(vpacked), nat.ptr(self.counters), nat.stream())
-        # work items: fixed-size row ranges of every super-tile's block, ~16 per warp
+        # work items: consecutive row ranges of every super-tile's block, ~16 per warp on
+        # average; the first 3/4 of a block in large items, then two rounds of smaller ones,
+        # so that the tail of a launch is short
         warps = nat.load().prb_v_warps()
-        R = int(os.environ.get("PRB_V_ITEM_ROWS", 0)) or max(64, -(-v_rows // (16 * warps)))
+        R = int(os.environ.get("PRB_V_ITEM_ROWS", 0)) or max(256, -(-v_rows // (12 * warps)))
         R = (R + 31) & ~31
-        item_off, vg0 = [0], []
+        item_off, row0, vg0 = [0], [], []
         for t in range(pl["n_st"]):
-            n_it = -(-(tile_row0[t + 1] - tile_row0[t]) // R)
-            if n_it:
-                q = tile_row0[t] + R * torch.arange(n_it, dtype=torch.int32, device=dev)
+            lo, hi = tile_row0[t], tile_row0[t + 1]
+            cuts, pos = [], lo
+            for frac, size in ((0.75, R), (0.92, max(256, R // 2)), (1.0, max(128, R // 4))):
+                stop = lo + int((hi - lo) * frac) if frac < 1.0 else hi
+                while pos < stop:
+                    cuts.append(pos)
+                    pos = min(pos + size, hi)
+            if cuts:
+                q = torch.tensor(cuts, dtype=torch.int32, device=dev)
                 vg0.append(torch.searchsorted(run_end[:, st[t + 1] - 1].contiguous(), q,
                                               right=True).to(torch.int32))
-            item_off.append(item_off[-1] + n_it)
+            row0.extend(cuts)
+            row0.append(hi)  # sentinel
+            item_off.append(item_off[-1] + len(cuts))
         item_vg0 = (torch.cat(vg0) if vg0 else torch.zeros(1, dtype=torch.int32, device=dev))
         self.v = dict(plan=pl, vpacked=vpacked, run_end=run_end, seglen=seglen, rows=v_rows,
                       tile_row0=torch.tensor(tile_row0, dtype=torch.int32, device=dev),
                       item_rows=R, n_items=item_off[-1], item_vg0=item_vg0.contiguous(),
+                      item_row0=torch.tensor(row0, dtype=torch.int32, device=dev),
                       item_off=torch.tensor(item_off, dtype=torch.int32, device=dev))
         self.epoch += 1
         return self.v
@@ -322,7 +333,7 @@ class Engine:
                  nat.ptr(pl["st_seg0"]),
                  nat.ptr(pl["seg_cell0"]), nat.ptr(pl["seg_class"]) if with_y else None,
                  pl["n_st"], pl["max_cells"], nat.ptr(sx), C, nat.ptr(hits),
-                 nat.ptr(self.counters), v["item_rows"], nat.ptr(v["item_off"]),
+                 nat.ptr(self.counters), nat.ptr(v["item_off"]), nat.ptr(v["item_row0"]),
                  nat.ptr(v["item_vg0"]), v["n_items"], nat.stream())
 
     # --------------------------------------------------------------- primitives
