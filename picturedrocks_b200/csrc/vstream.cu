@@ -123,8 +123,6 @@ k_stream_v(const uint32_t *__restrict__ vpacked, const int32_t *__restrict__ run
 {
     constexpr int SPAN = CFG::span, SR = CFG::stage_rows, STAGES = CFG::stages;
     constexpr int STAGE_BYTES = CFG::stage_bytes, THREADS = CFG::threads;
-    constexpr int RING_ROWS = SR * STAGES;
-    static_assert((RING_ROWS & (RING_ROWS - 1)) == 0, "ring rows must be a power of two");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ int s_flag;
     __shared__ int s_cls[V_MAX_SEGS + 1];
@@ -283,9 +281,9 @@ k_stream_v(const uint32_t *__restrict__ vpacked, const int32_t *__restrict__ run
                             }
                             v_mbar_wait(bar_s + 8 * wait_slot, (parity >> wait_slot) & 1u);
                             parity ^= 1u << wait_slot;
+                            rp = ring + wait_slot * (SR * 32);  // row r opens this stage
                             wait_slot = wait_slot + 1 == STAGES ? 0 : wait_slot + 1;
                             limit = min(nrows, r + SR);
-                            rp = ring + (r & (RING_ROWS - 1)) * 32;
                         }
                     }
                     v_flush(acc, oseg, woff, lane);  // hits are added to: partial runs are fine
@@ -445,10 +443,10 @@ using namespace prb;
 
 // Kernel configurations (cells per super-tile, rows per stage, stages per warp, warps per
 // CTA); all fit the 227 KB of shared memory.  PRB_V_CFG selects one for tuning runs.
-using VCfg0 = VCfg<1 << 16, 16, 2, 32>;  //  64 KB of shift codes + 32 warps x 2 x 2 KB
-using VCfg1 = VCfg<1 << 15, 32, 2, 24>;  //  32 KB + 24 x 2 x 4 KB
-using VCfg2 = VCfg<1 << 16, 32, 2, 16>;  //  64 KB + 16 x 2 x 4 KB
-using VCfg3 = VCfg<1 << 15, 16, 4, 24>;  //  32 KB + 24 x 4 x 2 KB
+using VCfg0 = VCfg<1 << 16, 20, 2, 32>;  //  64 KB of shift codes + 32 warps x 2 x 2.5 KB
+using VCfg1 = VCfg<1 << 16, 16, 2, 32>;  //  64 KB + 32 x 2 x 2 KB
+using VCfg2 = VCfg<1 << 16, 26, 2, 24>;  //  64 KB + 24 x 2 x 3.25 KB
+using VCfg3 = VCfg<1 << 16, 13, 3, 32>;  //  64 KB + 32 x 3 x 1.625 KB
 
 static int v_cfg()
 {
