@@ -89,9 +89,10 @@ int prb_stream_hits(const uint32_t *packed, const int64_t *tp, int64_t P, int64_
  * its run lengths, the class-conditional count tables behind entropy_wrt([]) / ([-1])
  * (ITER:30, 32), on a private re-ordering of the matrix (a histogram does not depend on the
  * order in which cells are visited):
- *  1. prb_class_sort relabels the cells so that classes are contiguous (out word =
- *     code | newpos[row], every gene's entries stably partitioned by cls[row] — int32[N],
- *     class of the CURRENT cell id; newpos must be increasing inside a class).
+ *  1. newpos int32[N] relabels the cells so that classes are contiguous (a stable sort of
+ *     the labels, by the caller; NULL = identity).  The generic packed CSC keeps the
+ *     original cell ids; only the V layout and the per-cell vectors of this path (x_j, sx,
+ *     the sorted labels) live in the new order.
  *  2. A host-built segment plan cuts the cells into SEGMENTS (a class, or a piece of one)
  *     and packs consecutive segments into SUPER-TILES of at most max_cells cells and
  *     max_segs segments (prb_v_tile_capacity): seg_cell0 int32[n_seg+1] ascending cell
@@ -100,7 +101,7 @@ int prb_stream_hits(const uint32_t *packed, const int64_t *tp, int64_t P, int64_
  *  3. prb_v_count -> caller's scan -> prb_v_scatter build the V layout: every gene g
  *     becomes K-1 virtual genes (g, v), one per non-zero code v; a RUN (vg, s) holds the
  *     entries of virtual gene vg in segment s (seg_of_cell int32[N] = segment of every
- *     cell), ascending, padded to a multiple of 32 entries (one 128-byte row); runs are
+ *     ORIGINAL cell id), relabelled (word = code<<24 | newpos[cell]), ascending, padded to a multiple of 32 entries (one 128-byte row); runs are
  *     stored TILE-MAJOR: by (super-tile of s, vg, s).
  *       seglen    int32[P*(K-1)][n_seg]  true run lengths
  *       run_end   int32[P*(K-1)][n_seg]  row just past each run (inclusive scan of
@@ -123,17 +124,14 @@ int prb_stream_hits(const uint32_t *packed, const int64_t *tp, int64_t P, int64_
  *     ending past the item's first row (a searchsorted of run_end, by the caller;
  *     prb_v_warps() = warps of one launch, to size the items).
  *     counters: int32[n_st] scratch (reset by the call); queue: device int32 scratch. */
-int prb_class_sort(const uint32_t *packed_in, const int64_t *indptr, int64_t P,
-                   const int32_t *newpos, const int32_t *cls, int C, uint32_t *packed_out,
-                   int32_t *queue, prb_stream_t stream);
 int prb_v_tile_capacity(int64_t *max_cells, int *max_segs);
 int prb_v_count(const uint32_t *packed, const int64_t *indptr, int64_t P,
                 const int32_t *seg_of_cell, int n_seg, int K1, int32_t *seglen, int32_t *queue,
                 prb_stream_t stream);
 int prb_v_scatter(const uint32_t *packed, const int64_t *indptr, int64_t P,
-                  const int32_t *seg_of_cell, int n_seg, int K1, const int32_t *seglen,
-                  const int32_t *run_end, const uint32_t *seg_pad, uint32_t *vpacked,
-                  int32_t *queue, prb_stream_t stream);
+                  const int32_t *seg_of_cell, int n_seg, int K1, const int32_t *newpos,
+                  const int32_t *seglen, const int32_t *run_end, const uint32_t *seg_pad,
+                  uint32_t *vpacked, int32_t *queue, prb_stream_t stream);
 int prb_state_v(uint8_t *xj, const int32_t *y, int64_t N, int C, int K, uint8_t *sx,
                 int32_t *hsize, int32_t *hs_begin, int32_t *hs_y, int32_t *hs_ysum, int32_t *ha,
                 int32_t *ticket, prb_stream_t stream);
@@ -149,9 +147,11 @@ int prb_v_tile_span(void);
 
 /* ---- joint-state build ("master column", _sparse_make_master_col INFOSET:431-442) */
 /* dense uint8 x_j[N] (zeroed by caller) <- codes of gene *gene_ptr (device int32;
- * genes outside [gene_lo, gene_lo+P) are ignored: multi-GPU owner test). */
+ * genes outside [gene_lo, gene_lo+P) are ignored: multi-GPU owner test), written at
+ * newpos[cell] (NULL = at cell). */
 int prb_scatter_gene_u8(const uint32_t *packed, const int64_t *indptr, const int32_t *gene_ptr,
-                        int32_t gene_lo, int64_t P, uint8_t *xj, prb_stream_t stream);
+                        int32_t gene_lo, int64_t P, const int32_t *newpos, uint8_t *xj,
+                        prb_stream_t stream);
 /* mpacked[row] |= code << shift_bits for every stored entry of gene `gene`. */
 int prb_scatter_gene_or32(const uint32_t *packed, const int64_t *indptr, int64_t gene,
                           int shift_bits, uint32_t *mpacked, prb_stream_t stream);

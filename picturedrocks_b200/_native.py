@@ -33,16 +33,15 @@ _SIGS = {
                         ctypes.POINTER(_int), ctypes.POINTER(_int), ctypes.POINTER(_i64)],
     "prb_tile_ptrs": [_vp, _vp, _i64, _i64, _int, _vp, _vp],
     "prb_stream_hits": [_vp, _vp, _i64, _i64, _vp, _i64, _i64, _int, _int, _vp, _vp, _vp],
-    "prb_class_sort": [_vp, _vp, _i64, _vp, _vp, _int, _vp, _vp, _vp],
     "prb_state_v": [_vp, _vp, _i64, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "prb_v_tile_capacity": [ctypes.POINTER(_i64), ctypes.POINTER(_int)],
     "prb_v_count": [_vp, _vp, _i64, _vp, _int, _int, _vp, _vp, _vp],
-    "prb_v_scatter": [_vp, _vp, _i64, _vp, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp],
+    "prb_v_scatter": [_vp, _vp, _i64, _vp, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "prb_v_tile_span": [],
     "prb_stream_v": [_vp, _vp, _vp, _int, _i64, _int, _i64, _vp, _vp, _vp, _int, _i64, _vp, _int,
                      _vp, _vp, _vp, _vp, _vp, _i64, _vp],
     "prb_v_warps": [],
-    "prb_scatter_gene_u8": [_vp, _vp, _vp, _i32, _i64, _vp, _vp],
+    "prb_scatter_gene_u8": [_vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp],
     "prb_scatter_gene_or32": [_vp, _vp, _i64, _int, _vp, _vp],
     "prb_state_direct": [_vp, _vp, _i64, _int, _int, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp],
     "prb_state_table": [_vp, _vp, _i64, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
@@ -112,7 +111,7 @@ class PrbError(RuntimeError):
 KERNELS = {
     "prb_pack_csc": 1, "prb_unpack_csc": 1, "prb_dense_count_nnz": 1, "prb_dense_fill_csc": 1,
     "prb_tile_ptrs": 1, "prb_stream_hits": 1,
-    "prb_state_v": 1, "prb_argmax_commit": 1, "prb_class_sort": 1, "prb_v_count": 1, "prb_v_scatter": 1,
+    "prb_state_v": 1, "prb_argmax_commit": 1, "prb_v_count": 1, "prb_v_scatter": 1,
     "prb_stream_v": 1, "prb_scatter_gene_u8": 1,
     "prb_scatter_gene_or32": 1, "prb_state_direct": 2, "prb_state_table": 2, "prb_state_assign": 1, "prb_finalize": 1, "prb_finalize_direct": 1,
     "prb_entropy_keys": 2, "prb_mi_base": 1, "prb_selector_update": 1, "prb_argmax_blocks": 1,

@@ -18,7 +18,7 @@ constexpr int SCATTER_BLOCKS_PER_SM = 4;
 __global__ void k_scatter_u8(const uint32_t *__restrict__ packed,
                              const int64_t *__restrict__ indptr,
                              const int32_t *__restrict__ gene_ptr, int32_t gene_lo, int64_t P,
-                             uint8_t *__restrict__ xj)
+                             const int32_t *__restrict__ newpos, uint8_t *__restrict__ xj)
 {
     const int64_t g = (int64_t)(*gene_ptr) - gene_lo;
     if (g < 0 || g >= P) return;
@@ -26,7 +26,8 @@ __global__ void k_scatter_u8(const uint32_t *__restrict__ packed,
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = b + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < e; i += stride) {
         const uint32_t w = __ldg(packed + i);
-        xj[w & ROW_MASK] = (uint8_t)(w >> 24);
+        const uint32_t cell = w & ROW_MASK;
+        xj[newpos ? (uint32_t)newpos[cell] : cell] = (uint8_t)(w >> 24);
     }
 }
 
@@ -283,10 +284,10 @@ static inline int cell_grid(int64_t N, int threads)
 
 extern "C" int prb_scatter_gene_u8(const uint32_t *packed, const int64_t *indptr,
                                    const int32_t *gene_ptr, int32_t gene_lo, int64_t P,
-                                   uint8_t *xj, prb_stream_t stream)
+                                   const int32_t *newpos, uint8_t *xj, prb_stream_t stream)
 {
     k_scatter_u8<<<devinfo().sm_count * SCATTER_BLOCKS_PER_SM, 256, 0, S(stream)>>>(
-        packed, indptr, gene_ptr, gene_lo, P, xj);
+        packed, indptr, gene_ptr, gene_lo, P, newpos, xj);
     PRB_LAUNCH_CHECK("k_scatter_u8");
     return 0;
 }

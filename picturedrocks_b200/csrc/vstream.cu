@@ -7,8 +7,9 @@
 // of the layout's own segment lengths (no streaming pass at all).
 //
 // V layout (a private re-ordering of the packed by-gene CSC; a histogram does not depend
-// on the order in which cells are visited).  Cells are sorted by class (prb_class_sort)
-// and cut into SEGMENTS (a class, or a piece of one that fits a shared-memory tile).
+// on the order in which cells are visited).  Cells are relabelled so that classes are
+// contiguous (newpos, a stable sort of the labels; only the V layout and the per-cell
+// vectors of this path live in the new order) and cut into SEGMENTS (a class, or a piece of one that fits a shared-memory tile).
 // Every gene g is split into K-1 VIRTUAL GENES (g, v), one per non-zero code v; the
 // entries of a virtual gene are grouped by segment, ascending inside a segment, and every
 // (g, v, segment) run is padded to a multiple of 32 entries (one 128-byte ROW, one entry
@@ -296,64 +297,6 @@ k_stream_v(const uint32_t *__restrict__ vpacked, const int32_t *__restrict__ run
 }
 
 // ---- building the V layout -------------------------------------------------------------
-// Stable partition of every gene's entries by the class of their cell, with the cell ids
-// relabelled: out word = code | newpos[row].  One warp per gene (dynamic queue), two passes:
-// class counts -> exclusive offsets -> ordered scatter (rank inside a 32-entry group by
-// __match_any_sync, so the ascending order inside a class is kept).
-constexpr int CS_WARPS = 8;
-
-__global__ void __launch_bounds__(CS_WARPS * 32)
-k_class_sort(const uint32_t *__restrict__ in, const int64_t *__restrict__ indptr, int64_t P,
-             const int32_t *__restrict__ newpos, const int32_t *__restrict__ cls, int C,
-             uint32_t *__restrict__ out, int *queue)
-{
-    extern __shared__ int off_all[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int *off = off_all + warp * C;
-    for (;;) {
-        int gi = 0;
-        if (lane == 0) gi = atomicAdd(queue, 1);
-        const int64_t g = __shfl_sync(0xffffffffu, gi, 0);
-        if (g >= P) break;
-        const int64_t b = indptr[g], e = indptr[g + 1];
-        for (int i = lane; i < C; i += 32) off[i] = 0;
-        __syncwarp();
-        for (int64_t i = b + lane; i < e; i += 32) atomicAdd(off + cls[in[i] & ROW_MASK], 1);
-        __syncwarp();
-        int carry = 0;
-        for (int c0 = 0; c0 < C; c0 += 32) {
-            const int i = c0 + lane;
-            const int v = i < C ? off[i] : 0;
-            int incl = v;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += t;
-            }
-            if (i < C) off[i] = carry + incl - v;
-            carry += __shfl_sync(0xffffffffu, incl, 31);
-        }
-        __syncwarp();
-        for (int64_t i0 = b; i0 < e; i0 += 32) {
-            const int64_t i = i0 + lane;
-            const bool valid = i < e;
-            const unsigned act = __ballot_sync(0xffffffffu, valid);
-            if (valid) {
-                const uint32_t w = in[i];
-                const uint32_t row = w & ROW_MASK;
-                const int cc = cls[row];
-                const unsigned m = __match_any_sync(act, cc);
-                const int rank = __popc(m & ((1u << lane) - 1u));
-                const int base = off[cc];
-                out[b + base + rank] = (w & ~ROW_MASK) | (uint32_t)newpos[row];
-                __syncwarp(act);
-                if (rank == 0) off[cc] = base + __popc(m);
-            }
-            __syncwarp();
-        }
-    }
-}
-
 // pass 1: per gene, entries per (code, segment) -> seglen[P*K1][n_seg].  One warp per gene
 // (dynamic queue), shared-memory histogram per warp.
 constexpr int VB_WARPS = 8;
@@ -386,14 +329,17 @@ k_vcount(const uint32_t *__restrict__ packed, const int64_t *__restrict__ indptr
 }
 
 // pass 2: ordered scatter into the padded runs (rank inside a 32-entry group by
-// __match_any_sync keeps the ascending cell order inside a run); run (vg, s) occupies rows
+// __match_any_sync keeps the ascending cell order inside a run; cells are relabelled on the
+// way: word = code | newpos[cell], seg_of_cell is indexed by the ORIGINAL cell id, and
+// newpos is increasing inside a class); run (vg, s) occupies rows
 // [run_end - ceil(len/32), run_end); the padding words of segment s are
 // seg_pad[s] = 0xFF000000 | (a cell slot the kernel keeps at "x_j = 0").
 __global__ void __launch_bounds__(VB_WARPS * 32)
 k_vscatter(const uint32_t *__restrict__ packed, const int64_t *__restrict__ indptr, int64_t P,
            const int32_t *__restrict__ seg_of_cell, int n_seg, int K1,
-           const int32_t *__restrict__ seglen, const int32_t *__restrict__ run_end,
-           const uint32_t *__restrict__ seg_pad, uint32_t *__restrict__ vpacked, int *queue)
+           const int32_t *__restrict__ newpos, const int32_t *__restrict__ seglen,
+           const int32_t *__restrict__ run_end, const uint32_t *__restrict__ seg_pad,
+           uint32_t *__restrict__ vpacked, int *queue)
 {
     extern __shared__ int64_t vb_smem64[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -420,7 +366,8 @@ k_vscatter(const uint32_t *__restrict__ packed, const int64_t *__restrict__ indp
                 const unsigned m = __match_any_sync(act, key);
                 const int rank = __popc(m & ((1u << lane) - 1u));
                 const int64_t base = off[key];
-                vpacked[base + rank] = w;
+                vpacked[base + rank] =
+                    newpos ? (w & ~ROW_MASK) | (uint32_t)newpos[w & ROW_MASK] : w;
                 __syncwarp(act);
                 if (rank == 0) off[key] = base + __popc(m);
             }
@@ -509,9 +456,10 @@ extern "C" int prb_v_count(const uint32_t *packed, const int64_t *indptr, int64_
 }
 
 extern "C" int prb_v_scatter(const uint32_t *packed, const int64_t *indptr, int64_t P,
-                             const int32_t *seg_of_cell, int n_seg, int K1, const int32_t *seglen,
-                             const int32_t *run_end, const uint32_t *seg_pad, uint32_t *vpacked,
-                             int32_t *queue, prb_stream_t stream)
+                             const int32_t *seg_of_cell, int n_seg, int K1, const int32_t *newpos,
+                             const int32_t *seglen, const int32_t *run_end,
+                             const uint32_t *seg_pad, uint32_t *vpacked, int32_t *queue,
+                             prb_stream_t stream)
 {
     if (P == 0) return 0;
     PRB_REQUIRE(K1 >= 1 && K1 <= 4 && n_seg >= 1, "bad arguments");
@@ -522,7 +470,8 @@ extern "C" int prb_v_scatter(const uint32_t *packed, const int64_t *indptr, int6
     PRB_CUDA(cudaMemsetAsync(queue, 0, sizeof(int32_t), S(stream)));
     const int grid = (int)hmin(ceil_div(P, VB_WARPS), (int64_t)devinfo().sm_count * 8);
     k_vscatter<<<grid, VB_WARPS * 32, smem, S(stream)>>>(packed, indptr, P, seg_of_cell, n_seg, K1,
-                                                         seglen, run_end, seg_pad, vpacked, queue);
+                                                         newpos, seglen, run_end, seg_pad, vpacked,
+                                                         queue);
     PRB_LAUNCH_CHECK("k_vscatter");
     return 0;
 }
@@ -565,19 +514,5 @@ extern "C" int prb_stream_v(const uint32_t *vpacked, const int32_t *run_end,
             if (launch(k_stream_v<VCfg0>, VCfg0::smem_bytes, VCfg0::warps)) return 1;
     }
     PRB_LAUNCH_CHECK("k_stream_v");
-    return 0;
-}
-
-extern "C" int prb_class_sort(const uint32_t *packed_in, const int64_t *indptr, int64_t P,
-                              const int32_t *newpos, const int32_t *cls, int C,
-                              uint32_t *packed_out, int32_t *queue, prb_stream_t stream)
-{
-    if (P == 0) return 0;
-    PRB_REQUIRE(C >= 1 && C <= 4096, "class count out of range");
-    PRB_CUDA(cudaMemsetAsync(queue, 0, sizeof(int32_t), S(stream)));
-    const int grid = (int)hmin(ceil_div(P, CS_WARPS), (int64_t)devinfo().sm_count * 8);
-    k_class_sort<<<grid, CS_WARPS * 32, (size_t)CS_WARPS * C * 4, S(stream)>>>(
-        packed_in, indptr, P, newpos, cls, C, packed_out, queue);
-    PRB_LAUNCH_CHECK("k_class_sort");
     return 0;
 }

@@ -88,7 +88,8 @@ class Engine:
         self._tps = {}
         self.vmode = USE_VLAYOUT and self.K1 <= 4
         self.v = None  # V layout (csrc/vstream.cu), built lazily for the current labels
-        self.cell_of_pos = None  # int64[N]: original cell id at each position (None = identity)
+        self.newpos = None    # V path: int32[N] new position of every cell (None = identity)
+        self.y_sorted = None  # V path: labels in the new order
         self.classsizes_host = None
         self.gene_ptr = torch.zeros(1, dtype=torch.int32, device=dev)
         self._hits = None
@@ -154,36 +155,28 @@ class Engine:
         return cnt
 
     def set_y(self, y):
-        """y: int32 device tensor [N] of labels in 0..C-1 (original cell order), or None
-        (infoset.py:202-216).  The cells are re-ordered so that classes are contiguous
-        (stable, so every gene's entries stay ascending): entropies do not depend on the
-        order of cells, and csrc/vstream.cu needs class-contiguous cells."""
+        """y: int32 device tensor [N] of labels in 0..C-1, or None (infoset.py:202-216).
+        The packed CSC keeps its cell ids; the V layout (csrc/vstream.cu) is built with the
+        cells RELABELLED so that classes are contiguous (newpos = a stable sort of the
+        labels — entropies do not depend on the order of cells), and the per-cell vectors of
+        that path (x_j, its shift codes, y_sorted) live in the new order."""
         self.epoch += 1
+        self.v = None  # new labels: new segments
         if y is None:
             self.has_y, self.y, self.C, self.classsizes, self.cnt_y = False, None, 1, None, None
-            self.classsizes_host = None
+            self.classsizes_host = self.newpos = self.y_sorted = None
             return
         assert y.dtype == torch.int32 and y.is_cuda and y.numel() == self.N
         C = int(y.max().item()) + 1
         if C > 256:
             raise NotImplementedError("more than 256 classes")
-        y_cur = y if self.cell_of_pos is None else y[self.cell_of_pos]
-        if self.N > 1 and not bool((y_cur[1:] >= y_cur[:-1]).all().item()):
-            order = torch.argsort(y_cur, stable=True)
-            newpos = torch.empty(self.N, dtype=torch.int32, device=self.device)
-            newpos[order] = torch.arange(self.N, dtype=torch.int32, device=self.device)
-            out = torch.empty_like(self.packed)
-            nat.call("prb_class_sort", nat.ptr(self.packed), nat.ptr(self.indptr), self.P,
-                     nat.ptr(newpos), nat.ptr(y_cur.contiguous()), C, nat.ptr(out),
-                     nat.ptr(self.counters), nat.stream())
-            self.packed = out
-            self.cell_of_pos = order if self.cell_of_pos is None else self.cell_of_pos[order]
-            y_cur = y_cur[order]
-            self._tps = {}
-        self.has_y, self.y, self.C = True, y_cur.contiguous(), C
+        self.has_y, self.y, self.C = True, y.contiguous(), C
         self.classsizes = torch.bincount(self.y, minlength=C).to(torch.int64)
         self.classsizes_host = [int(v) for v in self.classsizes.cpu().numpy()]
-        self.v = None  # new labels: new segments
+        if self.vmode:
+            self.y_sorted, order = torch.sort(self.y, stable=True)
+            self.newpos = torch.empty(self.N, dtype=torch.int32, device=self.device)
+            self.newpos[order] = torch.arange(self.N, dtype=torch.int32, device=self.device)
         self.cnt_y = self._count_table(self.y, C)
 
     # ------------------------------------------------ V layout (csrc/vstream.cu), K <= 5
@@ -230,8 +223,9 @@ class Engine:
         plan: (gene, code) virtual genes, runs per segment padded to 32-entry rows."""
         pl = self._v_plan()
         P, K1, n_seg, dev = self.P, self.K1, pl["n_seg"], self.device
-        seg_of_cell = torch.bucketize(torch.arange(self.N, dtype=torch.int32, device=dev),
-                                      pl["seg_cell0"][1:-1].contiguous(), right=True).to(torch.int32)
+        pos = self.newpos if self.has_y else torch.arange(self.N, dtype=torch.int32, device=dev)
+        seg_of_cell = torch.bucketize(pos, pl["seg_cell0"][1:-1].contiguous(),
+                                      right=True).to(torch.int32)  # by ORIGINAL cell id
         PV = max(P * K1, 1)
         seglen = torch.zeros(PV * n_seg, dtype=torch.int32, device=dev)
         nat.call("prb_v_count", nat.ptr(self.packed), nat.ptr(self.indptr), P,
@@ -258,8 +252,9 @@ class Engine:
         seg_pad = torch.from_numpy(pad.astype(np.uint32).view(np.int32)).to(dev)
         vpacked = torch.empty(v_rows * 32 + PACKED_PAD, dtype=torch.int32, device=dev)
         nat.call("prb_v_scatter", nat.ptr(self.packed), nat.ptr(self.indptr), P,
-                 nat.ptr(seg_of_cell), n_seg, K1, nat.ptr(seglen), nat.ptr(run_end),
-                 nat.ptr(seg_pad), nat.ptr(vpacked), nat.ptr(self.counters), nat.stream())
+                 nat.ptr(seg_of_cell), n_seg, K1, nat.ptr(self.newpos) if self.has_y else None,
+                 nat.ptr(seglen), nat.ptr(run_end), nat.ptr(seg_pad), nat.ptr(vpacked),
+                 nat.ptr(self.counters), nat.stream())
         # work items: consecutive row ranges of every super-tile's block, ~16 per warp on
         # average; the first 3/4 of a block in large items, then two rounds of smaller ones,
         # so that the tail of a launch is short
@@ -284,6 +279,7 @@ class Engine:
             item_off.append(item_off[-1] + len(cuts))
         item_vg0 = (torch.cat(vg0) if vg0 else torch.zeros(1, dtype=torch.int32, device=dev))
         self.v = dict(plan=pl, vpacked=vpacked, run_end=run_end, seglen=seglen, rows=v_rows,
+                      relabelled=self.has_y,
                       tile_row0=torch.tensor(tile_row0, dtype=torch.int32, device=dev),
                       item_rows=R, n_items=item_off[-1], item_vg0=item_vg0.contiguous(),
                       item_row0=torch.tensor(row0, dtype=torch.int32, device=dev),
@@ -388,11 +384,14 @@ class Engine:
     def scatter_selected_gene(self):
         """x_j[N] <- dense codes of gene *gene_ptr (owner rank), replicated to all ranks.
         (V path: prb_state_v hands x_j back all-zero, so no memset is needed.)"""
-        if not self.vmode:
+        newpos = None
+        if self.vmode:
+            newpos = self.newpos if self._v()["relabelled"] else None
+        else:
             self.xj.zero_()
         nat.call("prb_scatter_gene_u8", nat.ptr(self.packed), nat.ptr(self.indptr),
-                 nat.ptr(self.gene_ptr), _i32(self.gene_lo), self.P, nat.ptr(self.xj),
-                 nat.stream())
+                 nat.ptr(self.gene_ptr), _i32(self.gene_lo), self.P, nat.ptr(newpos),
+                 nat.ptr(self.xj), nat.stream())
         if self.comm is not None:
             self.comm.allreduce_max_(self.xj)
 
@@ -406,6 +405,8 @@ class Engine:
             raise NotImplementedError("C*(K-1)^2 exceeds 65536 histogram bins")
         self.scatter_selected_gene()
         if self.vmode:
+            if with_y:
+                y = self.y_sorted  # x_j was scattered in the V layout's cell order
             nat.call("prb_state_v", nat.ptr(self.xj), nat.ptr(y), self.N, C, self.K,
                      nat.ptr(self.state_buf), nat.ptr(self.hsize), nat.ptr(self.hs_begin),
                      nat.ptr(self.hs_y), nat.ptr(self.hs_ysum), nat.ptr(self.ha),
@@ -549,7 +550,7 @@ class Engine:
 
     def to_scipy_csc(self, n_genes=None):
         """Host scipy.sparse.csc_matrix (int64 data like the reference's) of the first
-        n_genes local genes (default all), in the ORIGINAL cell order."""
+        n_genes local genes (default all)."""
         import scipy.sparse
 
         G = self.P if n_genes is None else min(int(n_genes), self.P)
@@ -559,11 +560,6 @@ class Engine:
         codes = torch.empty(max(n, 1), dtype=torch.uint8, device=self.device)
         nat.call("prb_unpack_csc", nat.ptr(self.packed), n, nat.ptr(rows), nat.ptr(codes),
                  nat.stream())
-        rows = rows[:n]
-        if self.cell_of_pos is not None:
-            rows = self.cell_of_pos[rows.long()].to(torch.int32)
-        X = scipy.sparse.csc_matrix(
-            (codes[:n].cpu().numpy().astype(np.int64), rows.cpu().numpy(), ip),
+        return scipy.sparse.csc_matrix(
+            (codes[:n].cpu().numpy().astype(np.int64), rows[:n].cpu().numpy(), ip),
             shape=(self.N, G))
-        X.sort_indices()
-        return X

@@ -292,11 +292,10 @@ def test_edge_cases(pr):
 @pytest.mark.parametrize("tile_cells,vlayout", [(None, True), (4096, True), (256, True),
                                                  (None, False)])
 def test_class_sorted_cells_and_v_layout(pr, O, monkeypatch, tile_cells, vlayout):
-    """csrc/vstream.cu (K <= 5): class-sorted cells, class segments split and packed into
-    super-tiles of various sizes, tile-major padded runs, label re-targeting (cells move
-    again, layout rebuilt), export of X in the original cell order — all bit-identical to
-    the oracle; vlayout=False runs the same checks through the generic shared-histogram
-    kernel on the same re-ordered cells."""
+    """csrc/vstream.cu (K <= 5): cells relabelled by class inside the V layout, class segments
+    split and packed into super-tiles of various sizes, tile-major padded runs, label
+    re-targeting (layout rebuilt), export of X — all bit-identical to the oracle;
+    vlayout=False runs the same checks through the generic shared-histogram kernel."""
     import picturedrocks_b200.engine as E
     from picturedrocks_b200.synth import DiscretisedSpec
 
@@ -309,8 +308,8 @@ def test_class_sorted_cells_and_v_layout(pr, O, monkeypatch, tile_cells, vlayout
     inf = pr.markers.SparseInformationSet._from_engine(eng, yd)
     y = spec.cpu_labels()
     Xs = spec.cpu_csc(range(spec.P), y)
-    Xg = eng.to_scipy_csc()  # cells were re-ordered by set_y: export must undo it
-    assert eng.cell_of_pos is not None
+    Xg = eng.to_scipy_csc()  # the exported matrix keeps the original cell ids
+    assert (eng.newpos is not None) == vlayout  # cells are relabelled inside the V layout only
     assert np.array_equal(Xg.indptr, Xs.indptr) and np.array_equal(Xg.indices, Xs.indices)
     assert np.array_equal(Xg.data, Xs.data)
     ora = O.SparseInformationSet(Xs, y)
