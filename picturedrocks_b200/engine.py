@@ -102,9 +102,21 @@ class Engine:
         self.C = 1
         self.classsizes = None
         self.cnt_y = None
-        self.cnt_x = self._count_table(None, 1)
+        self._cnt_x = None  # label-free count table, built on first use
 
     # ------------------------------------------------------------------ tables
+    @property
+    def cnt_x(self):
+        """cnt_x[g][v-1] = #cells with code v in gene g (independent of the labels)."""
+        if self._cnt_x is None:
+            if self.vmode and self.v is not None and self.P:
+                n_seg = self.v["plan"]["n_seg"]  # sum of the run lengths over the segments
+                L = self.v["seglen"][: self.P * self.K1 * n_seg].view(self.P * self.K1, n_seg)
+                self._cnt_x = L.sum(1, dtype=torch.int32).contiguous()
+            else:
+                self._cnt_x = self._count_table(None, 1)
+        return self._cnt_x
+
     def _plan(self, n_states):
         """(tile_cells, n_tiles, teams, state_bytes) of a streaming launch with n_states states."""
         pl = self._plans.get(n_states)
@@ -264,25 +276,29 @@ class Engine:
         item_off, row0, vg0 = [0], [], []
         for t in range(pl["n_st"]):
             lo, hi = tile_row0[t], tile_row0[t + 1]
-            cuts, pos = [], lo
+            parts, pos = [], lo
             for frac, size in ((0.75, R), (0.92, max(256, R // 2)), (1.0, max(128, R // 4))):
                 stop = lo + int((hi - lo) * frac) if frac < 1.0 else hi
-                while pos < stop:
-                    cuts.append(pos)
-                    pos = min(pos + size, hi)
-            if cuts:
-                q = torch.tensor(cuts, dtype=torch.int32, device=dev)
-                vg0.append(torch.searchsorted(run_end[:, st[t + 1] - 1].contiguous(), q,
+                if pos < stop:
+                    parts.append(np.arange(pos, stop, size, dtype=np.int64))
+                    pos = int(parts[-1][-1]) + size
+            cuts = np.concatenate(parts) if parts else np.zeros(0, dtype=np.int64)
+            row0.append(cuts)
+            row0.append(np.array([hi], dtype=np.int64))  # sentinel
+            item_off.append(item_off[-1] + cuts.size)
+        row0 = np.concatenate(row0).astype(np.int32)
+        row0_d = torch.from_numpy(row0).to(dev)
+        for t in range(pl["n_st"]):
+            a, b = item_off[t] + t, item_off[t + 1] + t
+            if b > a:
+                vg0.append(torch.searchsorted(run_end[:, st[t + 1] - 1].contiguous(), row0_d[a:b],
                                               right=True).to(torch.int32))
-            row0.extend(cuts)
-            row0.append(hi)  # sentinel
-            item_off.append(item_off[-1] + len(cuts))
         item_vg0 = (torch.cat(vg0) if vg0 else torch.zeros(1, dtype=torch.int32, device=dev))
         self.v = dict(plan=pl, vpacked=vpacked, run_end=run_end, seglen=seglen, rows=v_rows,
                       relabelled=self.has_y,
                       tile_row0=torch.tensor(tile_row0, dtype=torch.int32, device=dev),
                       item_rows=R, n_items=item_off[-1], item_vg0=item_vg0.contiguous(),
-                      item_row0=torch.tensor(row0, dtype=torch.int32, device=dev),
+                      item_row0=row0_d,
                       item_off=torch.tensor(item_off, dtype=torch.int32, device=dev))
         self.epoch += 1
         return self.v
