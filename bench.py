@@ -308,7 +308,7 @@ def run_ours(args, w):
         e2e = {"value": spec.N * spec.P * args.steps / dt, "unit": UNIT,
                "h2d_bytes_per_step": int(h2d // args.steps), "d2h_bytes_per_step": 4,
                "seconds_total": dt,
-               "what": "pinned host CSC -> H2D -> pack, class sort, V layout -> %s init -> %d steps "
+               "what": "pinned host CSC -> H2D -> pack, V layout -> %s init -> %d steps "
                        "-> S to host"
                        % (args.selector, args.steps),
                "same_sequence_as_resident_run": S_e2e[: args.steps] == S_dev[args.warmup:][: args.steps]
@@ -328,7 +328,7 @@ def run_ours(args, w):
                     "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": k_ms,
                     "launches_timed": len(events), "peak_source": peak_src,
                     "share_of_step": k_ms / (ms / args.steps),
-                    "timed_how": "CUDA events around each k_stream launch in %d further greedy "
+                    "timed_how": "CUDA events around each k_stream_v launch in %d further greedy "
                                  "steps launched eagerly right after the timed region "
                                  "(%.3f ms/step eager vs %.3f ms/step in the CUDA-graph timed "
                                  "region)" % (n_inst, inst_ms, ms / args.steps),

@@ -23,7 +23,7 @@ import torch
 from . import _native as nat
 
 _I16_MAX_BINS = 65536
-# K <= 5: class-sorted cells + the V layout + register counters (csrc/vstream.cu);
+# K <= 5: the V layout (cells relabelled by class) + register counters (csrc/vstream.cu);
 # PRB_NO_VLAYOUT=1 forces the generic shared-histogram kernel (csrc/stream.cu) everywhere
 USE_VLAYOUT = os.environ.get("PRB_NO_VLAYOUT", "0") != "1"
 PACKED_PAD = 4  # words of slack after the last stored entry
@@ -231,7 +231,7 @@ class Engine:
                     seg_class=torch.tensor(cls, **i32) if classes else None)
 
     def _build_v(self):
-        """Re-order the (class-sorted) packed CSC into the V layout for the current segment
+        """Re-order the packed CSC into the V layout (cells relabelled by class) for the current segment
         plan: (gene, code) virtual genes, runs per segment padded to 32-entry rows."""
         pl = self._v_plan()
         P, K1, n_seg, dev = self.P, self.K1, pl["n_seg"], self.device
