@@ -259,6 +259,30 @@ int prb_qd_edges(const void *sorted, int dtype, int64_t N, int64_t P, int k, voi
 int prb_qd_digitize(const void *Xt, int dtype, int64_t N, int64_t P, int k, const void *edges,
                     const int32_t *n_edges, uint8_t *codes, int64_t ld, prb_stream_t stream);
 
+/* Sparse input (scipy CSR/CSC in the reference; INFOSET:66-67 densifies it, so the implicit
+ * zeros take part in the quantiles): by-gene CSC of RAW values on the device, rows ascending
+ * inside a gene.  Per block of genes: prb_sort_segments (ascending sort of every gene's stored
+ * values; offsets int64[n_segs+1] relative to vals_in; < 2^31 values per call) ->
+ * prb_qd_edges_sparse (edges as prb_qd_edges, the column being the sorted stored values plus
+ * N - nnz zeros; indptr points at the block's first gene, sorted_vals at its first value;
+ * zero_code[g] = code of the implicit zeros, 0 for non-negative data — the coded matrix is
+ * sparse only then).  Over all genes: prb_qd_count_sparse -> caller's scan ->
+ * prb_qd_fill_sparse digitise the stored values and emit the packed CSC, dropping the
+ * entries whose code is 0 (the reference's eliminate_zeros, INFOSET:195). */
+int prb_sort_segments_workspace(int dtype, int64_t n_items, int64_t n_segs, int64_t *bytes);
+int prb_sort_segments(const void *vals_in, void *vals_out, int dtype, int64_t n_items,
+                      int64_t n_segs, const int64_t *offsets, void *workspace,
+                      int64_t workspace_bytes, prb_stream_t stream);
+int prb_qd_edges_sparse(const void *sorted_vals, const int64_t *indptr, int dtype, int64_t N,
+                        int64_t P, int k, void *edges, int32_t *n_edges, int32_t *zero_code,
+                        prb_stream_t stream);
+int prb_qd_count_sparse(const int32_t *rows, const void *vals, const int64_t *indptr, int dtype,
+                        int64_t P, int k, const void *edges, const int32_t *n_edges,
+                        int64_t *nnz_per_gene, prb_stream_t stream);
+int prb_qd_fill_sparse(const int32_t *rows, const void *vals, const int64_t *indptr, int dtype,
+                       int64_t P, int k, const void *edges, const int32_t *n_edges,
+                       const int64_t *out_indptr, uint32_t *packed, prb_stream_t stream);
+
 /* ---- synthetic discretised matrices (bench/test utility; counter-based RNG,
  *      reproduced on the CPU by picturedrocks_b200/synth.py) -----------------
  * cum: uint32[4][K-2] cumulative 16-bit thresholds of the code distribution. */

@@ -63,6 +63,11 @@ _SIGS = {
     "prb_sort_columns": [_vp, _vp, _int, _i64, _i64, _vp, _i64, _vp],
     "prb_qd_edges": [_vp, _int, _i64, _i64, _int, _vp, _vp, _vp],
     "prb_qd_digitize": [_vp, _int, _i64, _i64, _int, _vp, _vp, _vp, _i64, _vp],
+    "prb_sort_segments_workspace": [_int, _i64, _i64, ctypes.POINTER(_i64)],
+    "prb_sort_segments": [_vp, _vp, _int, _i64, _i64, _vp, _vp, _i64, _vp],
+    "prb_qd_edges_sparse": [_vp, _vp, _int, _i64, _i64, _int, _vp, _vp, _vp, _vp],
+    "prb_qd_count_sparse": [_vp, _vp, _vp, _int, _i64, _int, _vp, _vp, _vp, _vp],
+    "prb_qd_fill_sparse": [_vp, _vp, _vp, _int, _i64, _int, _vp, _vp, _vp, _vp, _vp],
     "prb_synth_labels": [_vp, _i64, _int, _u64, _vp],
     "prb_synth_count": [_vp, _i64, _i64, _i64, _int, _int, _u32, _u64, _vp, _vp, _vp],
     "prb_synth_fill": [_vp, _i64, _i64, _i64, _int, _int, _u32, _u64, _vp, _vp, _vp, _vp],
@@ -116,7 +121,8 @@ KERNELS = {
     "prb_scatter_gene_or32": 1, "prb_state_direct": 2, "prb_state_table": 2, "prb_state_assign": 1, "prb_finalize": 1, "prb_finalize_direct": 1,
     "prb_entropy_keys": 2, "prb_mi_base": 1, "prb_selector_update": 1, "prb_argmax_blocks": 1,
     "prb_argmax_final": 1, "prb_commit_add": 1, "prb_transpose": 1, "prb_sort_columns": 1,
-    "prb_qd_edges": 1, "prb_qd_digitize": 1, "prb_synth_labels": 1, "prb_synth_count": 1,
+    "prb_qd_edges": 1, "prb_qd_digitize": 1, "prb_sort_segments": 1, "prb_qd_edges_sparse": 1,
+    "prb_qd_count_sparse": 1, "prb_qd_fill_sparse": 1, "prb_synth_labels": 1, "prb_synth_count": 1,
     "prb_synth_fill": 1,
 }
 LAUNCHES = 0

@@ -84,6 +84,97 @@ def discretize_to_device(X, k=5, gene_block=None):
     return codes
 
 
+def _sparse_csc_on_device(X):
+    """scipy sparse (cells x genes, any format) -> by-gene CSC of raw values on the device:
+    (indptr int64[P+1], rows int32[nnz], vals float32 | float64 | int64 [nnz]), rows ascending
+    inside a gene.  CSR input (how AnnData stores counts) is transposed on the GPU."""
+    dev = _device()
+    if not (scipy.sparse.isspmatrix_csr(X) or scipy.sparse.isspmatrix_csc(X)):
+        X = scipy.sparse.csr_matrix(X)
+    if not X.has_canonical_format:
+        X = X.copy()
+        X.sum_duplicates()  # also sorts the indices
+    dt = X.dtype
+    if dt not in (np.float32, np.float64):
+        if not (np.issubdtype(dt, np.integer) or dt == np.bool_):
+            raise TypeError("unsupported dtype %s" % dt)
+        dt = np.dtype(np.int64)
+    N, P = X.shape
+    up = lambda a, t: torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=True).to(t)
+    vals = torch.from_numpy(np.ascontiguousarray(X.data.astype(dt, copy=False))).to(dev)
+    if scipy.sparse.isspmatrix_csc(X):
+        return up(X.indptr, torch.int64), up(X.indices, torch.int32), vals, N, P
+    # CSR -> CSC on the device: a stable sort of the column ids keeps the rows ascending
+    # inside every gene
+    col = up(X.indices, torch.int64)
+    crow = up(X.indptr, torch.int64)
+    order = torch.argsort(col, stable=True)
+    indptr = torch.zeros(P + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(torch.bincount(col, minlength=P), 0, out=indptr[1:])
+    row_of_entry = torch.repeat_interleave(torch.arange(N, dtype=torch.int32, device=dev),
+                                           crow[1:] - crow[:-1])
+    return indptr, row_of_entry[order].contiguous(), vals[order].contiguous(), N, P
+
+
+def discretize_sparse_to_engine(X, k=5, max_block_nnz=1 << 28, **engine_kw):
+    """quantile_discretize of a NON-NEGATIVE scipy sparse matrix without densifying it
+    (infoset.py:50-83 densifies, infoset.py:66-67): per gene the stored values are sorted,
+    the N - nnz implicit zeros are accounted for by rank arithmetic, and only the stored
+    values are digitised.  Returns the Engine holding the packed by-gene CSC of bin codes,
+    or None when the coded matrix would not be sparse (an edge below zero)."""
+    if not (2 <= int(k) <= 256):
+        raise ValueError("k must be in [2, 256]")
+    k = int(k)
+    indptr, rows, vals, N, P = _sparse_csc_on_device(X)
+    if N == 0 or P == 0:
+        return None
+    dev = indptr.device
+    code, _, edt = _DT[np.dtype({torch.float32: np.float32, torch.float64: np.float64,
+                                 torch.int64: np.int64}[vals.dtype])]
+    if vals.numel() and bool((vals < 0).any().item()):
+        return None
+    s = nat.stream()
+    edges = torch.zeros((P, max(k - 1, 1)), dtype=edt, device=dev)
+    n_edges = torch.zeros(P, dtype=torch.int32, device=dev)
+    zero_code = torch.zeros(P, dtype=torch.int32, device=dev)
+    ip = indptr.cpu().numpy()
+    g0 = 0
+    while g0 < P:  # blocks of genes with a bounded number of stored values
+        g1 = int(np.searchsorted(ip, ip[g0] + max_block_nnz, side="right")) - 1
+        g1 = min(P, max(g1, g0 + 1))
+        n = int(ip[g1] - ip[g0])
+        if n >= (1 << 31):
+            raise NotImplementedError("a single gene with 2^31 stored values")
+        off = (indptr[g0: g1 + 1] - indptr[g0]).contiguous()
+        vin = vals[int(ip[g0]): int(ip[g1])]
+        vs = torch.empty_like(vin)
+        if n:
+            ws_bytes = ctypes.c_int64()
+            nat.call("prb_sort_segments_workspace", code, n, g1 - g0, ctypes.byref(ws_bytes))
+            ws = torch.empty(ws_bytes.value, dtype=torch.uint8, device=dev)
+            nat.call("prb_sort_segments", nat.ptr(vin), nat.ptr(vs), code, n, g1 - g0,
+                     nat.ptr(off), nat.ptr(ws), ws_bytes.value, s)
+        nat.call("prb_qd_edges_sparse", nat.ptr(vs), nat.ptr(indptr[g0: g1 + 1].contiguous()),
+                 code, N, g1 - g0, k, nat.ptr(edges[g0:g1]), nat.ptr(n_edges[g0:g1]),
+                 nat.ptr(zero_code[g0:g1]), s)
+        g0 = g1
+    if bool((zero_code != 0).any().item()):
+        return None
+    counts = torch.zeros(P, dtype=torch.int64, device=dev)
+    nat.call("prb_qd_count_sparse", nat.ptr(rows), nat.ptr(vals), nat.ptr(indptr), code, P, k,
+             nat.ptr(edges), nat.ptr(n_edges), nat.ptr(counts), s)
+    out_indptr = torch.zeros(P + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(counts, 0, out=out_indptr[1:])
+    nnz = int(out_indptr[-1].item())
+    from ...engine import PACKED_PAD
+
+    packed = torch.zeros(nnz + PACKED_PAD, dtype=torch.int32, device=dev)
+    nat.call("prb_qd_fill_sparse", nat.ptr(rows), nat.ptr(vals), nat.ptr(indptr), code, P, k,
+             nat.ptr(edges), nat.ptr(n_edges), nat.ptr(out_indptr), nat.ptr(packed), s)
+    K = int(n_edges.max().item()) + 1
+    return Engine(out_indptr, packed, N, K, **engine_kw)
+
+
 def quantile_discretize(X, k=5):
     """Discretize a data matrix with the recursive quantile transform (infoset.py:50-83).
 
@@ -94,9 +185,14 @@ def quantile_discretize(X, k=5):
 
 def makeinfoset(adata, include_y, k=5):
     """Discretize `adata.X` and wrap it in a SparseInformationSet (infoset.py:25-47).
-    The codes never leave the GPU: dense codes -> packed by-gene CSC on device."""
-    codes = discretize_to_device(adata.X, k)
-    infoset = SparseInformationSet._from_device_codes(codes)
+    The codes never leave the GPU: dense codes -> packed by-gene CSC on device; a
+    non-negative scipy sparse `adata.X` (CSR counts, as AnnData stores them) is never
+    densified (same codes as the reference, which densifies: infoset.py:66-67)."""
+    eng = discretize_sparse_to_engine(adata.X, k) if scipy.sparse.issparse(adata.X) else None
+    if eng is not None:
+        infoset = SparseInformationSet._from_engine(eng)
+    else:
+        infoset = SparseInformationSet._from_device_codes(discretize_to_device(adata.X, k))
     if include_y:
         infoset.set_y(adata.obs["y"].values)
     return infoset

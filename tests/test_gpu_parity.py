@@ -405,3 +405,51 @@ def test_full_size_config4_sampled_genes(pr, O):
     fs = pr.markers.CIFE(inf)
     fs.autoselect(3)
     assert fs.S[0] == j and len(set(fs.S)) == 3
+
+
+def test_makeinfoset_sparse_input_is_not_densified(pr, O):
+    """Sparse raw counts (CSR as AnnData stores them, CSC, float32 / float64 / int64, explicit
+    zeros, genes without zeros): the sparse-aware discretiser gives the codes the reference
+    gets by densifying (infoset.py:66-67, oracle on X.toarray()); negative values fall back
+    to the dense path."""
+    import types
+
+    import pandas as pd
+    from picturedrocks_b200.markers.mutualinformation.infoset import discretize_sparse_to_engine
+    from picturedrocks_b200.synth import poisson_gamma
+
+    X, y = poisson_gamma(4000, 300, 7, 13)
+    X[:, :6] += 2.0  # genes without zeros: edge_0 > 0, small stored values get code 0
+    X[:, 6] = 0.0    # all-zero gene
+    X[:, 7] = 5.0    # constant gene
+    for dt in (np.float32, np.float64, np.int64):
+        Xd = X.astype(dt)
+        want = O.quantile_discretize(Xd, 5)
+        for fmt in (scipy.sparse.csr_matrix, scipy.sparse.csc_matrix):
+            eng = discretize_sparse_to_engine(fmt(Xd), 5, max_block_nnz=50000)
+            assert eng is not None
+            assert np.array_equal(np.asarray(eng.to_scipy_csc().todense()), want), (dt, fmt)
+    for k in (2, 3, 8):
+        eng = discretize_sparse_to_engine(scipy.sparse.csr_matrix(X), k)
+        assert np.array_equal(np.asarray(eng.to_scipy_csc().todense()), O.quantile_discretize(X, k))
+    # explicit zeros stored in the sparse matrix behave like implicit ones
+    Xs = scipy.sparse.csr_matrix(X)
+    Xs.data[::7] = 0.0
+    eng = discretize_sparse_to_engine(Xs, 5)
+    assert np.array_equal(np.asarray(eng.to_scipy_csc().todense()),
+                          O.quantile_discretize(Xs.toarray(), 5))
+    # the public entry point: same selection as the oracle on the densified matrix
+    adata = types.SimpleNamespace(X=scipy.sparse.csr_matrix(X), obs=pd.DataFrame({"y": y}))
+    inf = pr.markers.makeinfoset(adata, True)
+    ora = O.makeinfoset(types.SimpleNamespace(X=X, obs=adata.obs), True)
+    a, b = pr.markers.CIFE(inf), O.CIFE(ora)
+    a.autoselect(6)
+    b.autoselect(6)
+    assert a.S == [int(s) for s in b.S] and np.array_equal(a.score, b.score)
+    # negative values: the coded matrix is not sparse -> dense path, still the same codes
+    Xn = X.copy()
+    Xn[::3, 10:20] -= 1.5
+    assert discretize_sparse_to_engine(scipy.sparse.csr_matrix(Xn), 5) is None
+    inf = pr.markers.makeinfoset(types.SimpleNamespace(X=scipy.sparse.csr_matrix(Xn),
+                                                       obs=adata.obs), False)
+    assert np.array_equal(np.asarray(inf.X.todense()), O.quantile_discretize(Xn, 5))
