@@ -453,3 +453,27 @@ def test_makeinfoset_sparse_input_is_not_densified(pr, O):
     inf = pr.markers.makeinfoset(types.SimpleNamespace(X=scipy.sparse.csr_matrix(Xn),
                                                        obs=adata.obs), False)
     assert np.array_equal(np.asarray(inf.X.todense()), O.quantile_discretize(Xn, 5))
+
+
+def test_sparse_discretiser_pbmc_shaped_sample(pr, O):
+    """PBMC-68k-shaped raw sparse counts (68,579 cells, 2 % stored, CSR): makeinfoset never
+    densifies; the codes of a sample of genes equal the oracle's on the densified columns."""
+    import types
+
+    import pandas as pd
+
+    rng = np.random.RandomState(3)
+    N, P, n = 68579, 8192, 11_000_000
+    rows, cols = rng.randint(0, N, n), (rng.beta(0.6, 3.0, n) * P).astype(np.int64)
+    vals = (1 + rng.poisson(1.5, n)).astype(np.float32)
+    X = scipy.sparse.csr_matrix((vals, (rows, cols)), shape=(N, P))
+    y = rng.randint(0, 10, N).astype(np.int64)
+    inf = pr.markers.makeinfoset(types.SimpleNamespace(X=X, obs=pd.DataFrame({"y": y})), True)
+    assert inf.N == N and inf.P == P and inf.has_y
+    got = inf.X
+    sample = [0, 1, 2, 5, 17, 100, 999, 2048, 4095, 6000, 8191]
+    want = O.quantile_discretize(np.asarray(X[:, sample].todense()), 5)
+    assert np.array_equal(np.asarray(got[:, sample].todense()), want)
+    fs = pr.markers.CIFE(inf)
+    fs.autoselect(3)
+    assert len(set(fs.S)) == 3
