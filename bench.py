@@ -31,6 +31,11 @@ WORKLOADS = {
     # BASELINE.json configs[2]: PBMC-68k-shaped sparse
     "c3": dict(N=68579, P=32738, C=10, K=5, mean_density=0.02, seed=3,
                name="PBMC-68k-shaped synthetic sparse 68,579 x 32,738, 10 clusters, 2% nnz"),
+    # BASELINE.json configs[0] / [1]: small dense count matrices through the real discretiser
+    "c1": dict(N=2730, P=3451, C=19, K=5, seed=1, dense=True,
+               name="Paul15-shaped synthetic dense 2,730 x 3,451, 19 clusters, makeinfoset (k=5)"),
+    "c2": dict(N=3005, P=19972, C=9, K=5, seed=2, dense=True,
+               name="Zeisel-shaped synthetic dense 3,005 x 19,972, 9 clusters, makeinfoset (k=5)"),
     # one eighth of the genes of c4: what each rank streams in the 8-GPU run (tuning aid)
     "c4_shard8": dict(N=1306127, P=3500, C=60, K=5, mean_density=0.07, seed=4,
                       name="c4 gene shard: 1,306,127 x 3,500, 60 clusters, 7% nnz"),
@@ -42,8 +47,47 @@ METRIC = "cell_gene_mi_evals_per_s_per_greedy_step"
 UNIT = "cell*gene/s"
 
 
+class DenseWorkload:
+    """Poisson-gamma counts (host) -> GPU quantile discretiser -> packed CSC engine."""
+
+    def __init__(self, w):
+        self.N, self.P, self.C, self.K, self.seed = w["N"], w["P"], w["C"], w["K"], w["seed"]
+
+    def _host(self):
+        from picturedrocks_b200.synth import poisson_gamma
+
+        return poisson_gamma(self.N, self.P, self.C, self.seed)
+
+    def cpu_labels(self):
+        return self._host()[1]
+
+    def cpu_csc(self, genes, y=None):
+        """Reference arm only: codes of the listed genes from the CPU oracle's discretiser."""
+        import scipy.sparse
+
+        from oracle import oracle as O
+
+        X = self._host()[0]
+        return scipy.sparse.csc_matrix(O.quantile_discretize(X[:, list(genes)], self.K))
+
+    def device_engine(self, lo, hi, comm=None):
+        import torch
+
+        from picturedrocks_b200.engine import Engine
+        from picturedrocks_b200.markers.mutualinformation.infoset import discretize_to_device
+        from picturedrocks_b200.synth import poisson_gamma
+
+        X, y = poisson_gamma(self.N, self.P, self.C, self.seed)
+        codes = discretize_to_device(X[:, lo:hi], self.K)
+        eng = Engine.from_dense_codes(codes, self.N, gene_lo=lo, P_total=self.P, comm=comm)
+        return eng, torch.from_numpy(y.astype(np.int32)).cuda()
+
+
 def make_spec(w):
     from picturedrocks_b200.synth import DiscretisedSpec
+
+    if w.get("dense"):
+        return DenseWorkload(w)
 
     return DiscretisedSpec(N=w["N"], P=w["P"], C=w["C"], K=w["K"], mean_density=w["mean_density"],
                            seed=w["seed"])

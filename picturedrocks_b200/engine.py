@@ -271,13 +271,16 @@ class Engine:
         # average; the first 3/4 of a block in large items, then two rounds of smaller ones,
         # so that the tail of a launch is short
         warps = nat.load().prb_v_warps()
-        R = int(os.environ.get("PRB_V_ITEM_ROWS", 0)) or max(256, -(-v_rows // (12 * warps)))
+        # (at least 256 rows each, unless that would leave warps without any item)
+        r_min = max(32, min(256, v_rows // max(warps, 1)))
+        R = int(os.environ.get("PRB_V_ITEM_ROWS", 0)) or max(r_min, -(-v_rows // (12 * warps)))
         R = (R + 31) & ~31
         item_off, row0, vg0 = [0], [], []
         for t in range(pl["n_st"]):
             lo, hi = tile_row0[t], tile_row0[t + 1]
             parts, pos = [], lo
-            for frac, size in ((0.75, R), (0.92, max(256, R // 2)), (1.0, max(128, R // 4))):
+            for frac, size in ((0.75, R), (0.92, max(min(R, 256), R // 2)),
+                               (1.0, max(min(R, 128), R // 4))):
                 stop = lo + int((hi - lo) * frac) if frac < 1.0 else hi
                 if pos < stop:
                     parts.append(np.arange(pos, stop, size, dtype=np.int64))
