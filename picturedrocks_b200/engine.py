@@ -231,8 +231,9 @@ class Engine:
                     seg_class=torch.tensor(cls, **i32) if classes else None)
 
     def _build_v(self):
-        """Re-order the packed CSC into the V layout (cells relabelled by class) for the current segment
-        plan: (gene, code) virtual genes, runs per segment padded to 32-entry rows."""
+        """Re-order the packed CSC into the V layout for the current segment plan: cells
+        relabelled by class, (gene, code) virtual genes, runs per segment padded to 32-entry
+        rows, stored tile-major; plus the work-item tables of csrc/vstream.cu."""
         pl = self._v_plan()
         P, K1, n_seg, dev = self.P, self.K1, pl["n_seg"], self.device
         pos = self.newpos if self.has_y else torch.arange(self.N, dtype=torch.int32, device=dev)
