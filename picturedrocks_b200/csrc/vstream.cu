@@ -37,7 +37,8 @@ struct VCfg {
     static constexpr int threads = WARPS * 32;
     static constexpr int stage_bytes = STAGE_ROWS * 128;
     static constexpr int ring_bytes = WARPS * STAGES * stage_bytes;
-    static constexpr int smem_bytes = SPAN + ring_bytes + WARPS * STAGES * 8;
+    static constexpr int ctl_bytes = 256;  // s_flag + per-segment class offsets
+    static constexpr int smem_bytes = SPAN + ring_bytes + WARPS * STAGES * 8 + ctl_bytes;
 };
 
 __device__ __forceinline__ uint32_t v_smem_u32(const void *p)
@@ -70,6 +71,20 @@ __device__ __forceinline__ void v_mbar_wait(uint32_t bar, uint32_t parity)
         "DONE_%=:\n"
         "}\n" ::"r"(bar), "r"(parity)
         : "memory");
+}
+
+// Shared-window address of the first byte of dynamic shared memory in a kernel without
+// static shared memory (sm_100: 1 KB of the window is reserved by the system).  The kernel
+// traps if the assumption does not hold.
+constexpr int V_SMEM_BASE = 1024;
+
+// shift code of the cell whose index (< SPAN) is idx: the tile is the first SPAN bytes of
+// dynamic shared memory, so the address is idx + an immediate (no add instruction)
+__device__ __forceinline__ uint32_t v_probe(uint32_t idx)
+{
+    uint32_t r;
+    asm volatile("ld.shared.u8 %0, [%1 + %2];" : "=r"(r) : "r"(idx), "n"(V_SMEM_BASE));
+    return r;
 }
 
 // PTX shl clamps: a shift amount >= 32 gives 0 (the shift code of a cell with x_j = 0).
@@ -124,10 +139,15 @@ k_stream_v(const uint32_t *__restrict__ vpacked, const int32_t *__restrict__ run
 {
     constexpr int SPAN = CFG::span, SR = CFG::stage_rows, STAGES = CFG::stages;
     constexpr int STAGE_BYTES = CFG::stage_bytes, THREADS = CFG::threads;
+    // The kernel has NO static shared memory, so the dynamic region starts at a fixed offset of
+    // the CTA's shared window and the tile (its first SPAN bytes) is addressed by the bare
+    // cell index: a probe is LDS.U16 (index from the ring) -> LDS.U8 [index + imm].
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ int s_flag;
-    __shared__ int s_cls[V_MAX_SEGS + 1];
+    int *s_ctl = (int *)(smem_raw + SPAN + CFG::ring_bytes + CFG::warps * STAGES * 8);
+    int &s_flag = s_ctl[0];
+    int *s_cls = s_ctl + 1;  // [V_MAX_SEGS + 1]
     uint8_t *st = (uint8_t *)smem_raw;
+    if (v_smem_u32(smem_raw) != V_SMEM_BASE) __trap();  // layout assumption of v_probe()
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t *ring = (const uint32_t *)(smem_raw + SPAN + warp * (STAGES * STAGE_BYTES)) + lane;
     const uint32_t ring_s = v_smem_u32(smem_raw + SPAN + warp * (STAGES * STAGE_BYTES));
@@ -261,12 +281,12 @@ k_stream_v(const uint32_t *__restrict__ vpacked, const int32_t *__restrict__ run
 #pragma unroll 1
                         for (; rp + 96 < rp_end; rp += 128) {
                             const uint32_t w0 = rp[0], w1 = rp[32], w2 = rp[64], w3 = rp[96];
-                            const uint32_t x0 = st[w0 & (SPAN - 1)], x1 = st[w1 & (SPAN - 1)];
-                            const uint32_t x2 = st[w2 & (SPAN - 1)], x3 = st[w3 & (SPAN - 1)];
+                            const uint32_t x0 = v_probe(w0 & (SPAN - 1)), x1 = v_probe(w1 & (SPAN - 1));
+                            const uint32_t x2 = v_probe(w2 & (SPAN - 1)), x3 = v_probe(w3 & (SPAN - 1));
                             acc += v_shl1(x0) + v_shl1(x1) + v_shl1(x2) + v_shl1(x3);
                         }
 #pragma unroll 1
-                        for (; rp < rp_end; rp += 32) acc += v_shl1(st[rp[0] & (SPAN - 1)]);
+                        for (; rp < rp_end; rp += 32) acc += v_shl1(v_probe(rp[0] & (SPAN - 1)));
                         r = stop;
                         if (r == e) break;
                         if (r == fb) {  // the 8-bit fields are full
