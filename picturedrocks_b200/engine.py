@@ -21,6 +21,7 @@ import numpy as np
 import torch
 
 from . import _native as nat
+from . import vplan
 
 _I16_MAX_BINS = 65536
 # K <= 5: the V layout (cells relabelled by class) + register counters (csrc/vstream.cu);
@@ -200,27 +201,9 @@ class Engine:
         nat.call("prb_v_tile_capacity", ctypes.byref(cap), ctypes.byref(max_segs))
         cap = max(128, min(int(os.environ.get("PRB_V_TILE_CELLS", cap.value)), cap.value))
         sizes = self.classsizes_host if classes else [self.N]
-        cell0, cls, pos = [], [], 0
-        for c, n in enumerate(sizes):
-            pieces = -(-n // cap)
-            for k in range(pieces):
-                cell0.append(pos + n * k // pieces)
-                cls.append(c)
-            pos += n
-        assert pos == self.N
-        cell0.append(self.N)
+        cell0, cls, st = vplan.segment_plan(sizes, cap, max_segs.value)
+        assert cell0[-1] == self.N
         n_seg = len(cls)
-        n_st_min = -(-self.N // cap)
-        target = -(-self.N // n_st_min)
-        st, cur_cells, cur_n = [0], 0, 0
-        for i in range(n_seg):
-            sz = cell0[i + 1] - cell0[i]
-            if cur_n and (cur_cells + sz > cap or cur_n == max_segs.value or cur_cells >= target):
-                st.append(i)
-                cur_cells, cur_n = 0, 0
-            cur_cells += sz
-            cur_n += 1
-        st.append(n_seg)
         n_st = len(st) - 1
         if n_st > self.counters.numel():
             raise NotImplementedError("too many cell tiles")
@@ -272,21 +255,11 @@ class Engine:
         # average; the first 3/4 of a block in large items, then two rounds of smaller ones,
         # so that the tail of a launch is short
         warps = nat.load().prb_v_warps()
-        # (at least 256 rows each, unless that would leave warps without any item)
-        r_min = max(32, min(256, v_rows // max(warps, 1)))
-        R = int(os.environ.get("PRB_V_ITEM_ROWS", 0)) or max(r_min, -(-v_rows // (12 * warps)))
-        R = (R + 31) & ~31
+        R = vplan.item_rows(v_rows, warps, int(os.environ.get("PRB_V_ITEM_ROWS", 0)))
         item_off, row0, vg0 = [0], [], []
         for t in range(pl["n_st"]):
-            lo, hi = tile_row0[t], tile_row0[t + 1]
-            parts, pos = [], lo
-            for frac, size in ((0.75, R), (0.92, max(min(R, 256), R // 2)),
-                               (1.0, max(min(R, 128), R // 4))):
-                stop = lo + int((hi - lo) * frac) if frac < 1.0 else hi
-                if pos < stop:
-                    parts.append(np.arange(pos, stop, size, dtype=np.int64))
-                    pos = int(parts[-1][-1]) + size
-            cuts = np.concatenate(parts) if parts else np.zeros(0, dtype=np.int64)
+            cuts = vplan.item_cuts(tile_row0[t], tile_row0[t + 1], R)
+            hi = tile_row0[t + 1]
             row0.append(cuts)
             row0.append(np.array([hi], dtype=np.int64))  # sentinel
             item_off.append(item_off[-1] + cuts.size)
