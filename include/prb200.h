@@ -309,6 +309,14 @@ int prb_sparse_entropy_wrt_host(const int32_t *dindices, const int64_t *dindptr,
                                 const int64_t *y, const double *classsizes, int64_t n_classes,
                                 double *out);
 
+/* Same for the scalar kernel
+ *   _sparse_entropy(indices, data, n_rows, max_val)          (INFOSET:413-428)
+ * The reference uses `indices` only for its length: pass nnz = len(indices) and the packed
+ * values `data` (HOST pointer, int64, each in [0, max_val]); *out (host) receives the
+ * entropy.  Bit-identical to the reference (same bins, same ascending order). */
+int prb_sparse_entropy_host(const int64_t *data, int64_t nnz, int64_t n_rows, int64_t max_val,
+                            double *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -73,6 +73,7 @@ _SIGS = {
     "prb_synth_fill": [_vp, _i64, _i64, _i64, _int, _int, _u32, _u64, _vp, _vp, _vp, _vp],
     "prb_sparse_entropy_wrt_host": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64,
                                     _vp, _vp, _i64, _vp],
+    "prb_sparse_entropy_host": [_vp, _i64, _i64, _i64, _vp],
 }
 _RESTYPES = {"prb_last_error": ctypes.c_char_p}
 

@@ -9,6 +9,8 @@
 // where ids are ORDER-PRESERVING w.r.t. the reference's packed id
 // (y most significant, then cols[0], ..., cols[m-1]) so that entropies can be
 // accumulated in the reference's ascending-bin order.
+#include <vector>
+
 #include "common.cuh"
 
 namespace prb {
@@ -400,5 +402,73 @@ extern "C" int prb_entropy_keys(const uint32_t *mpacked, const int32_t *y, int64
     if (table_count(mpacked, y, N, mbits, n_keys, table, 1, S(stream))) return 1;
     k_table_entropy<<<1, 32, 0, S(stream)>>>(table, n_keys, term_table, out);
     PRB_LAUNCH_CHECK("k_table_entropy");
+    return 0;
+}
+
+// ---- HOST-buffer drop-in for _sparse_entropy (infoset.py:413-428) -----------------------
+namespace prb {
+__global__ void k_count_values(const int64_t *__restrict__ data, int64_t nnz, int64_t max_val,
+                               int32_t *__restrict__ table, int *bad)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nnz; i += stride) {
+        const int64_t v = data[i];
+        if (v < 0 || v > max_val)
+            *bad = 1;
+        else
+            atomicAdd(table + v, 1);
+    }
+}
+__global__ void k_add_zero_bin(int32_t *table, int32_t add) { table[0] += add; }
+}  // namespace prb
+
+extern "C" int prb_sparse_entropy_host(const int64_t *data, int64_t nnz, int64_t n_rows,
+                                       int64_t max_val, double *out)
+{
+    // counts[0] = n_rows; every stored entry moves one count from bin 0 to bin data[i];
+    // h = sum over the bins in ascending order of -(c/n_rows) * log2(c/n_rows)
+    PRB_REQUIRE(n_rows > 0 && nnz >= 0 && nnz <= n_rows, "bad sizes");
+    PRB_REQUIRE(max_val >= 0 && max_val < (int64_t(1) << 24), "value space too large");
+    PRB_REQUIRE(out != nullptr && (nnz == 0 || data != nullptr), "null pointer");
+    const int64_t n_keys = max_val + 1;
+    int64_t *d_data = nullptr;
+    int32_t *d_table = nullptr;
+    double *d_term = nullptr, *d_out = nullptr;
+    int *d_bad = nullptr;
+    std::vector<double> h_term((size_t)n_rows + 1);
+    if (prb_term_table(n_rows, h_term.data())) return 1;
+    auto cleanup = [&]() {
+        cudaFree(d_data);
+        cudaFree(d_table);
+        cudaFree(d_term);
+        cudaFree(d_out);
+        cudaFree(d_bad);
+    };
+    cudaError_t e = cudaSuccess;
+    auto ok = [&](cudaError_t r) {
+        if (e == cudaSuccess) e = r;
+        return r == cudaSuccess;
+    };
+    int bad = 0;
+    if (ok(cudaMalloc(&d_data, sizeof(int64_t) * (size_t)(nnz ? nnz : 1))) &&
+        ok(cudaMalloc(&d_table, sizeof(int32_t) * (size_t)n_keys)) &&
+        ok(cudaMalloc(&d_term, sizeof(double) * (size_t)(n_rows + 1))) &&
+        ok(cudaMalloc(&d_out, sizeof(double))) && ok(cudaMalloc(&d_bad, sizeof(int))) &&
+        ok(cudaMemcpy(d_data, data, sizeof(int64_t) * (size_t)nnz, cudaMemcpyHostToDevice)) &&
+        ok(cudaMemcpy(d_term, h_term.data(), sizeof(double) * (size_t)(n_rows + 1),
+                      cudaMemcpyHostToDevice)) &&
+        ok(cudaMemset(d_table, 0, sizeof(int32_t) * (size_t)n_keys)) &&
+        ok(cudaMemset(d_bad, 0, sizeof(int)))) {
+        if (nnz)
+            k_count_values<<<cell_grid(nnz, 256), 256>>>(d_data, nnz, max_val, d_table, d_bad);
+        k_add_zero_bin<<<1, 1>>>(d_table, (int32_t)(n_rows - nnz));
+        k_table_entropy<<<1, 32>>>(d_table, n_keys, d_term, d_out);
+        ok(cudaGetLastError());
+        ok(cudaMemcpy(out, d_out, sizeof(double), cudaMemcpyDeviceToHost));
+        ok(cudaMemcpy(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost));
+    }
+    cleanup();
+    if (e != cudaSuccess) return fail(__func__, cudaGetErrorString(e));
+    if (bad) return fail(__func__, "a value lies outside [0, max_val]");
     return 0;
 }

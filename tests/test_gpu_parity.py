@@ -239,6 +239,32 @@ def test_c_abi_host_entry_matches_oracle(O):
         assert np.array_equal(out, inf.entropy_wrt(np.array(cols, dtype=np.int64))), cols
 
 
+def test_c_abi_host_scalar_entropy_matches_oracle(O):
+    """prb_sparse_entropy_host: the host-buffer drop-in for _sparse_entropy (INFOSET:413-428),
+    driven the way SparseInformationSet.entropy drives the reference kernel."""
+    from picturedrocks_b200 import _native as nat
+    from picturedrocks_b200.synth import DiscretisedSpec
+
+    spec = DiscretisedSpec(N=7000, P=40, C=6, K=5, mean_density=0.2, seed=2)
+    y = spec.cpu_labels()
+    inf = O.SparseInformationSet(spec.cpu_csc(range(spec.P), y), y)
+    for cols in ([3], [3, 9], [0, 5, 11]):
+        mi, md = O.make_master_col(inf.X, cols, inf._shift)
+        max_val = 2 ** (inf._shift * len(cols))
+        out = np.empty(1)
+        md = np.ascontiguousarray(md, dtype=np.int64)
+        nat.call("prb_sparse_entropy_host", md.ctypes.data, md.size, spec.N, max_val,
+                 out.ctypes.data)
+        assert out[0] == O.sparse_entropy(mi, md, spec.N, max_val)
+        assert out[0] == inf.entropy(np.array(cols, dtype=np.int64))
+    out = np.empty(1)
+    nat.call("prb_sparse_entropy_host", None, 0, 10, 7, out.ctypes.data)
+    assert out[0] == 0.0  # a constant column
+    with pytest.raises(nat.PrbError):
+        bad = np.array([9], dtype=np.int64)
+        nat.call("prb_sparse_entropy_host", bad.ctypes.data, 1, 10, 7, out.ctypes.data)
+
+
 def test_medium_sparse_against_oracle(pr, O):
     """60 classes, skewed densities: GPU vs live oracle, entropies and sequences."""
     from picturedrocks_b200.synth import DiscretisedSpec
