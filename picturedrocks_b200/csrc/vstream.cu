@@ -317,8 +317,24 @@ k_stream_v(const uint32_t *__restrict__ vpacked, const int32_t *__restrict__ run
 }
 
 // ---- building the V layout -------------------------------------------------------------
-// pass 1: per gene, entries per (code, segment) -> seglen[P*K1][n_seg].  One warp per gene
-// (dynamic queue), shared-memory histogram per warp.
+// segment of a (relabelled) cell position: number of boundaries <= pos, minus one
+// (bnd[0] = 0 < bnd[1] < ... < bnd[n_seg] = N, staged in shared memory)
+__device__ __forceinline__ int seg_of_pos(const int *bnd, int n_seg, int pos)
+{
+    int lo = 0, hi = n_seg;  // answer in [lo, hi)
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (bnd[mid] <= pos)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+// pass 1: per gene, entries per (code, segment) -> seglen[P*K1][n_seg]; seg_of_cell[cell] =
+// segment of the ORIGINAL cell id (NULL: one segment).  One warp per gene (dynamic queue),
+// shared-memory histogram per warp.
 constexpr int VB_WARPS = 8;
 
 __global__ void __launch_bounds__(VB_WARPS * 32)
@@ -340,7 +356,8 @@ k_vcount(const uint32_t *__restrict__ packed, const int64_t *__restrict__ indptr
         __syncwarp();
         for (int64_t i = b + lane; i < e; i += 32) {
             const uint32_t w = packed[i];
-            atomicAdd(cnt + ((w >> 24) - 1u) * n_seg + seg_of_cell[w & ROW_MASK], 1);
+            const int seg = seg_of_cell ? seg_of_cell[w & ROW_MASK] : 0;
+            atomicAdd(cnt + ((w >> 24) - 1u) * n_seg + seg, 1);
         }
         __syncwarp();
         for (int i = lane; i < nk; i += 32) seglen[g * nk + i] = cnt[i];
@@ -348,59 +365,96 @@ k_vcount(const uint32_t *__restrict__ packed, const int64_t *__restrict__ indptr
     }
 }
 
-// pass 2: ordered scatter into the padded runs (rank inside a 32-entry group by
-// __match_any_sync keeps the ascending cell order inside a run; cells are relabelled on the
-// way: word = code | newpos[cell], seg_of_cell is indexed by the ORIGINAL cell id, and
-// newpos is increasing inside a class); run (vg, s) occupies rows
-// [run_end - ceil(len/32), run_end); the padding words of segment s are
+// pass 2: ordered scatter of the relabelled entries (word = code | newpos[cell]) into the
+// padded runs.  One block per gene (dynamic queue); the gene is processed in chunks of 1024
+// entries that are multi-split by (code, segment) in shared memory — per-warp counts of every
+// key, rank inside a 32-entry group by __match_any_sync, an exclusive scan over the warps —
+// so that the ascending cell order inside a run is kept (newpos is increasing inside a class)
+// and the entries of a key leave the chunk as one contiguous write.  Run (vg, s) occupies
+// rows [run_end - ceil(len/32), run_end); the padding words of segment s are
 // seg_pad[s] = 0xFF000000 | (a cell slot the kernel keeps at "x_j = 0").
-__global__ void __launch_bounds__(VB_WARPS * 32)
+constexpr int VS_WARPS = 8, VS_U = 4, VS_CHUNK = VS_WARPS * 32 * VS_U;
+
+__global__ void __launch_bounds__(VS_WARPS * 32)
 k_vscatter(const uint32_t *__restrict__ packed, const int64_t *__restrict__ indptr, int64_t P,
-           const int32_t *__restrict__ seg_of_cell, int n_seg, int K1,
-           const int32_t *__restrict__ newpos, const int32_t *__restrict__ seglen,
-           const int32_t *__restrict__ run_end, const uint32_t *__restrict__ seg_pad,
-           uint32_t *__restrict__ vpacked, int *queue)
+           const int32_t *__restrict__ newpos, const int32_t *__restrict__ seg_cell0, int n_seg,
+           int K1, const int32_t *__restrict__ seglen, const int32_t *__restrict__ run_end,
+           const uint32_t *__restrict__ seg_pad, uint32_t *__restrict__ vpacked, int *queue)
 {
-    extern __shared__ int64_t vb_smem64[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    extern __shared__ __align__(8) unsigned char vs_raw[];
+    __shared__ int s_gene;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nk = K1 * n_seg;
-    int64_t *off = vb_smem64 + warp * nk;  // next free slot of every run
+    int64_t *off = (int64_t *)vs_raw;                  // [nk] next free slot of every run
+    int64_t *wbase = off + nk;                         // [VS_WARPS][nk] counts, then bases
+    int *bnd = (int *)(wbase + (int64_t)VS_WARPS * nk);  // [n_seg + 1]
+    for (int i = tid; i <= n_seg; i += blockDim.x) bnd[i] = seg_cell0[i];
     for (;;) {
-        int gi = 0;
-        if (lane == 0) gi = atomicAdd(queue, 1);
-        const int64_t g = __shfl_sync(0xffffffffu, gi, 0);
+        __syncthreads();
+        if (tid == 0) s_gene = atomicAdd(queue, 1);
+        __syncthreads();
+        const int64_t g = s_gene;
         if (g >= P) break;
         const int64_t b = indptr[g], e = indptr[g + 1];
-        for (int i = lane; i < nk; i += 32) {
+        for (int i = tid; i < nk; i += blockDim.x) {
             const int nr = (seglen[g * nk + i] + 31) >> 5;
             off[i] = (int64_t)(run_end[g * nk + i] - nr) * 32;
         }
-        __syncwarp();
-        for (int64_t i0 = b; i0 < e; i0 += 32) {
-            const int64_t i = i0 + lane;
-            const bool valid = i < e;
-            const unsigned act = __ballot_sync(0xffffffffu, valid);
-            if (valid) {
-                const uint32_t w = packed[i];
-                const int key = (int)((w >> 24) - 1u) * n_seg + seg_of_cell[w & ROW_MASK];
-                const unsigned m = __match_any_sync(act, key);
-                const int rank = __popc(m & ((1u << lane) - 1u));
-                const int64_t base = off[key];
-                vpacked[base + rank] =
-                    newpos ? (w & ~ROW_MASK) | (uint32_t)newpos[w & ROW_MASK] : w;
-                __syncwarp(act);
-                if (rank == 0) off[key] = base + __popc(m);
+        for (int64_t c0 = b; c0 < e; c0 += VS_CHUNK) {
+            for (int i = tid; i < VS_WARPS * nk; i += blockDim.x) wbase[i] = 0;
+            __syncthreads();
+            // per-warp counts and the rank of every entry inside its warp's part of the chunk
+            int64_t *wc = wbase + (int64_t)warp * nk;
+            uint32_t word[VS_U];
+            int key[VS_U], rk[VS_U];
+#pragma unroll
+            for (int u = 0; u < VS_U; ++u) {
+                const int64_t i = c0 + (warp * VS_U + u) * 32 + lane;
+                const bool valid = i < e;
+                const unsigned act = __ballot_sync(0xffffffffu, valid);
+                key[u] = -1;
+                if (valid) {
+                    const uint32_t w = packed[i];
+                    const int cell = (int)(w & ROW_MASK);
+                    const int pos = newpos ? newpos[cell] : cell;
+                    const int seg = n_seg > 1 ? seg_of_pos(bnd, n_seg, pos) : 0;
+                    key[u] = (int)((w >> 24) - 1u) * n_seg + seg;
+                    word[u] = (w & ~ROW_MASK) | (uint32_t)pos;
+                    const unsigned m = __match_any_sync(act, key[u]);
+                    const int r = __popc(m & ((1u << lane) - 1u));
+                    const int base = (int)wc[key[u]];
+                    rk[u] = base + r;
+                    __syncwarp(act);
+                    if (r == 0) wc[key[u]] = base + __popc(m);
+                }
+                __syncwarp();
             }
-            __syncwarp();
+            __syncthreads();
+            // exclusive scan over the warps: wbase[w][k] = first slot of warp w's entries
+            for (int k = tid; k < nk; k += blockDim.x) {
+                int64_t run = off[k];
+#pragma unroll
+                for (int w = 0; w < VS_WARPS; ++w) {
+                    const int64_t c = wbase[(int64_t)w * nk + k];
+                    wbase[(int64_t)w * nk + k] = run;
+                    run += c;
+                }
+                off[k] = run;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < VS_U; ++u)
+                if (key[u] >= 0) vpacked[wc[key[u]] + rk[u]] = word[u];
+            __syncthreads();
         }
+        __syncthreads();
         // padding up to the end of the run's last row
-        for (int i = lane; i < nk; i += 32) {
+        for (int i = tid; i < nk; i += blockDim.x) {
             const int s = i % n_seg;
             const int64_t end = (int64_t)run_end[g * nk + i] * 32;
             const uint32_t padw = seg_pad[s];
             for (int64_t p = off[i]; p < end; ++p) vpacked[p] = padw;
         }
-        __syncwarp();
     }
 }
 
@@ -464,6 +518,7 @@ extern "C" int prb_v_count(const uint32_t *packed, const int64_t *indptr, int64_
 {
     if (P == 0) return 0;
     PRB_REQUIRE(K1 >= 1 && K1 <= 4 && n_seg >= 1, "bad arguments");
+    PRB_REQUIRE(seg_of_cell != nullptr || n_seg == 1, "seg_of_cell is required");
     const size_t smem = (size_t)VB_WARPS * K1 * n_seg * 4;
     PRB_REQUIRE((int64_t)smem <= devinfo().smem_optin - 1024, "too many segments");
     PRB_CUDA(cudaFuncSetAttribute(k_vcount, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -476,22 +531,23 @@ extern "C" int prb_v_count(const uint32_t *packed, const int64_t *indptr, int64_
 }
 
 extern "C" int prb_v_scatter(const uint32_t *packed, const int64_t *indptr, int64_t P,
-                             const int32_t *seg_of_cell, int n_seg, int K1, const int32_t *newpos,
+                             const int32_t *newpos, const int32_t *seg_cell0, int n_seg, int K1,
                              const int32_t *seglen, const int32_t *run_end,
                              const uint32_t *seg_pad, uint32_t *vpacked, int32_t *queue,
                              prb_stream_t stream)
 {
     if (P == 0) return 0;
-    PRB_REQUIRE(K1 >= 1 && K1 <= 4 && n_seg >= 1, "bad arguments");
-    const size_t smem = (size_t)VB_WARPS * K1 * n_seg * 8;
+    PRB_REQUIRE(K1 >= 1 && K1 <= 4 && n_seg >= 1 && seg_cell0, "bad arguments");
+    const size_t nk = (size_t)K1 * n_seg;
+    const size_t smem = (nk + (size_t)VS_WARPS * nk) * 8 + ((size_t)n_seg + 1) * 4;
     PRB_REQUIRE((int64_t)smem <= devinfo().smem_optin - 1024, "too many segments");
     PRB_CUDA(cudaFuncSetAttribute(k_vscatter, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
     PRB_CUDA(cudaMemsetAsync(queue, 0, sizeof(int32_t), S(stream)));
-    const int grid = (int)hmin(ceil_div(P, VB_WARPS), (int64_t)devinfo().sm_count * 8);
-    k_vscatter<<<grid, VB_WARPS * 32, smem, S(stream)>>>(packed, indptr, P, seg_of_cell, n_seg, K1,
-                                                         newpos, seglen, run_end, seg_pad, vpacked,
-                                                         queue);
+    const int grid = (int)hmin(P, (int64_t)devinfo().sm_count * 8);
+    k_vscatter<<<grid, VS_WARPS * 32, smem, S(stream)>>>(packed, indptr, P, newpos, seg_cell0,
+                                                         n_seg, K1, seglen, run_end, seg_pad,
+                                                         vpacked, queue);
     PRB_LAUNCH_CHECK("k_vscatter");
     return 0;
 }

@@ -219,11 +219,15 @@ class Engine:
         rows, stored tile-major; plus the work-item tables of csrc/vstream.cu."""
         pl = self._v_plan()
         P, K1, n_seg, dev = self.P, self.K1, pl["n_seg"], self.device
-        pos = self.newpos if self.has_y else torch.arange(self.N, dtype=torch.int32, device=dev)
-        seg_of_cell = torch.bucketize(pos, pl["seg_cell0"][1:-1].contiguous(),
-                                      right=True).to(torch.int32)  # by ORIGINAL cell id
+        newpos = self.newpos if self.has_y else None
         PV = max(P * K1, 1)
         seglen = torch.zeros(PV * n_seg, dtype=torch.int32, device=dev)
+        seg_of_cell = None  # segment of every ORIGINAL cell id
+        if n_seg > 1:
+            pos = newpos if newpos is not None else torch.arange(self.N, dtype=torch.int32,
+                                                                 device=dev)
+            seg_of_cell = torch.bucketize(pos, pl["seg_cell0"][1:-1].contiguous(),
+                                          right=True).to(torch.int32)
         nat.call("prb_v_count", nat.ptr(self.packed), nat.ptr(self.indptr), P,
                  nat.ptr(seg_of_cell), n_seg, K1, nat.ptr(seglen), nat.ptr(self.counters),
                  nat.stream())
@@ -247,10 +251,9 @@ class Engine:
         v_rows = base
         seg_pad = torch.from_numpy(pad.astype(np.uint32).view(np.int32)).to(dev)
         vpacked = torch.empty(v_rows * 32 + PACKED_PAD, dtype=torch.int32, device=dev)
-        nat.call("prb_v_scatter", nat.ptr(self.packed), nat.ptr(self.indptr), P,
-                 nat.ptr(seg_of_cell), n_seg, K1, nat.ptr(self.newpos) if self.has_y else None,
-                 nat.ptr(seglen), nat.ptr(run_end), nat.ptr(seg_pad), nat.ptr(vpacked),
-                 nat.ptr(self.counters), nat.stream())
+        nat.call("prb_v_scatter", nat.ptr(self.packed), nat.ptr(self.indptr), P, nat.ptr(newpos),
+                 nat.ptr(pl["seg_cell0"]), n_seg, K1, nat.ptr(seglen), nat.ptr(run_end),
+                 nat.ptr(seg_pad), nat.ptr(vpacked), nat.ptr(self.counters), nat.stream())
         # work items: consecutive row ranges of every super-tile's block, ~16 per warp on
         # average; the first 3/4 of a block in large items, then two rounds of smaller ones,
         # so that the tail of a launch is short
@@ -290,9 +293,8 @@ class Engine:
         dev, P, K1 = self.device, self.P, self.K1
         if not with_classes:
             seglen = torch.zeros(max(P * K1, 1), dtype=torch.int32, device=dev)
-            seg0 = torch.zeros(self.N, dtype=torch.int32, device=dev)
-            nat.call("prb_v_count", nat.ptr(self.packed), nat.ptr(self.indptr), P, nat.ptr(seg0),
-                     1, K1, nat.ptr(seglen), nat.ptr(self.counters), nat.stream())
+            nat.call("prb_v_count", nat.ptr(self.packed), nat.ptr(self.indptr), P, None, 1, K1,
+                     nat.ptr(seglen), nat.ptr(self.counters), nat.stream())
             return seglen
         v = self._v()
         pl = v["plan"]
