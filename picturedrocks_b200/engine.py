@@ -35,9 +35,10 @@ def _i32(x):
 
 
 class Engine:
-    def __init__(self, indptr, packed, N, K, gene_lo=0, P_total=None, comm=None):
+    def __init__(self, indptr, packed, N, K, gene_lo=0, P_total=None, comm=None, term=None):
         """indptr: int64[P+1] device tensor (local offsets, indptr[0] == 0);
-        packed: int32 device tensor holding the uint32 words code<<24 | row."""
+        packed: int32 device tensor holding the uint32 words code<<24 | row;
+        term: optional host float64[N+1] term table (see host_term_table)."""
         nat.require_cuda()
         nat.load()
         assert indptr.dtype == torch.int64 and indptr.is_cuda and indptr.is_contiguous()
@@ -68,8 +69,7 @@ class Engine:
         nat.call("prb_device_info", ctypes.byref(sm), ctypes.byref(smem))
         self.sm_count, self.smem_optin = sm.value, smem.value
         # fp64 term table, built on the host (glibc log2), resident in HBM
-        tt = np.empty(self.N + 1, dtype=np.float64)
-        nat.call("prb_term_table", self.N, tt.ctypes.data)
+        tt = term if term is not None else self.host_term_table(self.N)
         self.term = torch.from_numpy(tt).to(self.device)
         # per-cell state workspaces
         dev = self.device
@@ -104,6 +104,13 @@ class Engine:
         self.classsizes = None
         self.cnt_y = None
         self._cnt_x = None  # label-free count table, built on first use
+
+    @staticmethod
+    def host_term_table(N):
+        """T[c] = -(c/N)*log2(c/N) for c = 0..N on the HOST (glibc log2; infoset.py:392-397)."""
+        tt = np.empty(int(N) + 1, dtype=np.float64)
+        nat.call("prb_term_table", int(N), tt.ctypes.data)
+        return tt
 
     # ------------------------------------------------------------------ tables
     @property
@@ -524,6 +531,8 @@ class Engine:
         packed = torch.zeros(nnz + PACKED_PAD, dtype=torch.int32, device=dev)
         nat.call("prb_pack_csc", nat.ptr(rows_d), nat.ptr(codes_d), nnz, nat.ptr(packed),
                  nat.stream())
+        # host work while the (asynchronous) upload is in flight
+        kw.setdefault("term", cls.host_term_table(N))
         K = (int(codes_d.max().item()) + 1) if nnz else 1
         return cls(indptr_d, packed, N, K, **kw)
 
