@@ -36,6 +36,12 @@ WORKLOADS = {
                name="Paul15-shaped synthetic dense 2,730 x 3,451, 19 clusters, makeinfoset (k=5)"),
     "c2": dict(N=3005, P=19972, C=9, K=5, seed=2, dense=True,
                name="Zeisel-shaped synthetic dense 3,005 x 19,972, 9 clusters, makeinfoset (k=5)"),
+    # BASELINE.json configs[4]: two points of the sweep (JMI); k = 10 / 20 go through the
+    # generic shared-histogram kernel, k = 5 through the V layout
+    "c5_k5": dict(N=1000000, P=20000, C=20, K=5, mean_density=0.05, seed=5,
+                  name="sweep point 1e6 x 2e4, 20 clusters, 5 bins, 5% nnz"),
+    "c5_k20": dict(N=100000, P=50000, C=20, K=20, mean_density=0.05, seed=5,
+                   name="sweep point 1e5 x 5e4, 20 clusters, 20 bins, 5% nnz"),
     # one eighth of the genes of c4: what each rank streams in the 8-GPU run (tuning aid)
     "c4_shard8": dict(N=1306127, P=3500, C=60, K=5, mean_density=0.07, seed=4,
                       name="c4 gene shard: 1,306,127 x 3,500, 60 clusters, 7% nnz"),
@@ -275,6 +281,7 @@ def run_ours(args, w):
     inf = pr.markers.SparseInformationSet._from_engine(eng, yd)
     nnz_local = eng.nnz
     stream_bytes = 128 * eng.v["rows"] if eng.v is not None else 4 * nnz_local
+    hot_kernel = "k_stream_v" if eng.vmode else "k_stream"
     fs = Selector(inf)
     os.environ.setdefault("PRB_GRAPH_MIN_STEPS", "3")
     import picturedrocks_b200.markers.mutualinformation.iterative as _it
@@ -368,12 +375,12 @@ def run_ours(args, w):
     if k_ms:
         alg_bytes = 4.0 * nnz_local  # one packed uint32 word per stored entry, read once
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "k_stream_v", "achieved": achieved, "peak": peak,
+        roofline = {"bound": "hbm", "kernel": hot_kernel, "achieved": achieved, "peak": peak,
                     "unit": "GB/s", "frac": achieved / peak, "traffic": known_traffic(args.workload),
                     "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": k_ms,
                     "launches_timed": len(events), "peak_source": peak_src,
                     "share_of_step": k_ms / (ms / args.steps),
-                    "timed_how": "CUDA events around each k_stream_v launch in %d further greedy "
+                    "timed_how": "CUDA events around each " + hot_kernel + " launch in %d further greedy "
                                  "steps launched eagerly right after the timed region "
                                  "(%.3f ms/step eager vs %.3f ms/step in the CUDA-graph timed "
                                  "region)" % (n_inst, inst_ms, ms / args.steps),

@@ -363,8 +363,11 @@ class Engine:
                  nat.ptr(self.counters), nat.stream())
 
     def _finalize(self, hits, cnt, clsz, C, n_hs_cap, n_hs_ptr, out_full, out_marg, direct):
-        if direct or hits is None:
-            # single-gene layout (or no master column at all): one thread per gene
+        wide = os.environ.get("PRB_WIDE_FINALIZE", "1") != "0" and self.K1 > 4
+        if hits is None or (direct and not wide):
+            # single-gene layout with K <= 5 (or no master column at all): lanes / one
+            # thread per gene.  More bins per class: the warp-per-gene kernel below, whose
+            # loads and term gathers run in parallel over the lanes.
             nat.call("prb_finalize_direct", nat.ptr(hits), nat.ptr(cnt), nat.ptr(clsz),
                      nat.ptr(self.hsize), nat.ptr(self.hs_ysum), nat.ptr(self.ha), C, self.K,
                      nat.ptr(self.term), self.N, self.P, nat.ptr(out_full), nat.ptr(out_marg),
