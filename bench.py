@@ -262,6 +262,9 @@ def run_ours(args, w):
     torch.cuda.set_device(local)
     comm = None
     if world > 1:
+        # NCCL's own log lines (e.g. NCCL_DEBUG=VERSION) go to stderr: stdout carries the one
+        # JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     spec = make_spec(w)
     parts = partition_genes(spec.P, world)
@@ -283,6 +286,11 @@ def run_ours(args, w):
     stream_bytes = 128 * eng.v["rows"] if eng.v is not None else 4 * nnz_local
     hot_kernel = "k_stream_v" if eng.vmode else "k_stream"
     fs = Selector(inf)
+    if args.skip_stream:
+        # overhead probe: every kernel of the step except the streaming pass (results are
+        # meaningless; the JSON line is marked invalid)
+        eng._stream_v_launch = lambda *a, **k: None
+        eng._stream_launch = lambda *a, **k: None
     os.environ.setdefault("PRB_GRAPH_MIN_STEPS", "3")
     import picturedrocks_b200.markers.mutualinformation.iterative as _it
     _it.GRAPH_MIN_STEPS = min(_it.GRAPH_MIN_STEPS, max(args.warmup, 2))
@@ -404,6 +412,9 @@ def run_ours(args, w):
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "cuda_graph": graphed, "roofline": roofline,
             "cpu_baseline": cpu, "selected": S_dev[:8],
         }
+        if args.skip_stream:
+            line["invalid"] = "overhead probe: the streaming kernel was not launched"
+
         print(json.dumps(line), flush=True)
     if world > 1:
         from picturedrocks_b200.dist import shutdown
@@ -422,6 +433,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--ref-genes", type=int, default=0)
+    ap.add_argument("--skip-stream", action="store_true",
+                    help="tuning aid: time the step without its streaming kernel (invalid result)")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -135,7 +135,8 @@ k_stream_v(const uint32_t *__restrict__ vpacked, const int32_t *__restrict__ run
            const int32_t *__restrict__ st_seg0, const int32_t *__restrict__ seg_cell0,
            const int32_t *__restrict__ seg_class, int n_st, const uint8_t *__restrict__ sx, int C,
            int32_t *__restrict__ hits, int *counters, const int32_t *__restrict__ item_off,
-           const int32_t *__restrict__ item_row0, const int32_t *__restrict__ item_vg0)
+           const int32_t *__restrict__ item_row0, const int32_t *__restrict__ item_vg0,
+           int help_min)
 {
     constexpr int SPAN = CFG::span, SR = CFG::stage_rows, STAGES = CFG::stages;
     constexpr int STAGE_BYTES = CFG::stage_bytes, THREADS = CFG::threads;
@@ -166,8 +167,7 @@ k_stream_v(const uint32_t *__restrict__ vpacked, const int32_t *__restrict__ run
     // A CTA starts on its home super-tile (blockIdx mod n_st) and drains it together with the
     // other CTAs that call it home.  Afterwards it helps the super-tile with the most
     // unclaimed items — but only when that is worth staging another 64 KB tile for
-    // (>= HELP_MIN items left), or when the tile has no home CTA at all (small grids).
-    constexpr int HELP_MIN = 8 * CFG::warps;
+    // (>= help_min items left), or when the tile has no home CTA at all (small grids).
     for (bool first = true;; first = false) {
         __syncthreads();  // every warp has left the previous super-tile
         if (warp == 0) {
@@ -179,7 +179,7 @@ k_stream_v(const uint32_t *__restrict__ vpacked, const int32_t *__restrict__ run
                 for (int tt = lane; tt < n_st; tt += 32) {
                     const int rem = item_off[tt + 1] - item_off[tt] - *(volatile int *)(counters + tt);
                     const bool homeless = tt >= (int)gridDim.x;
-                    if (rem > 0 && (rem >= HELP_MIN || homeless) && rem > best) {
+                    if (rem > 0 && (rem >= help_min || homeless) && rem > best) {
                         best = rem;
                         best_t = tt;
                     }
@@ -479,6 +479,15 @@ static int v_cfg()
     return cfg;
 }
 
+// items a super-tile must still have unclaimed for a CTA of another tile to come and help
+// (staging a 64 KB tile has to pay off); PRB_V_HELP_MIN overrides it for tuning runs
+static int v_help_min(int warps)
+{
+    const char *e = getenv("PRB_V_HELP_MIN");
+    const int forced = e ? atoi(e) : 0;
+    return forced > 0 ? forced : 8 * warps;
+}
+
 static int v_span()
 {
     switch (v_cfg()) {
@@ -573,7 +582,8 @@ extern "C" int prb_stream_v(const uint32_t *vpacked, const int32_t *run_end,
         PRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         kern<<<grid, warps * 32, smem, S(stream)>>>(vpacked, run_end, tile_row0, n_seg, PV, K1,
                                                     st_seg0, seg_cell0, seg_class, n_st, sx, C, hits,
-                                                    counters, item_off, item_row0, item_vg0);
+                                                    counters, item_off, item_row0, item_vg0,
+                                                    v_help_min(warps));
         return 0;
     };
     switch (v_cfg()) {

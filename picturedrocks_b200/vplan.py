@@ -41,12 +41,17 @@ def segment_plan(class_sizes, cap, max_segs):
 
 
 def item_rows(total_rows, warps, forced=0):
-    """Rows of the large work items: ~12 items per warp on average, at least 256 rows each
-    unless that would leave warps without any item; a multiple of 32."""
-    warps = max(int(warps), 1)
-    r_min = max(32, min(256, int(total_rows) // warps))
-    R = int(forced) or max(r_min, -(-int(total_rows) // (12 * warps)))
-    return (R + 31) & ~31
+    """Rows of the large work items, a multiple of 32.  Every item costs a pipeline restart
+    (favours few, large items), while large items spread the concurrently streamed ranges
+    over more memory and lengthen the tail (favours many, small ones).  Measured optimum on
+    B200 (profiles/r01_item_rows_sweep.txt; rows per warp -> rows per item: 481 -> 64,
+    2 254 -> 384..640, 4 652 -> 768, 9 198 -> 1 024, 18 159 -> 1 536):
+    R = min(4.7 * rpw^0.59, rpw / 6)."""
+    if forced:
+        return (int(forced) + 31) & ~31
+    rpw = max(int(total_rows), 0) / max(int(warps), 1)
+    R = int(min(4.7 * rpw ** 0.59, rpw / 6.0))
+    return max(32, (R + 16) & ~31)
 
 
 def item_cuts(lo, hi, R):
@@ -59,3 +64,4 @@ def item_cuts(lo, hi, R):
             parts.append(np.arange(pos, stop, size, dtype=np.int64))
             pos = int(parts[-1][-1]) + size
     return np.concatenate(parts) if parts else np.zeros(0, dtype=np.int64)
+

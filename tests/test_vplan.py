@@ -44,13 +44,16 @@ def test_segment_plan_balances_super_tiles():
     assert len(spans) == 20 and max(spans) == min(spans) == 3 * 21769
 
 
-@pytest.mark.parametrize("rows,warps", [(86_000_000, 4736), (10_900_000, 4736), (167_963, 4736),
-                                        (100, 4736), (0, 4736)])
-def test_item_rows(rows, warps):
+@pytest.mark.parametrize("rows,warps,lo,hi", [
+    (86_001_274, 4736, 1408, 1664),     # config 4 on one GPU: measured optimum 1 536
+    (43_563_220, 4736, 896, 1152),      # half / quarter / eighth of its genes
+    (22_035_146, 4736, 576, 832),
+    (10_678_142, 4736, 256, 640),
+    (2_278_450, 4736, 64, 96),          # config 3
+    (130_591, 4736, 32, 32), (100, 4736, 32, 32), (0, 4736, 32, 32)])
+def test_item_rows(rows, warps, lo, hi):
     R = vplan.item_rows(rows, warps)
-    assert R % 32 == 0 and R >= 32
-    if rows >= 256 * warps:
-        assert R >= 256 and abs(rows / (12 * warps) - R) <= 32 + 256
+    assert R % 32 == 0 and lo <= R <= hi
     assert vplan.item_rows(rows, warps, forced=320) == 320
 
 
@@ -68,3 +71,4 @@ def test_item_cuts_cover_the_block(lo, hi, R):
     assert np.all(np.diff(sizes[:-1]) <= 0)
     if hi - lo > 64 * R:
         assert sizes[0] == R and sizes[-2] <= max(128, R // 4)
+
