@@ -101,8 +101,10 @@ int prb_stream_hits(const uint32_t *packed, const int64_t *tp, int64_t P, int64_
  *  3. prb_v_count -> caller's scan -> prb_v_scatter build the V layout: every gene g
  *     becomes K-1 virtual genes (g, v), one per non-zero code v; a RUN (vg, s) holds the
  *     entries of virtual gene vg whose relabelled cell newpos[cell] lies in segment s
- *     (prb_v_count takes seg_of_cell int32[N], the segment of every ORIGINAL cell id, or
- *     NULL for a single segment), relabelled (word = code<<24 | newpos[cell]), ascending, padded to a multiple of 32 entries (one 128-byte row); runs are
+ *     (both calls take cellmap uint32[N], indexed by the ORIGINAL cell id: bits 0..23 =
+ *     newpos[cell], bits 24..31 = segment of the cell when n_seg <= 256 — otherwise the
+ *     segments come in seg16 uint16[N]; cellmap NULL = identity positions, one segment),
+ *     relabelled (word = code<<24 | newpos[cell]), in arbitrary order inside a run, padded to a multiple of 32 entries (one 128-byte row); runs are
  *     stored TILE-MAJOR: by (super-tile of s, vg, s).
  *       seglen    int32[P*(K-1)][n_seg]  true run lengths
  *       run_end   int32[P*(K-1)][n_seg]  row just past each run (inclusive scan of
@@ -127,10 +129,11 @@ int prb_stream_hits(const uint32_t *packed, const int64_t *tp, int64_t P, int64_
  *     counters: int32[n_st] scratch (reset by the call); queue: device int32 scratch. */
 int prb_v_tile_capacity(int64_t *max_cells, int *max_segs);
 int prb_v_count(const uint32_t *packed, const int64_t *indptr, int64_t P,
-                const int32_t *seg_of_cell, int n_seg, int K1, int32_t *seglen, int32_t *queue,
-                prb_stream_t stream);
-int prb_v_scatter(const uint32_t *packed, const int64_t *indptr, int64_t P, const int32_t *newpos,
-                  const int32_t *seg_cell0, int n_seg, int K1, const int32_t *seglen,
+                const uint32_t *cellmap, const uint16_t *seg16, int n_seg, int K1,
+                int32_t *seglen, int32_t *queue, prb_stream_t stream);
+int prb_v_scatter(const uint32_t *packed, const int64_t *indptr, int64_t P,
+                  const uint32_t *cellmap, const uint16_t *seg16, int n_seg, int K1,
+                  const int32_t *seglen,
                   const int32_t *run_end, const uint32_t *seg_pad, uint32_t *vpacked,
                   int32_t *queue, prb_stream_t stream);
 int prb_state_v(uint8_t *xj, const int32_t *y, int64_t N, int C, int K, uint8_t *sx,

@@ -35,7 +35,7 @@ _SIGS = {
     "prb_stream_hits": [_vp, _vp, _i64, _i64, _vp, _i64, _i64, _int, _int, _vp, _vp, _vp],
     "prb_state_v": [_vp, _vp, _i64, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "prb_v_tile_capacity": [ctypes.POINTER(_i64), ctypes.POINTER(_int)],
-    "prb_v_count": [_vp, _vp, _i64, _vp, _int, _int, _vp, _vp, _vp],
+    "prb_v_count": [_vp, _vp, _i64, _vp, _vp, _int, _int, _vp, _vp, _vp],
     "prb_v_scatter": [_vp, _vp, _i64, _vp, _vp, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp],
     "prb_v_tile_span": [],
     "prb_stream_v": [_vp, _vp, _vp, _int, _i64, _int, _i64, _vp, _vp, _vp, _int, _i64, _vp, _int,

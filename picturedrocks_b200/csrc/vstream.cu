@@ -11,7 +11,7 @@
 // contiguous (newpos, a stable sort of the labels; only the V layout and the per-cell
 // vectors of this path live in the new order) and cut into SEGMENTS (a class, or a piece of one that fits a shared-memory tile).
 // Every gene g is split into K-1 VIRTUAL GENES (g, v), one per non-zero code v; the
-// entries of a virtual gene are grouped by segment, ascending inside a segment, and every
+// entries of a virtual gene are grouped by segment (in arbitrary order inside a segment), and every
 // (g, v, segment) run is padded to a multiple of 32 entries (one 128-byte ROW, one entry
 // per lane).  Inside a run the class AND the candidate's code are known, so the joint
 // histogram of (y, x_j, x_i) restricted to it has only K-1 <= 4 bins (the value of the
@@ -317,143 +317,170 @@ k_stream_v(const uint32_t *__restrict__ vpacked, const int32_t *__restrict__ run
 }
 
 // ---- building the V layout -------------------------------------------------------------
-// segment of a (relabelled) cell position: number of boundaries <= pos, minus one
-// (bnd[0] = 0 < bnd[1] < ... < bnd[n_seg] = N, staged in shared memory)
-__device__ __forceinline__ int seg_of_pos(const int *bnd, int n_seg, int pos)
+// Both passes: one block per gene (dynamic queue), the gene's entries read with several
+// independent loads per thread in flight, per-(code, segment) counters of the gene in shared
+// memory.  Per-cell table cellmap uint32[N] (indexed by the ORIGINAL cell id): bits 0..23 =
+// relabelled cell position newpos[cell], bits 24..31 = segment of the cell when there are at
+// most 256 segments — ONE gather per entry gives both; with more segments seg16 uint16[N]
+// carries the segment instead.  cellmap == NULL: identity positions, a single segment.
+// (Both passes are bound by the number of distinct cache lines an entry touches: the table
+// gather and, in pass 2, the store.)
+constexpr int VL_WARPS = 8, VL_THREADS = VL_WARPS * 32, VL_U = 4;
+
+__device__ __forceinline__ int vl_seg(uint32_t cm, uint32_t cell, const uint16_t *seg16)
 {
-    int lo = 0, hi = n_seg;  // answer in [lo, hi)
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (bnd[mid] <= pos)
-            lo = mid;
-        else
-            hi = mid;
-    }
-    return lo;
+    return seg16 ? (int)seg16[cell] : (int)(cm >> 24);
 }
 
-// pass 1: per gene, entries per (code, segment) -> seglen[P*K1][n_seg]; seg_of_cell[cell] =
-// segment of the ORIGINAL cell id (NULL: one segment).  One warp per gene (dynamic queue),
-// shared-memory histogram per warp.
-constexpr int VB_WARPS = 8;
-
-__global__ void __launch_bounds__(VB_WARPS * 32)
+// pass 1: entries per (code, segment) -> seglen[P*K1][n_seg]
+__global__ void __launch_bounds__(VL_THREADS)
 k_vcount(const uint32_t *__restrict__ packed, const int64_t *__restrict__ indptr, int64_t P,
-         const int32_t *__restrict__ seg_of_cell, int n_seg, int K1,
-         int32_t *__restrict__ seglen, int *queue)
+         const uint32_t *__restrict__ cellmap, const uint16_t *__restrict__ seg16, int n_seg,
+         int K1, int32_t *__restrict__ seglen, int *queue)
 {
-    extern __shared__ int vb_smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    extern __shared__ int vb_cnt[];  // [nk]
+    __shared__ int s_gene;
+    const int tid = threadIdx.x;
     const int nk = K1 * n_seg;
-    int *cnt = vb_smem + warp * nk;
     for (;;) {
-        int gi = 0;
-        if (lane == 0) gi = atomicAdd(queue, 1);
-        const int64_t g = __shfl_sync(0xffffffffu, gi, 0);
+        __syncthreads();  // the previous gene's counters were written out
+        if (tid == 0) s_gene = atomicAdd(queue, 1);
+        for (int i = tid; i < nk; i += VL_THREADS) vb_cnt[i] = 0;
+        __syncthreads();
+        const int64_t g = s_gene;
         if (g >= P) break;
         const int64_t b = indptr[g], e = indptr[g + 1];
-        for (int i = lane; i < nk; i += 32) cnt[i] = 0;
-        __syncwarp();
-        for (int64_t i = b + lane; i < e; i += 32) {
-            const uint32_t w = packed[i];
-            const int seg = seg_of_cell ? seg_of_cell[w & ROW_MASK] : 0;
-            atomicAdd(cnt + ((w >> 24) - 1u) * n_seg + seg, 1);
+        for (int64_t i0 = b + tid; i0 < e; i0 += VL_THREADS * VL_U) {
+            uint32_t w[VL_U];
+#pragma unroll
+            for (int u = 0; u < VL_U; ++u) {
+                const int64_t i = i0 + u * VL_THREADS;
+                w[u] = i < e ? packed[i] : 0u;  // a stored entry has a non-zero code byte
+            }
+            int seg[VL_U];
+#pragma unroll
+            for (int u = 0; u < VL_U; ++u) {
+                const uint32_t cell = w[u] & ROW_MASK;
+                seg[u] = (w[u] && n_seg > 1) ? vl_seg(seg16 ? 0u : cellmap[cell], cell, seg16) : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < VL_U; ++u)
+                if (w[u]) atomicAdd(vb_cnt + ((w[u] >> 24) - 1u) * n_seg + seg[u], 1);
         }
-        __syncwarp();
-        for (int i = lane; i < nk; i += 32) seglen[g * nk + i] = cnt[i];
-        __syncwarp();
+        __syncthreads();
+        for (int i = tid; i < nk; i += VL_THREADS) seglen[g * nk + i] = vb_cnt[i];
     }
 }
 
-// pass 2: ordered scatter of the relabelled entries (word = code | newpos[cell]) into the
-// padded runs.  One block per gene (dynamic queue); the gene is processed in chunks of 1024
-// entries that are multi-split by (code, segment) in shared memory — per-warp counts of every
-// key, rank inside a 32-entry group by __match_any_sync, an exclusive scan over the warps —
-// so that the ascending cell order inside a run is kept (newpos is increasing inside a class)
-// and the entries of a key leave the chunk as one contiguous write.  Run (vg, s) occupies
-// rows [run_end - ceil(len/32), run_end); the padding words of segment s are
-// seg_pad[s] = 0xFF000000 | (a cell slot the kernel keeps at "x_j = 0").
-constexpr int VS_WARPS = 8, VS_U = 4, VS_CHUNK = VS_WARPS * 32 * VS_U;
+// pass 2: scatter of the relabelled entries (word = code | newpos[cell]) into the padded
+// runs.  Run (vg, s) occupies rows [run_end - ceil(len/32), run_end).  A gene is processed in
+// chunks of VS_CHUNK entries that are counting-sorted by (code, segment) in shared memory
+// (slot inside the chunk's group = old value of a shared counter, so the order of the
+// entries inside a run is arbitrary — the streaming kernel only counts them) and leave the
+// chunk group by group: consecutive threads write consecutive words.  The padding words of
+// segment s are seg_pad[s] = 0xFF000000 | (a cell slot the kernel keeps at "x_j = 0").
+constexpr int VS_U = 8, VS_CHUNK = VL_THREADS * VS_U;
 
-__global__ void __launch_bounds__(VS_WARPS * 32)
+__global__ void __launch_bounds__(VL_THREADS)
 k_vscatter(const uint32_t *__restrict__ packed, const int64_t *__restrict__ indptr, int64_t P,
-           const int32_t *__restrict__ newpos, const int32_t *__restrict__ seg_cell0, int n_seg,
+           const uint32_t *__restrict__ cellmap, const uint16_t *__restrict__ seg16, int n_seg,
            int K1, const int32_t *__restrict__ seglen, const int32_t *__restrict__ run_end,
            const uint32_t *__restrict__ seg_pad, uint32_t *__restrict__ vpacked, int *queue)
 {
     extern __shared__ __align__(8) unsigned char vs_raw[];
     __shared__ int s_gene;
+    __shared__ int s_wsum[VL_WARPS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nk = K1 * n_seg;
-    int64_t *off = (int64_t *)vs_raw;                  // [nk] next free slot of every run
-    int64_t *wbase = off + nk;                         // [VS_WARPS][nk] counts, then bases
-    int *bnd = (int *)(wbase + (int64_t)VS_WARPS * nk);  // [n_seg + 1]
-    for (int i = tid; i <= n_seg; i += blockDim.x) bnd[i] = seg_cell0[i];
+    const int per = (nk + VL_THREADS - 1) / VL_THREADS;  // keys per thread in the scan
+    int64_t *next = (int64_t *)vs_raw;       // [nk] next free slot of every run
+    int *ccnt = (int *)(next + nk);          // [nk] entries of the chunk per key
+    int *cstart = ccnt + nk;                 // [nk] first slot of the key inside the chunk
+    uint32_t *stage = (uint32_t *)(cstart + nk);       // [VS_CHUNK] words, grouped by key
+    uint16_t *skey = (uint16_t *)(stage + VS_CHUNK);   // [VS_CHUNK] key of every staged word
     for (;;) {
-        __syncthreads();
+        __syncthreads();  // the previous gene's padding pass is done with next[]
         if (tid == 0) s_gene = atomicAdd(queue, 1);
         __syncthreads();
         const int64_t g = s_gene;
         if (g >= P) break;
         const int64_t b = indptr[g], e = indptr[g + 1];
-        for (int i = tid; i < nk; i += blockDim.x) {
+        for (int i = tid; i < nk; i += VL_THREADS) {
             const int nr = (seglen[g * nk + i] + 31) >> 5;
-            off[i] = (int64_t)(run_end[g * nk + i] - nr) * 32;
+            next[i] = (int64_t)(run_end[g * nk + i] - nr) * 32;
+            ccnt[i] = 0;
         }
+        __syncthreads();
         for (int64_t c0 = b; c0 < e; c0 += VS_CHUNK) {
-            for (int i = tid; i < VS_WARPS * nk; i += blockDim.x) wbase[i] = 0;
-            __syncthreads();
-            // per-warp counts and the rank of every entry inside its warp's part of the chunk
-            int64_t *wc = wbase + (int64_t)warp * nk;
+            const int n_chunk = (int)min((int64_t)VS_CHUNK, e - c0);
+            // A: key of every entry, its slot inside the chunk's group of that key
+            uint32_t w[VS_U];
+#pragma unroll
+            for (int u = 0; u < VS_U; ++u) {
+                const int i = u * VL_THREADS + tid;
+                w[u] = i < n_chunk ? packed[c0 + i] : 0u;  // a stored entry has a non-zero code byte
+            }
             uint32_t word[VS_U];
             int key[VS_U], rk[VS_U];
 #pragma unroll
             for (int u = 0; u < VS_U; ++u) {
-                const int64_t i = c0 + (warp * VS_U + u) * 32 + lane;
-                const bool valid = i < e;
-                const unsigned act = __ballot_sync(0xffffffffu, valid);
-                key[u] = -1;
-                if (valid) {
-                    const uint32_t w = packed[i];
-                    const int cell = (int)(w & ROW_MASK);
-                    const int pos = newpos ? newpos[cell] : cell;
-                    const int seg = n_seg > 1 ? seg_of_pos(bnd, n_seg, pos) : 0;
-                    key[u] = (int)((w >> 24) - 1u) * n_seg + seg;
-                    word[u] = (w & ~ROW_MASK) | (uint32_t)pos;
-                    const unsigned m = __match_any_sync(act, key[u]);
-                    const int r = __popc(m & ((1u << lane) - 1u));
-                    const int base = (int)wc[key[u]];
-                    rk[u] = base + r;
-                    __syncwarp(act);
-                    if (r == 0) wc[key[u]] = base + __popc(m);
-                }
-                __syncwarp();
+                const uint32_t cell = w[u] & ROW_MASK;
+                const uint32_t cm = (w[u] && cellmap) ? cellmap[cell] : cell;
+                const int seg = (w[u] && n_seg > 1) ? vl_seg(cm, cell, seg16) : 0;
+                key[u] = (int)((w[u] >> 24) - 1u) * n_seg + seg;
+                word[u] = (w[u] & ~ROW_MASK) | (cm & ROW_MASK);
             }
-            __syncthreads();
-            // exclusive scan over the warps: wbase[w][k] = first slot of warp w's entries
-            for (int k = tid; k < nk; k += blockDim.x) {
-                int64_t run = off[k];
-#pragma unroll
-                for (int w = 0; w < VS_WARPS; ++w) {
-                    const int64_t c = wbase[(int64_t)w * nk + k];
-                    wbase[(int64_t)w * nk + k] = run;
-                    run += c;
-                }
-                off[k] = run;
-            }
-            __syncthreads();
 #pragma unroll
             for (int u = 0; u < VS_U; ++u)
-                if (key[u] >= 0) vpacked[wc[key[u]] + rk[u]] = word[u];
+                rk[u] = w[u] ? atomicAdd(ccnt + key[u], 1) : 0;
+            __syncthreads();
+            // exclusive scan of the chunk's counts over the keys (thread t: keys [t*per, ..))
+            {
+                int sum = 0;
+                for (int k = tid * per; k < min(nk, (tid + 1) * per); ++k) sum += ccnt[k];
+                int inc = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += v;
+                }
+                if (lane == 31) s_wsum[warp] = inc;
+                __syncthreads();
+                int run = inc - sum;
+                for (int wv = 0; wv < warp; ++wv) run += s_wsum[wv];
+                for (int k = tid * per; k < min(nk, (tid + 1) * per); ++k) {
+                    cstart[k] = run;
+                    run += ccnt[k];
+                }
+            }
+            __syncthreads();
+            // B: words into the staging buffer, grouped by key
+#pragma unroll
+            for (int u = 0; u < VS_U; ++u)
+                if (w[u]) {
+                    const int p = cstart[key[u]] + rk[u];
+                    stage[p] = word[u];
+                    skey[p] = (uint16_t)key[u];
+                }
+            __syncthreads();
+            // C: out, group by group (consecutive slots of a key -> consecutive words)
+            for (int p = tid; p < n_chunk; p += VL_THREADS) {
+                const int k = skey[p];
+                vpacked[next[k] + (p - cstart[k])] = stage[p];
+            }
+            __syncthreads();
+            for (int k = tid; k < nk; k += VL_THREADS) {
+                next[k] += ccnt[k];
+                ccnt[k] = 0;
+            }
             __syncthreads();
         }
-        __syncthreads();
         // padding up to the end of the run's last row
-        for (int i = tid; i < nk; i += blockDim.x) {
+        for (int i = tid; i < nk; i += VL_THREADS) {
             const int s = i % n_seg;
             const int64_t end = (int64_t)run_end[g * nk + i] * 32;
             const uint32_t padw = seg_pad[s];
-            for (int64_t p = off[i]; p < end; ++p) vpacked[p] = padw;
+            for (int64_t p = next[i]; p < end; ++p) vpacked[p] = padw;
         }
     }
 }
@@ -522,41 +549,46 @@ extern "C" int prb_v_tile_capacity(int64_t *max_cells, int *max_segs)
 }
 
 extern "C" int prb_v_count(const uint32_t *packed, const int64_t *indptr, int64_t P,
-                           const int32_t *seg_of_cell, int n_seg, int K1, int32_t *seglen,
+                           const uint32_t *cellmap, const uint16_t *seg16, int n_seg, int K1,
+                           int32_t *seglen,
                            int32_t *queue, prb_stream_t stream)
 {
     if (P == 0) return 0;
     PRB_REQUIRE(K1 >= 1 && K1 <= 4 && n_seg >= 1, "bad arguments");
-    PRB_REQUIRE(seg_of_cell != nullptr || n_seg == 1, "seg_of_cell is required");
-    const size_t smem = (size_t)VB_WARPS * K1 * n_seg * 4;
+    PRB_REQUIRE(n_seg == 1 || seg16 != nullptr || (cellmap != nullptr && n_seg <= 256),
+                "the segment of every cell is required (cellmap bits 24..31, or seg16)");
+    PRB_REQUIRE(n_seg <= 65536, "too many segments");
+    const size_t smem = (size_t)K1 * n_seg * 4;
     PRB_REQUIRE((int64_t)smem <= devinfo().smem_optin - 1024, "too many segments");
     PRB_CUDA(cudaFuncSetAttribute(k_vcount, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PRB_CUDA(cudaMemsetAsync(queue, 0, sizeof(int32_t), S(stream)));
-    const int grid = (int)hmin(ceil_div(P, VB_WARPS), (int64_t)devinfo().sm_count * 8);
-    k_vcount<<<grid, VB_WARPS * 32, smem, S(stream)>>>(packed, indptr, P, seg_of_cell, n_seg, K1,
-                                                       seglen, queue);
+    const int grid = (int)hmin(P, (int64_t)devinfo().sm_count * 8);
+    k_vcount<<<grid, VL_THREADS, smem, S(stream)>>>(packed, indptr, P, cellmap, seg16, n_seg, K1,
+                                                    seglen, queue);
     PRB_LAUNCH_CHECK("k_vcount");
     return 0;
 }
 
 extern "C" int prb_v_scatter(const uint32_t *packed, const int64_t *indptr, int64_t P,
-                             const int32_t *newpos, const int32_t *seg_cell0, int n_seg, int K1,
+                             const uint32_t *cellmap, const uint16_t *seg16, int n_seg, int K1,
                              const int32_t *seglen, const int32_t *run_end,
                              const uint32_t *seg_pad, uint32_t *vpacked, int32_t *queue,
                              prb_stream_t stream)
 {
     if (P == 0) return 0;
-    PRB_REQUIRE(K1 >= 1 && K1 <= 4 && n_seg >= 1 && seg_cell0, "bad arguments");
+    PRB_REQUIRE(K1 >= 1 && K1 <= 4 && n_seg >= 1, "bad arguments");
+    PRB_REQUIRE(n_seg == 1 || seg16 != nullptr || (cellmap != nullptr && n_seg <= 256),
+                "the segment of every cell is required (cellmap bits 24..31, or seg16)");
+    PRB_REQUIRE(n_seg <= 65536 / K1, "too many segments");
     const size_t nk = (size_t)K1 * n_seg;
-    const size_t smem = (nk + (size_t)VS_WARPS * nk) * 8 + ((size_t)n_seg + 1) * 4;
+    const size_t smem = nk * 16 + (size_t)VS_CHUNK * 6;
     PRB_REQUIRE((int64_t)smem <= devinfo().smem_optin - 1024, "too many segments");
     PRB_CUDA(cudaFuncSetAttribute(k_vscatter, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
     PRB_CUDA(cudaMemsetAsync(queue, 0, sizeof(int32_t), S(stream)));
     const int grid = (int)hmin(P, (int64_t)devinfo().sm_count * 8);
-    k_vscatter<<<grid, VS_WARPS * 32, smem, S(stream)>>>(packed, indptr, P, newpos, seg_cell0,
-                                                         n_seg, K1, seglen, run_end, seg_pad,
-                                                         vpacked, queue);
+    k_vscatter<<<grid, VL_THREADS, smem, S(stream)>>>(packed, indptr, P, cellmap, seg16, n_seg, K1,
+                                                      seglen, run_end, seg_pad, vpacked, queue);
     PRB_LAUNCH_CHECK("k_vscatter");
     return 0;
 }

@@ -229,15 +229,23 @@ class Engine:
         newpos = self.newpos if self.has_y else None
         PV = max(P * K1, 1)
         seglen = torch.zeros(PV * n_seg, dtype=torch.int32, device=dev)
-        seg_of_cell = None  # segment of every ORIGINAL cell id
-        if n_seg > 1:
+        # per-cell table of the two layout kernels, indexed by the ORIGINAL cell id:
+        # bits 0..23 relabelled position, bits 24..31 segment (seg16 when there are > 256)
+        cellmap = seg16 = None
+        if n_seg > 1 or newpos is not None:
             pos = newpos if newpos is not None else torch.arange(self.N, dtype=torch.int32,
                                                                  device=dev)
-            seg_of_cell = torch.bucketize(pos, pl["seg_cell0"][1:-1].contiguous(),
-                                          right=True).to(torch.int32)
-        nat.call("prb_v_count", nat.ptr(self.packed), nat.ptr(self.indptr), P,
-                 nat.ptr(seg_of_cell), n_seg, K1, nat.ptr(seglen), nat.ptr(self.counters),
-                 nat.stream())
+            cellmap = pos
+            if n_seg > 1:
+                if n_seg * K1 > 65536:
+                    raise NotImplementedError("too many cell segments")
+                seg = torch.bucketize(pos, pl["seg_cell0"][1:-1].contiguous(), right=True)
+                if n_seg <= 256:
+                    cellmap = (pos | (seg << 24).to(torch.int32)).contiguous()
+                else:
+                    seg16 = seg.to(torch.int16)  # bit pattern of a uint16
+        nat.call("prb_v_count", nat.ptr(self.packed), nat.ptr(self.indptr), P, nat.ptr(cellmap),
+                 nat.ptr(seg16), n_seg, K1, nat.ptr(seglen), nat.ptr(self.counters), nat.stream())
         # rows of every run, scanned in storage order: (super-tile, virtual gene, segment)
         span = nat.load().prb_v_tile_span()
         cell0, st = pl["cell0"], pl["st"]
@@ -258,8 +266,8 @@ class Engine:
         v_rows = base
         seg_pad = torch.from_numpy(pad.astype(np.uint32).view(np.int32)).to(dev)
         vpacked = torch.empty(v_rows * 32 + PACKED_PAD, dtype=torch.int32, device=dev)
-        nat.call("prb_v_scatter", nat.ptr(self.packed), nat.ptr(self.indptr), P, nat.ptr(newpos),
-                 nat.ptr(pl["seg_cell0"]), n_seg, K1, nat.ptr(seglen), nat.ptr(run_end),
+        nat.call("prb_v_scatter", nat.ptr(self.packed), nat.ptr(self.indptr), P, nat.ptr(cellmap),
+                 nat.ptr(seg16), n_seg, K1, nat.ptr(seglen), nat.ptr(run_end),
                  nat.ptr(seg_pad), nat.ptr(vpacked), nat.ptr(self.counters), nat.stream())
         # work items: consecutive row ranges of every super-tile's block, ~16 per warp on
         # average; the first 3/4 of a block in large items, then two rounds of smaller ones,
@@ -300,8 +308,8 @@ class Engine:
         dev, P, K1 = self.device, self.P, self.K1
         if not with_classes:
             seglen = torch.zeros(max(P * K1, 1), dtype=torch.int32, device=dev)
-            nat.call("prb_v_count", nat.ptr(self.packed), nat.ptr(self.indptr), P, None, 1, K1,
-                     nat.ptr(seglen), nat.ptr(self.counters), nat.stream())
+            nat.call("prb_v_count", nat.ptr(self.packed), nat.ptr(self.indptr), P, None, None, 1,
+                     K1, nat.ptr(seglen), nat.ptr(self.counters), nat.stream())
             return seglen
         v = self._v()
         pl = v["plan"]
@@ -531,7 +539,8 @@ class Engine:
         rows_d = up(indices, torch.int32)
         codes_d = up(data, torch.uint8)
         nnz = rows_d.numel()
-        packed = torch.zeros(nnz + PACKED_PAD, dtype=torch.int32, device=dev)
+        packed = torch.empty(nnz + PACKED_PAD, dtype=torch.int32, device=dev)
+        packed[nnz:].zero_()  # the slack words; everything below is written by the pack kernel
         nat.call("prb_pack_csc", nat.ptr(rows_d), nat.ptr(codes_d), nnz, nat.ptr(packed),
                  nat.stream())
         # host work while the (asynchronous) upload is in flight
