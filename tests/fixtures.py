@@ -92,3 +92,43 @@ def continuous_matrix(seed, N=2000, P=24):
     X[:, 6] = -X[:, 6]
     X[:, 7] = np.arange(N) % 10
     return X
+
+
+# ---- callers around the hot path (tests/test_performance.py, golden/make_golden_perf.py) ----
+FOLD_CASES = [(10, 3), (11, 5), (100, 7), (3, 5), (8, 1)]
+
+
+def cluster_names(n=57, p=9, seed=5):
+    """Small count matrix + string cluster names (three named clusters, unsorted)."""
+    rng = np.random.RandomState(seed)
+    names = rng.choice(["T cell", "B cell", "NK"], size=n, p=[0.5, 0.3, 0.2])
+    lam = 1.0 + 4.0 * rng.rand(3, p)
+    code = {"T cell": 0, "B cell": 1, "NK": 2}
+    X = rng.poisson(lam[[code[s] for s in names]]).astype(np.float32)
+    return X, names
+
+
+def predictions(n=200, K=5, seed=9):
+    rng = np.random.RandomState(seed)
+    y = rng.randint(0, K, n)
+    y[:K] = np.arange(K)
+    yhat = np.where(rng.rand(n) < 0.7, y, rng.randint(0, K, n))
+    return y, yhat
+
+
+def variance_selector(n):
+    """select_function: the n genes of largest variance over the training cells."""
+    def select(traindata):
+        X = np.asarray(traindata.X, dtype=np.float64)
+        return [int(g) for g in np.argsort(-X.var(axis=0), kind="stable")[:n]]
+    return select
+
+
+class MajorityClassifier:
+    """classifier protocol of FoldTester.classify: predicts the most frequent training label."""
+
+    def train(self, adata):
+        self.label = int(np.bincount(np.asarray(adata.obs["y"])).argmax())
+
+    def test(self, Xtest):
+        return np.full(Xtest.shape[0], self.label)
