@@ -321,6 +321,29 @@ int prb_sparse_entropy_wrt_host(const int32_t *dindices, const int64_t *dindptr,
 int prb_sparse_entropy_host(const int64_t *data, int64_t nnz, int64_t n_rows, int64_t max_val,
                             double *out);
 
+/* ---- Per-step exchange over NVLink peer memory (EXPERIMENTAL, csrc/peer.cu) -------------
+ * Replaces the two NCCL collectives of a gene-sharded greedy step (the reference has no
+ * multi-process mode; this is the SURVEY 8e exchange).  Every rank owns a SYMMETRIC buffer
+ * of prb_peer_layout().bytes bytes, zero-filled, and the device array peers[W] of all
+ * ranks' buffer addresses (rank order).  Per step, on every rank, in this order:
+ *   prb_peer_gather16  local argmax of the block candidates, 16-byte (score, index) record
+ *                      pushed to every peer, wait for all W records -> out double[W][2]
+ *                      (index as int64 bits); *seq (device uint32, 0 at start) += 1
+ *   prb_argmax_commit  on out (n_cand = W, stride = 2), as with the NCCL all-gather
+ *   prb_peer_clean     zero this rank's x_j area (mine + off_col) if *dirty
+ *   prb_scatter_gene_u8  into mine + off_col (a no-op on ranks that do not own the gene)
+ *   prb_peer_column    owner: publish; others: wait and pull the owner's x_j area;
+ *                      all: -> xj_local uint8[n_pad]; *dirty = (this rank is the owner)
+ * shard_lo int32[W+1]: first gene of every rank (last = P_total). */
+int prb_peer_layout(int64_t N, int W, int64_t *bytes, int64_t *off_col, int64_t *n_pad);
+int prb_peer_gather16(const double *cand_score, const int64_t *cand_idx, int64_t n_cand,
+                      const uint64_t *peers, int rank, int W, int64_t N, uint32_t *seq,
+                      double *out, prb_stream_t stream);
+int prb_peer_clean(void *mine, int64_t N, int W, const int32_t *dirty, prb_stream_t stream);
+int prb_peer_column(const uint64_t *peers, int rank, int W, int64_t N, const int32_t *gene_ptr,
+                    const int32_t *shard_lo, const uint32_t *seq, uint8_t *xj_local,
+                    int32_t *dirty, prb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

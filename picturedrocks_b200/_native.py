@@ -71,6 +71,11 @@ _SIGS = {
     "prb_synth_labels": [_vp, _i64, _int, _u64, _vp],
     "prb_synth_count": [_vp, _i64, _i64, _i64, _int, _int, _u32, _u64, _vp, _vp, _vp],
     "prb_synth_fill": [_vp, _i64, _i64, _i64, _int, _int, _u32, _u64, _vp, _vp, _vp, _vp],
+    "prb_peer_layout": [_i64, _int, ctypes.POINTER(_i64), ctypes.POINTER(_i64),
+                        ctypes.POINTER(_i64)],
+    "prb_peer_gather16": [_vp, _vp, _i64, _vp, _int, _int, _i64, _vp, _vp, _vp],
+    "prb_peer_clean": [_vp, _i64, _int, _vp, _vp],
+    "prb_peer_column": [_vp, _int, _int, _i64, _vp, _vp, _vp, _vp, _vp, _vp],
     "prb_sparse_entropy_wrt_host": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64,
                                     _vp, _vp, _i64, _vp],
     "prb_sparse_entropy_host": [_vp, _i64, _i64, _i64, _vp],
@@ -124,7 +129,7 @@ KERNELS = {
     "prb_argmax_final": 1, "prb_commit_add": 1, "prb_transpose": 1, "prb_sort_columns": 1,
     "prb_qd_edges": 1, "prb_qd_digitize": 1, "prb_sort_segments": 1, "prb_qd_edges_sparse": 1,
     "prb_qd_count_sparse": 1, "prb_qd_fill_sparse": 1, "prb_synth_labels": 1, "prb_synth_count": 1,
-    "prb_synth_fill": 1,
+    "prb_synth_fill": 1, "prb_peer_gather16": 1, "prb_peer_clean": 1, "prb_peer_column": 1,
 }
 LAUNCHES = 0
 

@@ -75,7 +75,7 @@ class Engine:
         dev = self.device
         # per-cell joint state (uint8 or uint16 view), padded for 128-bit tile copies
         self.state_buf = torch.zeros(2 * self.N + 64, dtype=torch.uint8, device=dev)
-        self.xj = torch.zeros(self.N, dtype=torch.uint8, device=dev)
+        self.xj = torch.zeros(self.N + 16, dtype=torch.uint8, device=dev)  # + slack: 16-byte copies
         self.mpacked = None
         self.hsize = torch.zeros(_I16_MAX_BINS, dtype=torch.int32, device=dev)
         self.hs_y = torch.zeros(_I16_MAX_BINS, dtype=torch.int32, device=dev)
@@ -104,6 +104,7 @@ class Engine:
         self.classsizes = None
         self.cnt_y = None
         self._cnt_x = None  # label-free count table, built on first use
+        self.peer_step = False  # True while a selector runs a step with the peer-memory exchange
 
     @staticmethod
     def host_term_table(N):
@@ -402,10 +403,20 @@ class Engine:
             newpos = self.newpos if self._v()["relabelled"] else None
         else:
             self.xj.zero_()
+        peer = self.comm.peer if (self.comm is not None and self.peer_step) else None
+        if peer is not None:
+            # greedy step with the peer-memory exchange (csrc/peer.cu): the owner scatters
+            # into the x_j area of its symmetric buffer, everyone pulls it from there
+            peer.clean()
+            target = peer.col
+        else:
+            target = self.xj
         nat.call("prb_scatter_gene_u8", nat.ptr(self.packed), nat.ptr(self.indptr),
                  nat.ptr(self.gene_ptr), _i32(self.gene_lo), self.P, nat.ptr(newpos),
-                 nat.ptr(self.xj), nat.stream())
-        if self.comm is not None:
+                 nat.ptr(target), nat.stream())
+        if peer is not None:
+            peer.fetch_column(self.gene_ptr, self.xj)
+        elif self.comm is not None:
             self.comm.allreduce_max_(self.xj)
 
     def direct_step(self, with_y, out_full, out_marg):

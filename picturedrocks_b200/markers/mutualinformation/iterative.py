@@ -110,9 +110,14 @@ class _DeviceScores:
             nat.call("prb_argmax_commit", nat.ptr(self.cand_score), nat.ptr(self.cand_idx),
                      self.n_blocks, 1, nat.ptr(self.best_score), nat.ptr(self.best_idx), *commit)
             return
-        nat.call("prb_argmax_final", nat.ptr(self.cand_score), nat.ptr(self.cand_idx),
-                 self.n_blocks, 1, nat.ptr(self.best_score), nat.ptr(self.best_idx), s)
-        g = self.comm.all_gather_cat(self.best)  # [world][score, idx]
+        peer = self.comm.enable_peer(e.N)
+        if peer is not None:
+            # one kernel over NVLink peer memory instead of argmax_final + NCCL all-gather
+            g = peer.gather_candidates(self.cand_score, self.cand_idx, self.n_blocks)
+        else:
+            nat.call("prb_argmax_final", nat.ptr(self.cand_score), nat.ptr(self.cand_idx),
+                     self.n_blocks, 1, nat.ptr(self.best_score), nat.ptr(self.best_idx), s)
+            g = self.comm.all_gather_cat(self.best)  # [world][score, idx]
         nat.call("prb_argmax_commit", nat.ptr(g), nat.ptr(g) + 8, self.comm.world, 2,
                  nat.ptr(self.best_score), nat.ptr(self.best_idx), *commit)
 
@@ -210,7 +215,12 @@ class _GreedyDevice(IterativeFeatureSelection):
     def _one_step(self):
         d = self._d
         d.pick_and_commit()
-        d.apply(self._kind, False)
+        # (the column exchange may go over peer memory only in steps whose candidates did)
+        d.engine.peer_step = d.comm is not None and d.comm.peer is not None
+        try:
+            d.apply(self._kind, False)
+        finally:
+            d.engine.peer_step = False
 
     def _capture(self):
         """Capture one greedy step (kernels + collectives) on a side stream."""

@@ -16,10 +16,12 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, ret):
+def _worker(rank, world, port, ret, peer=False):
     import torch
     import torch.distributed as dist
 
+    if peer:
+        os.environ["PRB_PEER_EXCHANGE"] = "1"
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -55,18 +57,21 @@ def _worker(rank, world, port, ret):
 
 
 @pytest.mark.timeout(600)
-def test_two_rank_selection_equals_single_gpu():
+@pytest.mark.parametrize("peer", [False, True], ids=["nccl", "peer-memory"])
+def test_two_rank_selection_equals_single_gpu(peer):
     import torch
     import torch.multiprocessing as mp
 
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
+    if peer and os.environ.get("PRB_TEST_PEER", "0") != "1":
+        pytest.skip("experimental peer-memory exchange (csrc/peer.cu): set PRB_TEST_PEER=1")
     import picturedrocks_b200 as pr
     from picturedrocks_b200.synth import DiscretisedSpec
 
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), ret, peer), nprocs=2, join=True)
     spec = DiscretisedSpec(N=40000, P=1203, C=9, K=5, mean_density=0.08, seed=21)
     eng, yd = spec.device_engine()
     inf = pr.markers.SparseInformationSet._from_engine(eng, yd)
