@@ -270,9 +270,9 @@ class Engine:
         nat.call("prb_v_scatter", nat.ptr(self.packed), nat.ptr(self.indptr), P, nat.ptr(cellmap),
                  nat.ptr(seg16), n_seg, K1, nat.ptr(seglen), nat.ptr(run_end),
                  nat.ptr(seg_pad), nat.ptr(vpacked), nat.ptr(self.counters), nat.stream())
-        # work items: consecutive row ranges of every super-tile's block, ~16 per warp on
-        # average; the first 3/4 of a block in large items, then two rounds of smaller ones,
-        # so that the tail of a launch is short
+        # work items: consecutive row ranges of every super-tile's block (size: the measured
+        # rule of vplan.item_rows); the first 3/4 of a block in large items, then two rounds
+        # of smaller ones, so that the tail of a launch is short
         warps = nat.load().prb_v_warps()
         R = vplan.item_rows(v_rows, warps, int(os.environ.get("PRB_V_ITEM_ROWS", 0)))
         item_off, row0, vg0 = [0], [], []
