@@ -136,6 +136,19 @@ int prb_v_scatter(const uint32_t *packed, const int64_t *indptr, int64_t P,
                   const int32_t *seglen,
                   const int32_t *run_end, const uint32_t *seg_pad, uint32_t *vpacked,
                   int32_t *queue, prb_stream_t stream);
+/* EXPERIMENTAL "V16" layout (PRB_V16=1; staged, not yet run on hardware): rows of 64 entries
+ * of 16 bits (the cell id inside its super-tile), runs padded to 64 entries, run_end / tile_row0 /
+ * item_row0 in rows of 64; same arguments as prb_v_scatter / prb_stream_v. */
+int prb_v_scatter16(const uint32_t *packed, const int64_t *indptr, int64_t P,
+                    const uint32_t *cellmap, const uint16_t *seg16, int n_seg, int K1,
+                    const int32_t *seglen, const int32_t *run_end, const uint32_t *seg_pad,
+                    uint32_t *vpacked, int32_t *queue, prb_stream_t stream);
+int prb_stream_v16(const uint32_t *vpacked, const int32_t *run_end, const int32_t *tile_row0,
+                   int n_seg, int64_t P, int K1, int64_t v_rows, const int32_t *st_seg0,
+                   const int32_t *seg_cell0, const int32_t *seg_class, int n_st,
+                   int64_t max_tile_cells, const uint8_t *sx, int C, int32_t *hits,
+                   int32_t *counters, const int32_t *item_off, const int32_t *item_row0,
+                   const int32_t *item_vg0, int64_t n_items, prb_stream_t stream);
 int prb_state_v(uint8_t *xj, const int32_t *y, int64_t N, int C, int K, uint8_t *sx,
                 int32_t *hsize, int32_t *hs_begin, int32_t *hs_y, int32_t *hs_ysum, int32_t *ha,
                 int32_t *ticket, prb_stream_t stream);

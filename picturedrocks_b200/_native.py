@@ -37,9 +37,12 @@ _SIGS = {
     "prb_v_tile_capacity": [ctypes.POINTER(_i64), ctypes.POINTER(_int)],
     "prb_v_count": [_vp, _vp, _i64, _vp, _vp, _int, _int, _vp, _vp, _vp],
     "prb_v_scatter": [_vp, _vp, _i64, _vp, _vp, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp],
+    "prb_v_scatter16": [_vp, _vp, _i64, _vp, _vp, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp],
     "prb_v_tile_span": [],
     "prb_stream_v": [_vp, _vp, _vp, _int, _i64, _int, _i64, _vp, _vp, _vp, _int, _i64, _vp, _int,
                      _vp, _vp, _vp, _vp, _vp, _i64, _vp],
+    "prb_stream_v16": [_vp, _vp, _vp, _int, _i64, _int, _i64, _vp, _vp, _vp, _int, _i64, _vp, _int,
+                       _vp, _vp, _vp, _vp, _vp, _i64, _vp],
     "prb_v_warps": [],
     "prb_scatter_gene_u8": [_vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp],
     "prb_scatter_gene_or32": [_vp, _vp, _i64, _int, _vp, _vp],
@@ -130,6 +133,7 @@ KERNELS = {
     "prb_qd_edges": 1, "prb_qd_digitize": 1, "prb_sort_segments": 1, "prb_qd_edges_sparse": 1,
     "prb_qd_count_sparse": 1, "prb_qd_fill_sparse": 1, "prb_synth_labels": 1, "prb_synth_count": 1,
     "prb_synth_fill": 1, "prb_peer_gather16": 1, "prb_peer_clean": 1, "prb_peer_column": 1,
+    "prb_v_scatter16": 1, "prb_stream_v16": 1,
 }
 LAUNCHES = 0
 

@@ -95,6 +95,12 @@ __device__ __forceinline__ uint32_t v_shl1(uint32_t s)
     return r;
 }
 
+// the two 16-bit entries of a V16 word
+__device__ __forceinline__ uint32_t v_pair(uint32_t w)
+{
+    return v_shl1(v_probe(w & 0xFFFFu)) + v_shl1(v_probe(w >> 16));
+}
+
 // Sum the four 8-bit fields of acc over the warp (two REDUX.SUM on 16-bit field pairs: a
 // per-lane field is <= 255, so 32 lanes fit 16 bits) and add field a to out[a*K1].
 // woff = lane*K1 for the writer lanes 0..K1-1, -1 elsewhere.
@@ -128,7 +134,10 @@ __device__ __forceinline__ void v_flush(uint32_t &acc, int32_t *out, int woff, i
 // loader sets to "x_j = 0", so every row is counted the same way (no lane masks).
 // sx: uint8[N] shift codes 8*(x_j-1), >= 32 where x_j = 0 (prb_state_v).
 // hits: int32[P][C][K1][K1], added to.
-template <typename CFG>
+// EPW = entries per 32-bit word of the layout: 1 (word = code<<24 | cell, of which this kernel
+// only reads the cell's low 16 bits) or 2 (EXPERIMENTAL "V16" layout, PRB_V16=1: a row holds
+// 64 entries of 16 bits, the cell id inside its super-tile; half the bytes per entry).
+template <typename CFG, int EPW>
 __global__ void __launch_bounds__(CFG::threads, 1)
 k_stream_v(const uint32_t *__restrict__ vpacked, const int32_t *__restrict__ run_end,
            const int32_t *__restrict__ tile_row0, int n_seg, int64_t PV, int K1,
@@ -140,6 +149,7 @@ k_stream_v(const uint32_t *__restrict__ vpacked, const int32_t *__restrict__ run
 {
     constexpr int SPAN = CFG::span, SR = CFG::stage_rows, STAGES = CFG::stages;
     constexpr int STAGE_BYTES = CFG::stage_bytes, THREADS = CFG::threads;
+    constexpr int FB = 255 / EPW;  // rows after which a lane's 8-bit fields could overflow
     // The kernel has NO static shared memory, so the dynamic region starts at a fixed offset of
     // the CTA's shared window and the tile (its first SPAN bytes) is addressed by the bare
     // cell index: a probe is LDS.U16 (index from the ring) -> LDS.U8 [index + imm].
@@ -254,7 +264,7 @@ k_stream_v(const uint32_t *__restrict__ vpacked, const int32_t *__restrict__ run
             int wait_slot = 0;  // ring slot of the next stage to wait for
             int r = 0;          // next row to count (relative to row_begin)
             int limit = 0;      // rows below it are in shared memory (next stage boundary)
-            int fb = 255;       // row at which the 8-bit fields could overflow
+            int fb = FB;        // row at which the 8-bit fields could overflow
             const uint32_t *rp = ring;  // lane's word of row r
             int64_t g = vg_a / K1;
             int v = (int)(vg_a - g * K1);
@@ -278,20 +288,31 @@ k_stream_v(const uint32_t *__restrict__ vpacked, const int32_t *__restrict__ run
                     for (;;) {
                         const int stop = min(min(e, limit), fb);
                         const uint32_t *rp_end = rp + (stop - r) * 32;
+                        if constexpr (EPW == 1) {
 #pragma unroll 1
-                        for (; rp + 96 < rp_end; rp += 128) {
-                            const uint32_t w0 = rp[0], w1 = rp[32], w2 = rp[64], w3 = rp[96];
-                            const uint32_t x0 = v_probe(w0 & (SPAN - 1)), x1 = v_probe(w1 & (SPAN - 1));
-                            const uint32_t x2 = v_probe(w2 & (SPAN - 1)), x3 = v_probe(w3 & (SPAN - 1));
-                            acc += v_shl1(x0) + v_shl1(x1) + v_shl1(x2) + v_shl1(x3);
+                            for (; rp + 96 < rp_end; rp += 128) {
+                                const uint32_t w0 = rp[0], w1 = rp[32], w2 = rp[64], w3 = rp[96];
+                                const uint32_t x0 = v_probe(w0 & (SPAN - 1)), x1 = v_probe(w1 & (SPAN - 1));
+                                const uint32_t x2 = v_probe(w2 & (SPAN - 1)), x3 = v_probe(w3 & (SPAN - 1));
+                                acc += v_shl1(x0) + v_shl1(x1) + v_shl1(x2) + v_shl1(x3);
+                            }
+#pragma unroll 1
+                            for (; rp < rp_end; rp += 32) acc += v_shl1(v_probe(rp[0] & (SPAN - 1)));
+                        } else {
+                            static_assert(EPW == 1 || SPAN == 65536, "16-bit entries index a 64 K tile");
+#pragma unroll 1
+                            for (; rp + 96 < rp_end; rp += 128) {
+                                const uint32_t w0 = rp[0], w1 = rp[32], w2 = rp[64], w3 = rp[96];
+                                acc += v_pair(w0) + v_pair(w1) + v_pair(w2) + v_pair(w3);
+                            }
+#pragma unroll 1
+                            for (; rp < rp_end; rp += 32) acc += v_pair(rp[0]);
                         }
-#pragma unroll 1
-                        for (; rp < rp_end; rp += 32) acc += v_shl1(v_probe(rp[0] & (SPAN - 1)));
                         r = stop;
                         if (r == e) break;
                         if (r == fb) {  // the 8-bit fields are full
                             v_flush(acc, oseg, woff, lane);
-                            fb = r + 255;
+                            fb = r + FB;
                         }
                         if (r == limit) {
                             // ring event at a stage boundary: hand the stage just counted back
@@ -308,7 +329,7 @@ k_stream_v(const uint32_t *__restrict__ vpacked, const int32_t *__restrict__ run
                         }
                     }
                     v_flush(acc, oseg, woff, lane);  // hits are added to: partial runs are fine
-                    fb = r + 255;
+                    fb = r + FB;
                 }
             }
             __syncwarp();  // the ring is free for the next item
@@ -379,8 +400,11 @@ k_vcount(const uint32_t *__restrict__ packed, const int64_t *__restrict__ indptr
 // entries inside a run is arbitrary — the streaming kernel only counts them) and leave the
 // chunk group by group: consecutive threads write consecutive words.  The padding words of
 // segment s are seg_pad[s] = 0xFF000000 | (a cell slot the kernel keeps at "x_j = 0").
+// E16: the EXPERIMENTAL V16 layout (PRB_V16=1) — rows of 64 entries, an entry is the low
+// 16 bits of the word (the cell id inside its super-tile), runs padded to 64 entries.
 constexpr int VS_U = 8, VS_CHUNK = VL_THREADS * VS_U;
 
+template <bool E16>
 __global__ void __launch_bounds__(VL_THREADS)
 k_vscatter(const uint32_t *__restrict__ packed, const int64_t *__restrict__ indptr, int64_t P,
            const uint32_t *__restrict__ cellmap, const uint16_t *__restrict__ seg16, int n_seg,
@@ -405,9 +429,10 @@ k_vscatter(const uint32_t *__restrict__ packed, const int64_t *__restrict__ indp
         const int64_t g = s_gene;
         if (g >= P) break;
         const int64_t b = indptr[g], e = indptr[g + 1];
+        constexpr int EPR_LOG = E16 ? 6 : 5, EPR = 1 << EPR_LOG;  // entries per 128-byte row
         for (int i = tid; i < nk; i += VL_THREADS) {
-            const int nr = (seglen[g * nk + i] + 31) >> 5;
-            next[i] = (int64_t)(run_end[g * nk + i] - nr) * 32;
+            const int nr = (seglen[g * nk + i] + EPR - 1) >> EPR_LOG;
+            next[i] = (int64_t)(run_end[g * nk + i] - nr) * EPR;
             ccnt[i] = 0;
         }
         __syncthreads();
@@ -466,7 +491,10 @@ k_vscatter(const uint32_t *__restrict__ packed, const int64_t *__restrict__ indp
             // C: out, group by group (consecutive slots of a key -> consecutive words)
             for (int p = tid; p < n_chunk; p += VL_THREADS) {
                 const int k = skey[p];
-                vpacked[next[k] + (p - cstart[k])] = stage[p];
+                if (E16)
+                    ((uint16_t *)vpacked)[next[k] + (p - cstart[k])] = (uint16_t)stage[p];
+                else
+                    vpacked[next[k] + (p - cstart[k])] = stage[p];
             }
             __syncthreads();
             for (int k = tid; k < nk; k += VL_THREADS) {
@@ -478,9 +506,14 @@ k_vscatter(const uint32_t *__restrict__ packed, const int64_t *__restrict__ indp
         // padding up to the end of the run's last row
         for (int i = tid; i < nk; i += VL_THREADS) {
             const int s = i % n_seg;
-            const int64_t end = (int64_t)run_end[g * nk + i] * 32;
+            const int64_t end = (int64_t)run_end[g * nk + i] * EPR;
             const uint32_t padw = seg_pad[s];
-            for (int64_t p = next[i]; p < end; ++p) vpacked[p] = padw;
+            for (int64_t p = next[i]; p < end; ++p) {
+                if (E16)
+                    ((uint16_t *)vpacked)[p] = (uint16_t)padw;
+                else
+                    vpacked[p] = padw;
+            }
         }
     }
 }
@@ -569,11 +602,11 @@ extern "C" int prb_v_count(const uint32_t *packed, const int64_t *indptr, int64_
     return 0;
 }
 
-extern "C" int prb_v_scatter(const uint32_t *packed, const int64_t *indptr, int64_t P,
-                             const uint32_t *cellmap, const uint16_t *seg16, int n_seg, int K1,
-                             const int32_t *seglen, const int32_t *run_end,
-                             const uint32_t *seg_pad, uint32_t *vpacked, int32_t *queue,
-                             prb_stream_t stream)
+template <bool E16>
+static int v_scatter_impl(const uint32_t *packed, const int64_t *indptr, int64_t P,
+                          const uint32_t *cellmap, const uint16_t *seg16, int n_seg, int K1,
+                          const int32_t *seglen, const int32_t *run_end, const uint32_t *seg_pad,
+                          uint32_t *vpacked, int32_t *queue, prb_stream_t stream)
 {
     if (P == 0) return 0;
     PRB_REQUIRE(K1 >= 1 && K1 <= 4 && n_seg >= 1, "bad arguments");
@@ -583,23 +616,45 @@ extern "C" int prb_v_scatter(const uint32_t *packed, const int64_t *indptr, int6
     const size_t nk = (size_t)K1 * n_seg;
     const size_t smem = nk * 16 + (size_t)VS_CHUNK * 6;
     PRB_REQUIRE((int64_t)smem <= devinfo().smem_optin - 1024, "too many segments");
-    PRB_CUDA(cudaFuncSetAttribute(k_vscatter, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    PRB_CUDA(cudaFuncSetAttribute(k_vscatter<E16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
     PRB_CUDA(cudaMemsetAsync(queue, 0, sizeof(int32_t), S(stream)));
     const int grid = (int)hmin(P, (int64_t)devinfo().sm_count * 8);
-    k_vscatter<<<grid, VL_THREADS, smem, S(stream)>>>(packed, indptr, P, cellmap, seg16, n_seg, K1,
-                                                      seglen, run_end, seg_pad, vpacked, queue);
+    k_vscatter<E16><<<grid, VL_THREADS, smem, S(stream)>>>(packed, indptr, P, cellmap, seg16, n_seg,
+                                                           K1, seglen, run_end, seg_pad, vpacked,
+                                                           queue);
     PRB_LAUNCH_CHECK("k_vscatter");
     return 0;
 }
 
-extern "C" int prb_stream_v(const uint32_t *vpacked, const int32_t *run_end,
-                            const int32_t *tile_row0, int n_seg, int64_t P, int K1,
-                            int64_t v_rows, const int32_t *st_seg0, const int32_t *seg_cell0,
-                            const int32_t *seg_class, int n_st, int64_t max_tile_cells,
-                            const uint8_t *sx, int C, int32_t *hits, int32_t *counters,
-                            const int32_t *item_off, const int32_t *item_row0,
-                            const int32_t *item_vg0, int64_t n_items, prb_stream_t stream)
+extern "C" int prb_v_scatter(const uint32_t *packed, const int64_t *indptr, int64_t P,
+                             const uint32_t *cellmap, const uint16_t *seg16, int n_seg, int K1,
+                             const int32_t *seglen, const int32_t *run_end,
+                             const uint32_t *seg_pad, uint32_t *vpacked, int32_t *queue,
+                             prb_stream_t stream)
+{
+    return v_scatter_impl<false>(packed, indptr, P, cellmap, seg16, n_seg, K1, seglen, run_end,
+                                 seg_pad, vpacked, queue, stream);
+}
+
+// EXPERIMENTAL (PRB_V16=1, staged for round 2): run_end counts rows of 64 entries.
+extern "C" int prb_v_scatter16(const uint32_t *packed, const int64_t *indptr, int64_t P,
+                               const uint32_t *cellmap, const uint16_t *seg16, int n_seg, int K1,
+                               const int32_t *seglen, const int32_t *run_end,
+                               const uint32_t *seg_pad, uint32_t *vpacked, int32_t *queue,
+                               prb_stream_t stream)
+{
+    return v_scatter_impl<true>(packed, indptr, P, cellmap, seg16, n_seg, K1, seglen, run_end,
+                                seg_pad, vpacked, queue, stream);
+}
+
+template <int EPW>
+static int stream_v_impl(const uint32_t *vpacked, const int32_t *run_end, const int32_t *tile_row0,
+                         int n_seg, int64_t P, int K1, int64_t v_rows, const int32_t *st_seg0,
+                         const int32_t *seg_cell0, const int32_t *seg_class, int n_st,
+                         int64_t max_tile_cells, const uint8_t *sx, int C, int32_t *hits,
+                         int32_t *counters, const int32_t *item_off, const int32_t *item_row0,
+                         const int32_t *item_vg0, int64_t n_items, prb_stream_t stream)
 {
     if (P == 0 || v_rows == 0) return 0;
     PRB_REQUIRE(K1 >= 1 && K1 <= 4, "the register-counter path needs K <= 5");
@@ -620,17 +675,46 @@ extern "C" int prb_stream_v(const uint32_t *vpacked, const int32_t *run_end,
     };
     switch (v_cfg()) {
         case 1:
-            if (launch(k_stream_v<VCfg1>, VCfg1::smem_bytes, VCfg1::warps)) return 1;
+            if (launch(k_stream_v<VCfg1, EPW>, VCfg1::smem_bytes, VCfg1::warps)) return 1;
             break;
         case 2:
-            if (launch(k_stream_v<VCfg2>, VCfg2::smem_bytes, VCfg2::warps)) return 1;
+            if (launch(k_stream_v<VCfg2, EPW>, VCfg2::smem_bytes, VCfg2::warps)) return 1;
             break;
         case 3:
-            if (launch(k_stream_v<VCfg3>, VCfg3::smem_bytes, VCfg3::warps)) return 1;
+            if (launch(k_stream_v<VCfg3, EPW>, VCfg3::smem_bytes, VCfg3::warps)) return 1;
             break;
         default:
-            if (launch(k_stream_v<VCfg0>, VCfg0::smem_bytes, VCfg0::warps)) return 1;
+            if (launch(k_stream_v<VCfg0, EPW>, VCfg0::smem_bytes, VCfg0::warps)) return 1;
     }
     PRB_LAUNCH_CHECK("k_stream_v");
     return 0;
+}
+
+extern "C" int prb_stream_v(const uint32_t *vpacked, const int32_t *run_end,
+                            const int32_t *tile_row0, int n_seg, int64_t P, int K1,
+                            int64_t v_rows, const int32_t *st_seg0, const int32_t *seg_cell0,
+                            const int32_t *seg_class, int n_st, int64_t max_tile_cells,
+                            const uint8_t *sx, int C, int32_t *hits, int32_t *counters,
+                            const int32_t *item_off, const int32_t *item_row0,
+                            const int32_t *item_vg0, int64_t n_items, prb_stream_t stream)
+{
+    return stream_v_impl<1>(vpacked, run_end, tile_row0, n_seg, P, K1, v_rows, st_seg0, seg_cell0,
+                            seg_class, n_st, max_tile_cells, sx, C, hits, counters, item_off,
+                            item_row0, item_vg0, n_items, stream);
+}
+
+// EXPERIMENTAL (PRB_V16=1, staged for round 2): the same pass over the V16 layout built by
+// prb_v_scatter16 (rows of 64 16-bit entries).
+extern "C" int prb_stream_v16(const uint32_t *vpacked, const int32_t *run_end,
+                              const int32_t *tile_row0, int n_seg, int64_t P, int K1,
+                              int64_t v_rows, const int32_t *st_seg0, const int32_t *seg_cell0,
+                              const int32_t *seg_class, int n_st, int64_t max_tile_cells,
+                              const uint8_t *sx, int C, int32_t *hits, int32_t *counters,
+                              const int32_t *item_off, const int32_t *item_row0,
+                              const int32_t *item_vg0, int64_t n_items, prb_stream_t stream)
+{
+    PRB_REQUIRE(v_span() == 65536, "16-bit entries need 64 K-cell tiles");
+    return stream_v_impl<2>(vpacked, run_end, tile_row0, n_seg, P, K1, v_rows, st_seg0, seg_cell0,
+                            seg_class, n_st, max_tile_cells, sx, C, hits, counters, item_off,
+                            item_row0, item_vg0, n_items, stream);
 }

@@ -88,6 +88,9 @@ class Engine:
         self._plans = {}
         self._tps = {}
         self.vmode = USE_VLAYOUT and self.K1 <= 4
+        # EXPERIMENTAL (staged for round 2, not yet run on hardware): the V layout with
+        # 16-bit entries, 64 per row (prb_v_scatter16 / prb_stream_v16)
+        self.v16 = self.vmode and os.environ.get("PRB_V16", "0") == "1"
         self.v = None  # V layout (csrc/vstream.cu), built lazily for the current labels
         self.newpos = None    # V path: int32[N] new position of every cell (None = identity)
         self.y_sorted = None  # V path: labels in the new order
@@ -250,7 +253,8 @@ class Engine:
         # rows of every run, scanned in storage order: (super-tile, virtual gene, segment)
         span = nat.load().prb_v_tile_span()
         cell0, st = pl["cell0"], pl["st"]
-        nr = (seglen.view(PV, n_seg) + 31) >> 5
+        epr_log = 6 if self.v16 else 5  # entries per 128-byte row: 64 (16-bit) or 32
+        nr = (seglen.view(PV, n_seg) + ((1 << epr_log) - 1)) >> epr_log
         run_end = torch.empty((PV, n_seg), dtype=torch.int32, device=dev)
         tile_row0, base = [0], 0
         pad = np.zeros(n_seg, dtype=np.int64)
@@ -267,7 +271,8 @@ class Engine:
         v_rows = base
         seg_pad = torch.from_numpy(pad.astype(np.uint32).view(np.int32)).to(dev)
         vpacked = torch.empty(v_rows * 32 + PACKED_PAD, dtype=torch.int32, device=dev)
-        nat.call("prb_v_scatter", nat.ptr(self.packed), nat.ptr(self.indptr), P, nat.ptr(cellmap),
+        nat.call("prb_v_scatter16" if self.v16 else "prb_v_scatter", nat.ptr(self.packed),
+                 nat.ptr(self.indptr), P, nat.ptr(cellmap),
                  nat.ptr(seg16), n_seg, K1, nat.ptr(seglen), nat.ptr(run_end),
                  nat.ptr(seg_pad), nat.ptr(vpacked), nat.ptr(self.counters), nat.stream())
         # work items: consecutive row ranges of every super-tile's block (size: the measured
@@ -335,7 +340,8 @@ class Engine:
     def _stream_v_launch(self, with_y, sx, C, hits):
         v = self._v()
         pl = v["plan"]
-        nat.call("prb_stream_v", nat.ptr(v["vpacked"]), nat.ptr(v["run_end"]),
+        nat.call("prb_stream_v16" if self.v16 else "prb_stream_v", nat.ptr(v["vpacked"]),
+                 nat.ptr(v["run_end"]),
                  nat.ptr(v["tile_row0"]), pl["n_seg"], self.P, self.K1, v["rows"],
                  nat.ptr(pl["st_seg0"]),
                  nat.ptr(pl["seg_cell0"]), nat.ptr(pl["seg_class"]) if with_y else None,

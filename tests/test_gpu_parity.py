@@ -5,6 +5,7 @@ Bar: bin codes, selected gene sequences bit-exact; entropies / scores compared w
 np.array_equal (bit-identical fp64) — the 1e-9 relative tolerance of the north star is
 the fallback documented in DESIGN.md, not what these tests accept."""
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -357,6 +358,35 @@ def test_class_sorted_cells_and_v_layout(pr, O, monkeypatch, tile_cells, vlayout
             assert np.array_equal(a.score, b.score), kind
     Xg = eng.to_scipy_csc()
     assert np.array_equal(Xg.indices, Xs.indices) and np.array_equal(Xg.data, Xs.data)
+
+
+@pytest.mark.parametrize("tile_cells", [None, 4096])
+def test_v16_layout_staged(pr, O, monkeypatch, tile_cells):
+    """EXPERIMENTAL V layout with 16-bit entries (PRB_V16=1: prb_v_scatter16 / prb_stream_v16),
+    staged in round 1 without a hardware run: opt in with PRB_TEST_V16=1.  Same checks as the
+    32-bit layout: entropies, scores and sequences bit-identical to the oracle."""
+    if os.environ.get("PRB_TEST_V16", "0") != "1":
+        pytest.skip("staged V16 layout: set PRB_TEST_V16=1")
+    from picturedrocks_b200.synth import DiscretisedSpec
+
+    monkeypatch.setenv("PRB_V16", "1")
+    if tile_cells:
+        monkeypatch.setenv("PRB_V_TILE_CELLS", str(tile_cells))
+    spec = DiscretisedSpec(N=70001, P=301, C=7, K=5, mean_density=0.09, seed=12)  # two 64 K tiles
+    eng, yd = spec.device_engine()
+    assert eng.v16
+    inf = pr.markers.SparseInformationSet._from_engine(eng, yd)
+    y = spec.cpu_labels()
+    ora = O.SparseInformationSet(spec.cpu_csc(range(spec.P), y), y)
+    for cols in ([], [-1], [5], [-1, 5], [200], [-1, 200]):
+        c = np.array(cols, dtype=np.int64)
+        assert np.array_equal(inf.entropy_wrt(c), ora.entropy_wrt(c)), cols
+    for kind in ("CIFE", "JMI", "CIFEUnsup"):
+        a, b = getattr(pr.markers, kind)(inf), getattr(O, kind)(ora)
+        a.autoselect(9)
+        b.autoselect(9)
+        assert a.S == [int(s) for s in b.S], kind
+        assert np.array_equal(a.score, b.score), kind
 
 
 @pytest.mark.parametrize("K", [2, 3, 4])
