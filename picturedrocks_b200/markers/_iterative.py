@@ -1,56 +1,70 @@
 """Selector base classes (reference: picturedrocks/markers/_iterative.py:22-83).
 
-`IterativeFeatureSelection` keeps the reference's contract — attributes
-`infoset`, `score` (float64 ndarray, -inf for selected features), `S` (list),
-methods `add(ind)`, `remove(ind)`, `autoselect(n_feats)`.  The generic
-`autoselect` below is the reference's host loop (np.argmax then add,
-_iterative.py:64-66); the device-resident selectors override it with a loop
-that never leaves the GPU.
+Contract shared by every selector of this package, identical to the reference's:
+
+* attributes `infoset`, `score` (float64 ndarray over the features; `-inf` marks a selected
+  feature) and `S` (Python list of selected feature indices, in selection order);
+* `add(ind)` / `remove(ind)` select / un-select one feature;
+* `autoselect(n_feats)` selects n_feats more features greedily: highest score first, the
+  lowest index among equal scores (np.argmax, _iterative.py:64-66).
+
+The greedy device-resident selectors (mutualinformation/iterative.py) override `autoselect`
+with a loop that never leaves the GPU; the univariate ones below keep their score vector on
+the host, because their whole selection is two numpy calls.
 """
 from abc import ABC, abstractmethod
 
 import numpy as np
 
+NEG_INF = -np.inf
+
 
 class IterativeFeatureSelection(ABC):
-    """Abstract greedy feature selector."""
+    """Abstract greedy feature selector over an information set."""
 
     @abstractmethod
     def __init__(self, infoset):
-        self.infoset = infoset
-        self.score = None
-        self.S = []
+        self.infoset, self.score, self.S = infoset, None, []
 
     @abstractmethod
     def add(self, ind):
-        """Select feature `ind`."""
+        """Select feature `ind` (an int index into the information set's features)."""
 
     @abstractmethod
     def remove(self, ind):
-        """Un-select feature `ind`."""
+        """Un-select feature `ind`; raises ValueError if it is not selected."""
 
     def autoselect(self, n_feats):
-        """Greedily select `n_feats` features: highest score first, lowest index on ties."""
-        for _ in range(n_feats):
+        """Host loop of the reference: n_feats times, take the arg-max of the current score
+        vector (first index on ties) and `add` it.  Returns None."""
+        remaining = int(n_feats)
+        while remaining > 0:
             self.add(int(np.argmax(self.score)))
+            remaining -= 1
 
 
 class UnivariateMixin:
-    """Selection without redundancy penalty (_iterative.py:69-83).  The score vector is
-    a host ndarray; tie order of the top-n is numpy's, obtained with the same two numpy
-    calls the reference makes."""
+    """Selection by a fixed per-feature score, no redundancy penalty (_iterative.py:69-83):
+    MIM and UniEntropy.  `score` / `base_score` are host ndarrays.  The order of the top-n —
+    including the order among exactly equal scores — is whatever numpy's `argpartition`
+    followed by `argsort` give, so the same two calls are made here."""
+
+    def _mark(self, which, value):
+        self.score[which] = value
 
     def add(self, ind):
         self.S.append(ind)
-        self.score[ind] = -np.inf
+        self._mark(ind, NEG_INF)
 
     def remove(self, ind):
         self.S.remove(ind)
-        self.score[ind] = self.base_score[ind]
+        self._mark(ind, self.base_score[ind])
 
     def autoselect(self, n_feats):
-        top = np.argpartition(self.score, -n_feats)[-n_feats:]
-        top = top[np.argsort(self.score[top])[::-1]]
-        self.S.extend(top)
-        self.score[top] = -np.inf
-        return top
+        """Select the n_feats best-scoring features at once; returns their indices, best
+        first (unlike the greedy selectors, which return None)."""
+        cut = np.argpartition(self.score, -n_feats)[-n_feats:]
+        ranked = cut[np.argsort(self.score[cut])[::-1]]
+        self.S.extend(ranked)
+        self._mark(ranked, NEG_INF)
+        return ranked
