@@ -49,7 +49,7 @@ static void jitter(std::mt19937 &rng)
 
 static bool timed_out(std::chrono::steady_clock::time_point t0)
 {
-    return std::chrono::steady_clock::now() - t0 > std::chrono::seconds(2);
+    return std::chrono::steady_clock::now() - t0 > std::chrono::seconds(6);
 }
 
 static void fail(const char *what, int rank, int step)
