@@ -40,6 +40,8 @@ WORKLOADS = {
     # generic shared-histogram kernel, k = 5 through the V layout
     "c5_k5": dict(N=1000000, P=20000, C=20, K=5, mean_density=0.05, seed=5,
                   name="sweep point 1e6 x 2e4, 20 clusters, 5 bins, 5% nnz"),
+    "c5_k10": dict(N=100000, P=50000, C=20, K=10, mean_density=0.05, seed=5,
+                   name="sweep point 1e5 x 5e4, 20 clusters, 10 bins, 5% nnz"),
     "c5_k20": dict(N=100000, P=50000, C=20, K=20, mean_density=0.05, seed=5,
                    name="sweep point 1e5 x 5e4, 20 clusters, 20 bins, 5% nnz"),
     # one eighth of the genes of c4: what each rank streams in the 8-GPU run (tuning aid)

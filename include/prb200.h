@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define PRB_ABI_VERSION 1
+#define PRB_ABI_VERSION 2
 #define PRB_MAX_ROWS (1 << 24) /* cell id field of the packed CSC word */
 #define PRB_MAX_CODES 256      /* K <= 256 */
 
@@ -113,11 +113,10 @@ int prb_stream_hits(const uint32_t *packed, const int64_t *tp, int64_t P, int64_
  *       vpacked   uint32[32 * rows]      words code<<24 | cell; the padding words of segment
  *                 s are seg_pad[s] = 0xFF000000 | ((first cell after the segment's
  *                 super-tile) mod tile span): a slot the kernel keeps at "x_j = 0"
- *  4. prb_state_v: per-cell shift code of the selected gene, sx uint8[N] (+16 bytes of
- *     padding) = 8*(x_j-1), 64 where x_j = 0, plus the same hsize / hs_begin / hs_y /
- *     hs_ysum / ha tables as prb_state_direct (derived by the last block to finish;
- *     ticket: device int32, zero on entry and on exit).  x_j is read and RESET to zero,
- *     so the next prb_scatter_gene_u8 needs no memset.
+ *  4. prb_pick_scatter (below) writes the per-cell shift code of the selected gene,
+ *     sx uint8[N] (+16 bytes of padding) = 8*(x_j-1), 64 where x_j = 0 — sx is all 64
+ *     between steps —, and the hsize / hs_ysum / ha tables (taken from the count table of
+ *     the selected gene).
  *  5. prb_stream_v adds the joint counts to hits int32[P][C][K-1][K-1]
  *     (bin = (x_j-1)*(K-1) + x_g-1).  Work items are consecutive row ranges of a
  *     super-tile's block (large first, small last): item_off int32[n_st+1] = first item id
@@ -126,7 +125,8 @@ int prb_stream_hits(const uint32_t *packed, const int64_t *tp, int64_t P, int64_
  *     entry item_off[t] + t + k; item_vg0 int32[n_items] = first virtual gene with a run
  *     ending past the item's first row (a searchsorted of run_end, by the caller;
  *     prb_v_warps() = warps of one launch, to size the items).
- *     counters: int32[n_st] scratch (reset by the call); queue: device int32 scratch. */
+ *     counters: int32[n_st] scratch (reset by the call unless counters_clean says the caller
+ *     already did — prb_pick_scatter does); queue: device int32 scratch. */
 int prb_v_tile_capacity(int64_t *max_cells, int *max_segs);
 int prb_v_count(const uint32_t *packed, const int64_t *indptr, int64_t P,
                 const uint32_t *cellmap, const uint16_t *seg16, int n_seg, int K1,
@@ -148,30 +148,32 @@ int prb_stream_v16(const uint32_t *vpacked, const int32_t *run_end, const int32_
                    const int32_t *seg_cell0, const int32_t *seg_class, int n_st,
                    int64_t max_tile_cells, const uint8_t *sx, int C, int32_t *hits,
                    int32_t *counters, const int32_t *item_off, const int32_t *item_row0,
-                   const int32_t *item_vg0, int64_t n_items, prb_stream_t stream);
-int prb_state_v(uint8_t *xj, const int32_t *y, int64_t N, int C, int K, uint8_t *sx,
-                int32_t *hsize, int32_t *hs_begin, int32_t *hs_y, int32_t *hs_ysum, int32_t *ha,
-                int32_t *ticket, prb_stream_t stream);
+                   const int32_t *item_vg0, int64_t n_items, int counters_clean,
+                   prb_stream_t stream);
 int prb_stream_v(const uint32_t *vpacked, const int32_t *run_end, const int32_t *tile_row0,
                  int n_seg, int64_t P, int K1, int64_t v_rows, const int32_t *st_seg0,
                  const int32_t *seg_cell0, const int32_t *seg_class, int n_st,
                  int64_t max_tile_cells, const uint8_t *sx, int C, int32_t *hits,
                  int32_t *counters, const int32_t *item_off, const int32_t *item_row0,
-                 const int32_t *item_vg0, int64_t n_items, prb_stream_t stream);
+                 const int32_t *item_vg0, int64_t n_items, int counters_clean,
+                 prb_stream_t stream);
 int prb_v_warps(void);
 /* cells per super-tile modulus (power of two) of the active kernel configuration */
 int prb_v_tile_span(void);
 
 /* ---- joint-state build ("master column", _sparse_make_master_col INFOSET:431-442) */
-/* dense uint8 x_j[N] (zeroed by caller) <- codes of gene *gene_ptr (device int32;
- * genes outside [gene_lo, gene_lo+P) are ignored: multi-GPU owner test), written at
- * newpos[cell] (NULL = at cell). */
-int prb_scatter_gene_u8(const uint32_t *packed, const int64_t *indptr, const int32_t *gene_ptr,
-                        int32_t gene_lo, int64_t P, const int32_t *newpos, uint8_t *xj,
+/* Columns are addressed through col_begin / col_end int64[P]: first / past-the-last word of
+ * every gene in `packed` (indptr[:-1] / indptr[1:] of a contiguous CSC; multi-GPU: the slots
+ * of the replicated copy of all ranks' shards, gene ids global).
+ * dense uint8 x_j[N] (zeroed by caller) <- codes of gene *gene_ptr (device int32), written
+ * at newpos[cell] (NULL = at cell). */
+int prb_scatter_gene_u8(const uint32_t *packed, const int64_t *col_begin, const int64_t *col_end,
+                        const int32_t *gene_ptr, int64_t P, const int32_t *newpos, uint8_t *xj,
                         prb_stream_t stream);
 /* mpacked[row] |= code << shift_bits for every stored entry of gene `gene`. */
-int prb_scatter_gene_or32(const uint32_t *packed, const int64_t *indptr, int64_t gene,
-                          int shift_bits, uint32_t *mpacked, prb_stream_t stream);
+int prb_scatter_gene_or32(const uint32_t *packed, const int64_t *col_begin,
+                          const int64_t *col_end, int64_t gene, int shift_bits, uint32_t *mpacked,
+                          prb_stream_t stream);
 /* direct single-column state: state = 1 + (x_j-1)*C + y for x_j > 0 (y = 0 without
  * labels).  Writes state[N] (state_bytes 1|2), hsize int32[C*(K-1)] indexed
  * y*(K-1)+x_j-1 (zeroed here), hs_begin int32[C+1], hs_y int32[C*(K-1)],
@@ -255,6 +257,48 @@ int prb_argmax_commit(const double *cand_score, const int64_t *cand_idx, int64_t
 int prb_commit_add(const int64_t *best_idx, int32_t *gene_ptr, int32_t *S, int32_t *n_sel_ptr,
                    uint8_t *selected, int32_t gene_lo, int64_t P, prb_stream_t stream);
 
+/* ---- the greedy step on the V-layout path in three launches (csrc/step.cu, finalize.cu) ----
+ * prb_pick_scatter -> prb_stream_v[16] (counters_clean = 1) -> prb_finalize_update.
+ *
+ * prb_pick_scatter: np.argmax + add()'s bookkeeping (BASE:64-66, ITER:48-49) and the master
+ * column of the winner (INFOSET:289, 431-442).  records double[n_rec][2] = (score, index as
+ * int64 bits) candidates, one per rank (all-gathered) or this rank's own; reduced by every
+ * block with np.argmax's rule.  n_rec = 0: the gene already in *gene_ptr (add(ind) /
+ * remove(ind) / entropy_wrt([j]) — nothing is committed).  Commit: *gene_ptr <- j,
+ * S[(*n_sel_ptr)++] <- j, selected[j - gene_lo] <- 1 when local.  cnt_all int32[P_total][C][K-1]
+ * (count table of ALL genes) gives hsize[y][a] = cnt_all[j][y][a], hs_ysum[y], ha[a].
+ * counters[n_counters] <- 0.  Column j (col_packed / col_begin / col_end, global gene ids)
+ * is scattered into sx (all 64 on entry) at newpos[cell]. */
+int prb_pick_scatter(const double *records, int n_rec, int32_t *gene_ptr, int32_t *S,
+                     int32_t *n_sel_ptr, uint8_t *selected, int32_t gene_lo, int64_t P_local,
+                     const uint32_t *col_packed, const int64_t *col_begin, const int64_t *col_end,
+                     const int32_t *newpos, uint8_t *sx, const int32_t *cnt_all, int C, int K,
+                     int32_t *hsize, int32_t *hs_ysum, int32_t *ha, int32_t *counters,
+                     int n_counters, prb_stream_t stream);
+/* prb_finalize_direct + prb_selector_update + the reduction of the block candidates to ONE
+ * record best double[2] = (score, index bits) of this rank (done by the last block; ticket:
+ * device int32, zero on entry and exit; cand_score / cand_idx: scratch of
+ * prb_finalize_update_blocks(P, C) entries) + the reset of column *gene_ptr of sx to 64.
+ * Supervised kinds use H(y,x_j,x_g) and H(x_j,x_g); PRB_SEL_CIFE_UNSUP (C = 1) H(x_j,x_g). */
+int64_t prb_finalize_update_blocks(int64_t P, int C);
+int prb_finalize_update(int32_t *hits, const int32_t *cnt, const int64_t *classsizes,
+                        const int32_t *hsize, const int32_t *hs_ysum, const int32_t *ha, int C,
+                        int K, const double *table, int64_t N, int64_t P, int kind, int is_remove,
+                        const double *base, double *penalty, double *score,
+                        const uint8_t *selected, const double *Hx_all, const double *Hyx_all,
+                        const int32_t *gene_ptr, const int32_t *n_sel_ptr, int32_t gene_lo,
+                        double *cand_score, int64_t *cand_idx, double *best, int32_t *ticket,
+                        const uint32_t *col_packed, const int64_t *col_begin,
+                        const int64_t *col_end, const int32_t *newpos, uint8_t *sx,
+                        prb_stream_t stream);
+/* sx <- 64 at the stored entries of gene *gene_ptr (after a stand-alone streaming pass). */
+int prb_v_unscatter(const int32_t *gene_ptr, const uint32_t *col_packed, const int64_t *col_begin,
+                    const int64_t *col_end, const int32_t *newpos, uint8_t *sx,
+                    prb_stream_t stream);
+/* block candidates of prb_argmax_blocks -> best double[2] (score, index bits). */
+int prb_best_record(const double *cand_score, const int64_t *cand_idx, int64_t n_cand,
+                    double *best, prb_stream_t stream);
+
 /* ---- discretiser (quantile_discretize, INFOSET:50-83) ---------------------
  * dtype: 0 = float32, 1 = float64, 2 = int64 (edges float64 for int64 input).
  * Pipeline: row-major X[N][P] --transpose--> Xt[P][N] --sort_columns--> Xs[P][N]
@@ -333,29 +377,6 @@ int prb_sparse_entropy_wrt_host(const int32_t *dindices, const int64_t *dindptr,
  * entropy.  Bit-identical to the reference (same bins, same ascending order). */
 int prb_sparse_entropy_host(const int64_t *data, int64_t nnz, int64_t n_rows, int64_t max_val,
                             double *out);
-
-/* ---- Per-step exchange over NVLink peer memory (EXPERIMENTAL, csrc/peer.cu) -------------
- * Replaces the two NCCL collectives of a gene-sharded greedy step (the reference has no
- * multi-process mode; this is the SURVEY 8e exchange).  Every rank owns a SYMMETRIC buffer
- * of prb_peer_layout().bytes bytes, zero-filled, and the device array peers[W] of all
- * ranks' buffer addresses (rank order).  Per step, on every rank, in this order:
- *   prb_peer_gather16  local argmax of the block candidates, 16-byte (score, index) record
- *                      pushed to every peer, wait for all W records -> out double[W][2]
- *                      (index as int64 bits); *seq (device uint32, 0 at start) += 1
- *   prb_argmax_commit  on out (n_cand = W, stride = 2), as with the NCCL all-gather
- *   prb_peer_clean     zero this rank's x_j area (mine + off_col) if *dirty
- *   prb_scatter_gene_u8  into mine + off_col (a no-op on ranks that do not own the gene)
- *   prb_peer_column    owner: publish; others: wait and pull the owner's x_j area;
- *                      all: -> xj_local uint8[n_pad]; *dirty = (this rank is the owner)
- * shard_lo int32[W+1]: first gene of every rank (last = P_total). */
-int prb_peer_layout(int64_t N, int W, int64_t *bytes, int64_t *off_col, int64_t *n_pad);
-int prb_peer_gather16(const double *cand_score, const int64_t *cand_idx, int64_t n_cand,
-                      const uint64_t *peers, int rank, int W, int64_t N, uint32_t *seq,
-                      double *out, prb_stream_t stream);
-int prb_peer_clean(void *mine, int64_t N, int W, const int32_t *dirty, prb_stream_t stream);
-int prb_peer_column(const uint64_t *peers, int rank, int W, int64_t N, const int32_t *gene_ptr,
-                    const int32_t *shard_lo, const uint32_t *seq, uint8_t *xj_local,
-                    int32_t *dirty, prb_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -33,8 +33,8 @@ _f64p = ctypes.POINTER(ctypes.c_double)
 def build(force=False):
     """Compile oracle.c → liboracle.so (gcc).  Building the checker is not using it."""
     so = os.path.join(_HERE, "liboracle.so")
-    src = os.path.join(_HERE, "oracle.c")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("oracle.c", "synth_cpu.c")]
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(map(os.path.getmtime, srcs)):
         subprocess.run(["make", "-C", _HERE, "-B", "liboracle.so"], check=True,
                        stdout=subprocess.DEVNULL)
     return so
@@ -51,6 +51,14 @@ def lib():
 
 def max_threads():
     return int(lib().orc_max_threads())
+
+
+def host_cores():
+    """Cores this process may run on (ignores OMP_NUM_THREADS, which torchrun sets to 1)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 def _p(a, t):
@@ -249,6 +257,65 @@ class SparseInformationSet:
         return sparse_entropy_wrt(self.X.indices, self.X.indptr, self.X.data, mi, md, self.N,
                                   self.P, len(cols), self._shift, ybits, y, cs,
                                   nthreads=self._nthreads, feat_range=feat_range)
+
+
+class _FlatCSC:
+    """The members of scipy's csc_matrix the oracle touches, over caller-owned flat arrays
+    (no index widening, no int64 copy of the codes)."""
+
+    def __init__(self, indptr, indices, data, shape):
+        self.indptr, self.indices, self.data, self.shape = indptr, indices, data, tuple(shape)
+
+    def max(self):
+        return int(self.data.max())
+
+    def getcol(self, j):
+        b, e = int(self.indptr[j]), int(self.indptr[j + 1])
+        return _FlatCSC(np.array([0, e - b]), self.indices[b:e], self.data[b:e], (self.shape[0], 1))
+
+
+class FlatSparseInformationSet(SparseInformationSet):
+    """INFOSET:176-303 over flat canonical CSC arrays (indptr int64[P+1], row ids int32[nnz]
+    ascending inside a column, codes uint8[nnz], all non-zero).  For matrices with more than
+    2^31 stored entries: scipy would widen the row ids to int64 and the reference keeps int64
+    data (42 GB at BASELINE config 4); the algorithm and the C kernels are the same."""
+
+    def __init__(self, indptr, indices, data, n_rows, y=None, nthreads=1):
+        indptr = _c(indptr, np.int64)
+        indices = _c(indices, np.int32)
+        data = _c(data, np.uint8)
+        assert indptr[0] == 0 and indptr[-1] == indices.size == data.size
+        self.X = _FlatCSC(indptr, indices, data, (int(n_rows), indptr.size - 1))
+        self.N, self.P = self.X.shape
+        self._shift = _bit_length_like_ref(self.X.max())
+        self._nthreads = nthreads
+        self.set_y(y)
+
+
+def synth_csc(spec, gene_lo=0, gene_hi=None, nthreads=None):
+    """Genes [gene_lo, gene_hi) of a picturedrocks_b200.synth.DiscretisedSpec through
+    synth_cpu.c: (indptr int64, row ids int32, codes uint8, labels int64)."""
+    L = lib()
+    nthreads = host_cores() if nthreads is None else int(nthreads)
+    gene_hi = spec.P if gene_hi is None else int(gene_hi)
+    P = gene_hi - int(gene_lo)
+    y = np.empty(spec.N, dtype=np.int64)
+    seed = ctypes.c_uint64(spec.seed & ((1 << 64) - 1))
+    L.orc_synth_labels(_p(y, _i64p), ctypes.c_int64(spec.N), ctypes.c_int64(spec.C), seed)
+    cum = np.ascontiguousarray(spec.cum_table(), dtype=np.uint32)
+    u32p = ctypes.POINTER(ctypes.c_uint32)
+    args = (_p(y, _i64p), ctypes.c_int64(spec.N), ctypes.c_int64(gene_lo), ctypes.c_int64(P),
+            ctypes.c_int64(spec.C), ctypes.c_int64(spec.K), ctypes.c_uint32(spec.mean_q24), seed,
+            _p(cum, u32p))
+    counts = np.zeros(P, dtype=np.int64)
+    assert L.orc_synth_count(*args, _p(counts, _i64p), ctypes.c_int(nthreads)) == 0
+    indptr = np.zeros(P + 1, dtype=np.int64)
+    np.cumsum(counts, out=indptr[1:])
+    rows = np.empty(int(indptr[-1]), dtype=np.int32)
+    codes = np.empty(int(indptr[-1]), dtype=np.uint8)
+    assert L.orc_synth_fill(*args, _p(indptr, _i64p), _p(rows, _i32p), _p(codes, _u8p),
+                            ctypes.c_int(nthreads)) == 0
+    return indptr, rows, codes, y
 
 
 def makeinfoset(adata, include_y, k=5, nthreads=1):

@@ -33,19 +33,26 @@ _SIGS = {
                         ctypes.POINTER(_int), ctypes.POINTER(_int), ctypes.POINTER(_i64)],
     "prb_tile_ptrs": [_vp, _vp, _i64, _i64, _int, _vp, _vp],
     "prb_stream_hits": [_vp, _vp, _i64, _i64, _vp, _i64, _i64, _int, _int, _vp, _vp, _vp],
-    "prb_state_v": [_vp, _vp, _i64, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "prb_v_tile_capacity": [ctypes.POINTER(_i64), ctypes.POINTER(_int)],
     "prb_v_count": [_vp, _vp, _i64, _vp, _vp, _int, _int, _vp, _vp, _vp],
     "prb_v_scatter": [_vp, _vp, _i64, _vp, _vp, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp],
     "prb_v_scatter16": [_vp, _vp, _i64, _vp, _vp, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp],
     "prb_v_tile_span": [],
     "prb_stream_v": [_vp, _vp, _vp, _int, _i64, _int, _i64, _vp, _vp, _vp, _int, _i64, _vp, _int,
-                     _vp, _vp, _vp, _vp, _vp, _i64, _vp],
+                     _vp, _vp, _vp, _vp, _vp, _i64, _int, _vp],
     "prb_stream_v16": [_vp, _vp, _vp, _int, _i64, _int, _i64, _vp, _vp, _vp, _int, _i64, _vp, _int,
-                       _vp, _vp, _vp, _vp, _vp, _i64, _vp],
+                       _vp, _vp, _vp, _vp, _vp, _i64, _int, _vp],
     "prb_v_warps": [],
-    "prb_scatter_gene_u8": [_vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp],
-    "prb_scatter_gene_or32": [_vp, _vp, _i64, _int, _vp, _vp],
+    "prb_scatter_gene_u8": [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
+    "prb_scatter_gene_or32": [_vp, _vp, _vp, _i64, _int, _vp, _vp],
+    "prb_pick_scatter": [_vp, _int, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
+                         _int, _int, _vp, _vp, _vp, _vp, _int, _vp],
+    "prb_finalize_update_blocks": [_i64, _int],
+    "prb_finalize_update": [_vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _vp, _i64, _i64, _int, _int,
+                            _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp,
+                            _vp, _vp, _vp, _vp, _vp, _vp],
+    "prb_v_unscatter": [_vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "prb_best_record": [_vp, _vp, _i64, _vp, _vp],
     "prb_state_direct": [_vp, _vp, _i64, _int, _int, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp],
     "prb_state_table": [_vp, _vp, _i64, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
     "prb_state_assign": [_vp, _vp, _i64, _int, _vp, _vp, _int, _vp],
@@ -74,16 +81,11 @@ _SIGS = {
     "prb_synth_labels": [_vp, _i64, _int, _u64, _vp],
     "prb_synth_count": [_vp, _i64, _i64, _i64, _int, _int, _u32, _u64, _vp, _vp, _vp],
     "prb_synth_fill": [_vp, _i64, _i64, _i64, _int, _int, _u32, _u64, _vp, _vp, _vp, _vp],
-    "prb_peer_layout": [_i64, _int, ctypes.POINTER(_i64), ctypes.POINTER(_i64),
-                        ctypes.POINTER(_i64)],
-    "prb_peer_gather16": [_vp, _vp, _i64, _vp, _int, _int, _i64, _vp, _vp, _vp],
-    "prb_peer_clean": [_vp, _i64, _int, _vp, _vp],
-    "prb_peer_column": [_vp, _int, _int, _i64, _vp, _vp, _vp, _vp, _vp, _vp],
     "prb_sparse_entropy_wrt_host": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64,
                                     _vp, _vp, _i64, _vp],
     "prb_sparse_entropy_host": [_vp, _i64, _i64, _i64, _vp],
 }
-_RESTYPES = {"prb_last_error": ctypes.c_char_p}
+_RESTYPES = {"prb_last_error": ctypes.c_char_p, "prb_finalize_update_blocks": _i64}
 
 EXPORTED = tuple(_SIGS)
 
@@ -111,7 +113,7 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = _RESTYPES.get(name, _int)
-    if lib.prb_abi_version() != 1:
+    if lib.prb_abi_version() != 2:
         raise ImportError("libprb200.so ABI version mismatch")
     _LIB = lib
     return lib
@@ -125,14 +127,15 @@ class PrbError(RuntimeError):
 KERNELS = {
     "prb_pack_csc": 1, "prb_unpack_csc": 1, "prb_dense_count_nnz": 1, "prb_dense_fill_csc": 1,
     "prb_tile_ptrs": 1, "prb_stream_hits": 1,
-    "prb_state_v": 1, "prb_argmax_commit": 1, "prb_v_count": 1, "prb_v_scatter": 1,
+    "prb_argmax_commit": 1, "prb_pick_scatter": 1, "prb_finalize_update": 1,
+    "prb_v_unscatter": 1, "prb_best_record": 1, "prb_v_count": 1, "prb_v_scatter": 1,
     "prb_stream_v": 1, "prb_scatter_gene_u8": 1,
     "prb_scatter_gene_or32": 1, "prb_state_direct": 2, "prb_state_table": 2, "prb_state_assign": 1, "prb_finalize": 1, "prb_finalize_direct": 1,
     "prb_entropy_keys": 2, "prb_mi_base": 1, "prb_selector_update": 1, "prb_argmax_blocks": 1,
     "prb_argmax_final": 1, "prb_commit_add": 1, "prb_transpose": 1, "prb_sort_columns": 1,
     "prb_qd_edges": 1, "prb_qd_digitize": 1, "prb_sort_segments": 1, "prb_qd_edges_sparse": 1,
     "prb_qd_count_sparse": 1, "prb_qd_fill_sparse": 1, "prb_synth_labels": 1, "prb_synth_count": 1,
-    "prb_synth_fill": 1, "prb_peer_gather16": 1, "prb_peer_clean": 1, "prb_peer_column": 1,
+    "prb_synth_fill": 1,
     "prb_v_scatter16": 1, "prb_stream_v16": 1,
 }
 LAUNCHES = 0

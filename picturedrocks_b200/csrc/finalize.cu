@@ -17,7 +17,7 @@
 //   (y, 0,   0)   = classsize[y] - Σ hsize(states of y) - Σ_v (y,0,v)
 #include <stdlib.h>
 
-#include "common.cuh"
+#include "select.cuh"
 
 namespace prb {
 
@@ -349,14 +349,39 @@ k_finalize_direct(int32_t *__restrict__ hits, int64_t hits_stride,
 // so the sequence of fp64 roundings is exactly the reference's (y, x_j, x_i) bin order.
 // Classes past C contribute +0.0 terms (exact no-ops).
 // ---------------------------------------------------------------------------
-template <int TK1, int L>
+// SEL: the greedy step's tail fused in (prb_finalize_update) — the selector update of
+// ITER:48-59 / 76-87 / 112-121 for the gene just finished (score algebra of select.cuh), the
+// block's argmax candidate, the reduction of all candidates to ONE (score, index) record by
+// the last block to finish (np.argmax of BASE:65 over this rank's genes), and the reset of
+// the selected gene's entries of sx to "x_j = 0" (the streaming pass is over), so the next
+// step's scatter starts from a clean vector.  Entropies are not written out then.
+struct SelFuse {
+    int kind, is_remove;
+    const double *base;
+    double *penalty, *score;
+    const uint8_t *selected;
+    const double *Hx_all, *Hyx_all;
+    const int32_t *gene_ptr, *n_sel_ptr;
+    int32_t gene_lo;
+    double *cand_score;   // [gridDim.x] scratch
+    int64_t *cand_idx;    // [gridDim.x] scratch
+    double *best;         // [2]: score, index (int64 bits)
+    int *ticket;          // zero on entry and on exit
+    // column of the selected gene (packed CSC holding every gene: gene ids are global)
+    const uint32_t *col_packed;
+    const int64_t *col_begin, *col_end;
+    const int32_t *newpos;
+    uint8_t *sx;
+};
+
+template <int TK1, int L, bool SEL>
 __global__ void __launch_bounds__(256)
 k_finalize_direct_grp(int32_t *__restrict__ hits, int64_t hits_stride,
                       const int32_t *__restrict__ cnt, const int64_t *__restrict__ clsz,
                       const int32_t *__restrict__ hsize, const int32_t *__restrict__ hs_ysum,
                       const int32_t *__restrict__ ha, int C, const double *__restrict__ term,
                       int64_t N, int64_t P, double *__restrict__ out_full,
-                      double *__restrict__ out_marg)
+                      double *__restrict__ out_marg, int want_marg, SelFuse sel)
 {
     constexpr int TK = TK1, KK = TK1 * TK1, NT = 1 + TK + TK * (TK + 1);
     const int lane = threadIdx.x & 31;
@@ -365,7 +390,17 @@ k_finalize_direct_grp(int32_t *__restrict__ hits, int64_t hits_stride,
     const int64_t g_raw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / L;
     const bool active = g_raw < P;
     const int64_t g = active ? g_raw : P - 1;  // keep whole warps alive for the shuffles
-    const bool marg = out_marg != nullptr;
+    const bool marg = want_marg != 0;
+    if constexpr (SEL) {
+        // the streaming pass has consumed sx: hand it back all "x_j = 0"
+        const int64_t j = *sel.gene_ptr;
+        const int64_t cb = sel.col_begin[j], ce = sel.col_end[j];
+        const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+        for (int64_t i = cb + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < ce; i += stride) {
+            const uint32_t cell = __ldg(sel.col_packed + i) & ROW_MASK;
+            sel.sx[sel.newpos ? (uint32_t)sel.newpos[cell] : cell] = (uint8_t)PRB_SX_NONE;
+        }
+    }
     const int32_t *crow = cnt + g * (int64_t)C * TK;
     int32_t *hrow = hits ? hits + g * hits_stride : nullptr;
     auto T = [&](int c) -> double { return c ? __ldg(term + c) : 0.0; };
@@ -453,7 +488,8 @@ k_finalize_direct_grp(int32_t *__restrict__ hits, int64_t hits_stride,
             h = __shfl_sync(0xffffffffu, hh, grp0 + l2);
         }
     }
-    if (active && sub == 0) out_full[g] = h;
+    if (!SEL && active && sub == 0) out_full[g] = h;
+    double h2_out = 0.0;
     if (marg) {
         // class sums of the group -> every lane
 #pragma unroll
@@ -490,7 +526,53 @@ k_finalize_direct_grp(int32_t *__restrict__ hits, int64_t hits_stride,
 #pragma unroll
                 for (int v = 0; v < TK; ++v) h2 = __dadd_rn(h2, T(m2[a * TK + v]));
             }
-            out_marg[g] = h2;
+            if (SEL)
+                h2_out = h2;
+            else
+                out_marg[g] = h2;
+        }
+    }
+    if constexpr (SEL) {
+        // supervised: h = H(y, x_j, x_g), h2 = H(x_j, x_g); unsupervised: h = H(x_j, x_g)
+        double sc = 0.0;
+        int64_t idx = -1;
+        if (active && sub == 0) {
+            const int j = *sel.gene_ptr;
+            const bool unsup = sel.kind == PRB_SEL_CIFE_UNSUP;
+            double pen = sel.penalty[g];
+            sc = sel_update(sel.kind, sel.is_remove, sel.base[g], sel.Hx_all[j], unsup ? h : h2_out,
+                            unsup ? 0.0 : sel.Hyx_all[j], unsup ? 0.0 : h, &pen, sel.score[g],
+                            *sel.n_sel_ptr, sel.selected[g] != 0);
+            sel.penalty[g] = pen;
+            sel.score[g] = sc;
+            idx = sel.gene_lo + g;
+        }
+        block_argmax<256>(sc, idx);
+        __shared__ int s_last;
+        if (threadIdx.x == 0) {
+            sel.cand_score[blockIdx.x] = sc;
+            sel.cand_idx[blockIdx.x] = idx;
+            __threadfence();
+            s_last = atomicAdd(sel.ticket, 1) == (int)gridDim.x - 1;
+        }
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        sc = 0.0;
+        idx = -1;
+        for (int c = threadIdx.x; c < (int)gridDim.x; c += 256) {
+            const double s2 = __ldcg(sel.cand_score + c);
+            const int64_t i2 = __ldcg((const long long *)sel.cand_idx + c);
+            if (i2 >= 0 && (idx < 0 || better(s2, i2, sc, idx))) {
+                sc = s2;
+                idx = i2;
+            }
+        }
+        block_argmax<256>(sc, idx);
+        if (threadIdx.x == 0) {
+            sel.best[0] = sc;
+            ((int64_t *)sel.best)[1] = idx;
+            *sel.ticket = 0;
         }
     }
 }
@@ -528,6 +610,20 @@ extern "C" int prb_finalize(int32_t *hits, const int32_t *cnt, const int64_t *cl
 }
 
 
+// lanes per gene of k_finalize_direct_grp: 8 when there are enough genes to fill the GPU, more
+// for small gene counts (a multi-GPU shard), where the kernel is bound by the per-gene chain
+static int grp_lanes(int64_t P, int C)
+{
+    static const int forced = [] {
+        const char *e = getenv("PRB_FINALIZE_L");
+        return e ? atoi(e) : 0;
+    }();
+    int L = P * 8 >= (int64_t)devinfo().sm_count * 256 * 3 ? 8 : 16;
+    if (forced == 8 || forced == 16 || forced == 32) L = forced;
+    if (C <= 8) L = 8;
+    return L;
+}
+
 template <int TK1>
 static int launch_direct(int32_t *hits, int64_t stride, const int32_t *cnt, const int64_t *clsz,
                          const int32_t *hsize, const int32_t *hs_ysum, const int32_t *ha, int C,
@@ -535,19 +631,13 @@ static int launch_direct(int32_t *hits, int64_t stride, const int32_t *cnt, cons
                          double *out_marg, cudaStream_t st)
 {
     if constexpr (TK1 > 0) {
-        // lanes per gene: 8 when there are enough genes to fill the GPU, more for small
-        // gene counts (a multi-GPU shard), where the kernel is bound by the per-gene chain
-        static const int forced = [] {
-            const char *e = getenv("PRB_FINALIZE_L");
-            return e ? atoi(e) : 0;
-        }();
         const int threads = 256;
-        int L = P * 8 >= (int64_t)devinfo().sm_count * threads * 3 ? 8 : 16;
-        if (forced == 8 || forced == 16 || forced == 32) L = forced;
-        if (C <= 8) L = 8;
-#define PRB_FG(LL)                                                                            \
-    k_finalize_direct_grp<TK1, LL><<<(unsigned)ceil_div(P * LL, threads), threads, 0, st>>>(  \
-        hits, stride, cnt, clsz, hsize, hs_ysum, ha, C, table, N, P, out_full, out_marg)
+        const int L = grp_lanes(P, C);
+        const int wm = out_marg != nullptr;
+#define PRB_FG(LL)                                                                                   \
+    k_finalize_direct_grp<TK1, LL, false><<<(unsigned)ceil_div(P * LL, threads), threads, 0, st>>>(  \
+        hits, stride, cnt, clsz, hsize, hs_ysum, ha, C, table, N, P, out_full, out_marg, wm,         \
+        SelFuse{})
         if (L == 32)
             PRB_FG(32);
         else if (L == 16)
@@ -596,4 +686,72 @@ extern "C" int prb_finalize_direct(int32_t *hits, const int32_t *cnt, const int6
         default: PRB_FD(0);
     }
 #undef PRB_FD
+}
+
+
+// ---- the greedy step's tail in one launch (V-layout path, K <= 5) ---------------------------
+extern "C" int64_t prb_finalize_update_blocks(int64_t P, int C)
+{
+    return ceil_div(hmax(P, 1) * grp_lanes(P, C), 256);
+}
+
+template <int TK1>
+static int launch_update(int32_t *hits, const int32_t *cnt, const int64_t *clsz,
+                         const int32_t *hsize, const int32_t *hs_ysum, const int32_t *ha, int C,
+                         const double *table, int64_t N, int64_t P, int want_marg,
+                         const SelFuse &sel, cudaStream_t st)
+{
+    const int threads = 256;
+    const int L = grp_lanes(P, C);
+    const int64_t stride = (int64_t)C * TK1 * TK1;
+#define PRB_FU(LL)                                                                                  \
+    k_finalize_direct_grp<TK1, LL, true><<<(unsigned)ceil_div(P * LL, threads), threads, 0, st>>>(  \
+        hits, stride, cnt, clsz, hsize, hs_ysum, ha, C, table, N, P, nullptr, nullptr, want_marg,   \
+        sel)
+    if (L == 32)
+        PRB_FU(32);
+    else if (L == 16)
+        PRB_FU(16);
+    else
+        PRB_FU(8);
+#undef PRB_FU
+    PRB_LAUNCH_CHECK("k_finalize_update");
+    return 0;
+}
+
+extern "C" int prb_finalize_update(int32_t *hits, const int32_t *cnt, const int64_t *classsizes,
+                                   const int32_t *hsize, const int32_t *hs_ysum,
+                                   const int32_t *ha, int C, int K, const double *table,
+                                   int64_t N, int64_t P, int kind, int is_remove,
+                                   const double *base, double *penalty, double *score,
+                                   const uint8_t *selected, const double *Hx_all,
+                                   const double *Hyx_all, const int32_t *gene_ptr,
+                                   const int32_t *n_sel_ptr, int32_t gene_lo, double *cand_score,
+                                   int64_t *cand_idx, double *best, int32_t *ticket,
+                                   const uint32_t *col_packed, const int64_t *col_begin,
+                                   const int64_t *col_end, const int32_t *newpos, uint8_t *sx,
+                                   prb_stream_t stream)
+{
+    PRB_REQUIRE(P >= 1 && C >= 1 && K >= 2 && K <= 5, "the fused step tail needs 2 <= K <= 5");
+    PRB_REQUIRE(kind == PRB_SEL_CIFE || kind == PRB_SEL_JMI || kind == PRB_SEL_CIFE_UNSUP,
+                "unknown selector kind");
+    PRB_REQUIRE(hits && base && penalty && score && selected && Hx_all && gene_ptr && n_sel_ptr,
+                "null pointer");
+    PRB_REQUIRE(kind == PRB_SEL_CIFE_UNSUP || Hyx_all, "supervised update needs Hyx_all");
+    PRB_REQUIRE(cand_score && cand_idx && best && ticket && col_packed && col_begin && col_end && sx,
+                "null pointer");
+    SelFuse sel{kind, is_remove, base, penalty, score, selected, Hx_all, Hyx_all, gene_ptr,
+                n_sel_ptr, gene_lo, cand_score, cand_idx, best, ticket, col_packed, col_begin,
+                col_end, newpos, sx};
+    const int want_marg = kind != PRB_SEL_CIFE_UNSUP;
+#define PRB_LU(T)                                                                               \
+    return launch_update<T>(hits, cnt, classsizes, hsize, hs_ysum, ha, C, table, N, P, want_marg, \
+                            sel, S(stream))
+    switch (K - 1) {
+        case 1: PRB_LU(1);
+        case 2: PRB_LU(2);
+        case 3: PRB_LU(3);
+        default: PRB_LU(4);
+    }
+#undef PRB_LU
 }

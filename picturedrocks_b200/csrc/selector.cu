@@ -6,52 +6,15 @@
 // and np.argmax in picturedrocks/markers/_iterative.py:64-66.
 // All arithmetic is fp64 with explicit round-to-nearest adds in the reference's
 // left-to-right order, so scores are bit-identical given bit-identical entropies.
-#include <math.h>
-
-#include "common.cuh"
+#include "select.cuh"
 
 namespace prb {
-
-constexpr int SEL_BLOCK = 256;
 
 __global__ void k_mi_base(const double *__restrict__ Hx, double Hy, const double *__restrict__ Hyx,
                           int64_t P, double *__restrict__ base)
 {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < P) base[i] = __dsub_rn(__dadd_rn(Hx[i], Hy), Hyx[i]);
-}
-
-// block-wide argmax with np.argmax semantics; result valid in thread 0.
-__device__ __forceinline__ void block_argmax(double &s, int64_t &idx)
-{
-    __shared__ double ss[SEL_BLOCK / 32];
-    __shared__ int64_t si[SEL_BLOCK / 32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int o = 16; o > 0; o >>= 1) {
-        const double s2 = __shfl_down_sync(0xffffffffu, s, o);
-        const int64_t i2 = __shfl_down_sync(0xffffffffu, idx, o);
-        if (i2 >= 0 && (idx < 0 || better(s2, i2, s, idx))) {
-            s = s2;
-            idx = i2;
-        }
-    }
-    if (lane == 0) {
-        ss[warp] = s;
-        si[warp] = idx;
-    }
-    __syncthreads();
-    if (warp == 0) {
-        s = lane < SEL_BLOCK / 32 ? ss[lane] : 0.0;
-        idx = lane < SEL_BLOCK / 32 ? si[lane] : -1;
-        for (int o = 16; o > 0; o >>= 1) {
-            const double s2 = __shfl_down_sync(0xffffffffu, s, o);
-            const int64_t i2 = __shfl_down_sync(0xffffffffu, idx, o);
-            if (i2 >= 0 && (idx < 0 || better(s2, i2, s, idx))) {
-                s = s2;
-                idx = i2;
-            }
-        }
-    }
 }
 
 __global__ void __launch_bounds__(SEL_BLOCK)
@@ -69,29 +32,16 @@ k_selector_update(int kind, int is_remove, const double *__restrict__ base,
     double sc = 0.0;
     int64_t idx = -1;
     if (i < P) {
-        const double b = base[i];
-        double d;
-        if (kind == PRB_SEL_CIFE_UNSUP) {
-            d = __dsub_rn(__dadd_rn(b, Hj), Hij[i]);
-        } else {
-            const double Hyj = Hyx_all[j];
-            d = __dadd_rn(__dsub_rn(__dsub_rn(__dadd_rn(b, Hj), Hij[i]), Hyj), Hyij[i]);
-        }
-        const double pen = is_remove ? __dsub_rn(penalty[i], d) : __dadd_rn(penalty[i], d);
+        const double Hyj = kind == PRB_SEL_CIFE_UNSUP ? 0.0 : Hyx_all[j];
+        double pen = penalty[i];
+        sc = sel_update(kind, is_remove, base[i], Hj, Hij[i], Hyj,
+                        kind == PRB_SEL_CIFE_UNSUP ? 0.0 : Hyij[i], &pen, score[i], *n_sel_ptr,
+                        selected[i] != 0);
         penalty[i] = pen;
-        if (kind == PRB_SEL_JMI) {
-            const double n = (double)(*n_sel_ptr);
-            sc = __dsub_rn(b, __ddiv_rn(pen, n));
-        } else if (is_remove) {
-            sc = __dsub_rn(b, pen);
-        } else {
-            sc = __dsub_rn(score[i], d);
-        }
-        if (selected[i]) sc = -INFINITY;
         score[i] = sc;
         idx = gene_lo + i;
     }
-    block_argmax(sc, idx);
+    block_argmax<SEL_BLOCK>(sc, idx);
     if (threadIdx.x == 0) {
         cand_score[blockIdx.x] = sc;
         cand_idx[blockIdx.x] = idx;
@@ -105,7 +55,7 @@ k_argmax_blocks(const double *__restrict__ score, int64_t P, int32_t gene_lo,
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     double sc = i < P ? score[i] : 0.0;
     int64_t idx = i < P ? gene_lo + i : -1;
-    block_argmax(sc, idx);
+    block_argmax<SEL_BLOCK>(sc, idx);
     if (threadIdx.x == 0) {
         cand_score[blockIdx.x] = sc;
         cand_idx[blockIdx.x] = idx;
@@ -127,7 +77,7 @@ k_argmax_final(const double *__restrict__ cand_score, const int64_t *__restrict_
             idx = i2;
         }
     }
-    block_argmax(sc, idx);
+    block_argmax<SEL_BLOCK>(sc, idx);
     if (threadIdx.x == 0) {
         *best_score = sc;
         *best_idx = idx;
@@ -151,7 +101,7 @@ k_argmax_commit(const double *__restrict__ cand_score, const int64_t *__restrict
             idx = i2;
         }
     }
-    block_argmax(sc, idx);
+    block_argmax<SEL_BLOCK>(sc, idx);
     if (threadIdx.x == 0) {
         *best_score = sc;
         *best_idx = idx;

@@ -17,14 +17,17 @@ namespace prb {
 
 constexpr int SCATTER_BLOCKS_PER_SM = 4;
 
+// col_begin / col_end: first / past-the-last word of every gene's column in `packed`
+// (indptr[:-1] / indptr[1:] of a contiguous CSC, or the slots of the replicated copy)
 __global__ void k_scatter_u8(const uint32_t *__restrict__ packed,
-                             const int64_t *__restrict__ indptr,
-                             const int32_t *__restrict__ gene_ptr, int32_t gene_lo, int64_t P,
+                             const int64_t *__restrict__ col_begin,
+                             const int64_t *__restrict__ col_end,
+                             const int32_t *__restrict__ gene_ptr, int64_t P,
                              const int32_t *__restrict__ newpos, uint8_t *__restrict__ xj)
 {
-    const int64_t g = (int64_t)(*gene_ptr) - gene_lo;
+    const int64_t g = *gene_ptr;
     if (g < 0 || g >= P) return;
-    const int64_t b = indptr[g], e = indptr[g + 1];
+    const int64_t b = col_begin[g], e = col_end[g];
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = b + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < e; i += stride) {
         const uint32_t w = __ldg(packed + i);
@@ -34,10 +37,11 @@ __global__ void k_scatter_u8(const uint32_t *__restrict__ packed,
 }
 
 __global__ void k_scatter_or32(const uint32_t *__restrict__ packed,
-                               const int64_t *__restrict__ indptr, int64_t gene, int shift_bits,
+                               const int64_t *__restrict__ col_begin,
+                               const int64_t *__restrict__ col_end, int64_t gene, int shift_bits,
                                uint32_t *__restrict__ mpacked)
 {
-    const int64_t b = indptr[gene], e = indptr[gene + 1];
+    const int64_t b = col_begin[gene], e = col_end[gene];
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = b + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < e; i += stride) {
         const uint32_t w = __ldg(packed + i);
@@ -96,62 +100,6 @@ __global__ void k_state_direct_sums(const int32_t *__restrict__ hsize, int C, in
         ha[a] = s;
     }
     (void)work_counter;
-}
-
-// Per-cell shift code of the selected gene (x_j in the class-sorted cell order) for
-// vstream.cu:  sx = 8*(x_j-1) (offset of x_j's 8-bit counter field), PRB_SX_NONE for x_j = 0,
-// and hsize[y*(K-1) + x_j-1] = #cells (the sizes of the hit states).
-__global__ void __launch_bounds__(256)
-k_state_v(uint8_t *__restrict__ xj, const int32_t *__restrict__ y, int64_t N, int K1, int C,
-          uint8_t *__restrict__ sx, int32_t *__restrict__ hsize, int use_smem_hist,
-          int32_t *__restrict__ hs_begin, int32_t *__restrict__ hs_y,
-          int32_t *__restrict__ hs_ysum, int32_t *__restrict__ ha, int *ticket)
-{
-    extern __shared__ int sh_hist[];
-    __shared__ int s_last;
-    const int n_hs = C * K1;
-    if (use_smem_hist) {
-        for (int i = threadIdx.x; i < n_hs; i += blockDim.x) sh_hist[i] = 0;
-        __syncthreads();
-    }
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t cell = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; cell < N; cell += stride) {
-        const int a = xj[cell];
-        int s = PRB_SX_NONE;
-        if (a) {
-            const int yy = y ? y[cell] : 0;
-            s = 8 * (a - 1);
-            atomicAdd(use_smem_hist ? sh_hist + yy * K1 + a - 1 : hsize + yy * K1 + a - 1, 1);
-            xj[cell] = 0;  // leave the scatter buffer clean for the next selected gene
-        }
-        sx[cell] = (uint8_t)s;
-    }
-    if (use_smem_hist) {
-        __syncthreads();
-        for (int i = threadIdx.x; i < n_hs; i += blockDim.x)
-            if (sh_hist[i]) atomicAdd(hsize + i, sh_hist[i]);
-    }
-    // the last block to finish derives the per-class / per-value sums (k_state_direct_sums)
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1) == (int)gridDim.x - 1;
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    const int t = threadIdx.x, nt = blockDim.x;
-    for (int yy = t; yy <= C; yy += nt) hs_begin[yy] = yy * K1;
-    for (int h = t; h < n_hs; h += nt) hs_y[h] = h / K1;
-    for (int yy = t; yy < C; yy += nt) {
-        int sum = 0;
-        for (int a = 0; a < K1; ++a) sum += __ldcg(hsize + yy * K1 + a);
-        hs_ysum[yy] = sum;
-    }
-    for (int a = t; a < K1; a += nt) {
-        int sum = 0;
-        for (int yy = 0; yy < C; ++yy) sum += __ldcg(hsize + yy * K1 + a);
-        ha[a] = sum;
-    }
-    if (t == 0) *ticket = 0;
 }
 
 // ---- generic multi-column state through a presence table --------------------
@@ -284,22 +232,23 @@ static inline int cell_grid(int64_t N, int threads)
     return (int)hmax(1, hmin(ceil_div(N, threads), (int64_t)devinfo().sm_count * 8));
 }
 
-extern "C" int prb_scatter_gene_u8(const uint32_t *packed, const int64_t *indptr,
-                                   const int32_t *gene_ptr, int32_t gene_lo, int64_t P,
+extern "C" int prb_scatter_gene_u8(const uint32_t *packed, const int64_t *col_begin,
+                                   const int64_t *col_end, const int32_t *gene_ptr, int64_t P,
                                    const int32_t *newpos, uint8_t *xj, prb_stream_t stream)
 {
     k_scatter_u8<<<devinfo().sm_count * SCATTER_BLOCKS_PER_SM, 256, 0, S(stream)>>>(
-        packed, indptr, gene_ptr, gene_lo, P, newpos, xj);
+        packed, col_begin, col_end, gene_ptr, P, newpos, xj);
     PRB_LAUNCH_CHECK("k_scatter_u8");
     return 0;
 }
 
-extern "C" int prb_scatter_gene_or32(const uint32_t *packed, const int64_t *indptr, int64_t gene,
-                                     int shift_bits, uint32_t *mpacked, prb_stream_t stream)
+extern "C" int prb_scatter_gene_or32(const uint32_t *packed, const int64_t *col_begin,
+                                     const int64_t *col_end, int64_t gene, int shift_bits,
+                                     uint32_t *mpacked, prb_stream_t stream)
 {
     PRB_REQUIRE(shift_bits >= 0 && shift_bits < 32, "shift out of range");
     k_scatter_or32<<<devinfo().sm_count * SCATTER_BLOCKS_PER_SM, 256, 0, S(stream)>>>(
-        packed, indptr, gene, shift_bits, mpacked);
+        packed, col_begin, col_end, gene, shift_bits, mpacked);
     PRB_LAUNCH_CHECK("k_scatter_or32");
     return 0;
 }
@@ -328,22 +277,6 @@ extern "C" int prb_state_direct(const uint8_t *xj, const int32_t *y, int64_t N, 
     k_state_direct_sums<<<1, 256, 0, S(stream)>>>(hsize, C, K1, hs_begin, hs_y, hs_ysum, ha,
                                                   nullptr);
     PRB_LAUNCH_CHECK("k_state_direct_sums");
-    return 0;
-}
-
-extern "C" int prb_state_v(uint8_t *xj, const int32_t *y, int64_t N, int C, int K, uint8_t *sx,
-                           int32_t *hsize, int32_t *hs_begin, int32_t *hs_y, int32_t *hs_ysum,
-                           int32_t *ha, int32_t *ticket, prb_stream_t stream)
-{
-    PRB_REQUIRE(N > 0 && N <= PRB_MAX_ROWS, "N out of range");
-    PRB_REQUIRE(C >= 1 && K >= 2 && K <= 5, "the V-layout path needs 2 <= K <= 5");
-    const int K1 = K - 1;
-    const int64_t n_hs = (int64_t)C * K1;
-    PRB_CUDA(cudaMemsetAsync(hsize, 0, sizeof(int32_t) * n_hs, S(stream)));
-    const int use_smem = n_hs <= 8192;
-    k_state_v<<<cell_grid(N, 256), 256, use_smem ? n_hs * 4 : 0, S(stream)>>>(
-        xj, y, N, K1, C, sx, hsize, use_smem, hs_begin, hs_y, hs_ysum, ha, ticket);
-    PRB_LAUNCH_CHECK("k_state_v");
     return 0;
 }
 

@@ -654,14 +654,16 @@ static int stream_v_impl(const uint32_t *vpacked, const int32_t *run_end, const 
                          const int32_t *seg_cell0, const int32_t *seg_class, int n_st,
                          int64_t max_tile_cells, const uint8_t *sx, int C, int32_t *hits,
                          int32_t *counters, const int32_t *item_off, const int32_t *item_row0,
-                         const int32_t *item_vg0, int64_t n_items, prb_stream_t stream)
+                         const int32_t *item_vg0, int64_t n_items, int counters_clean,
+                         prb_stream_t stream)
 {
     if (P == 0 || v_rows == 0) return 0;
     PRB_REQUIRE(K1 >= 1 && K1 <= 4, "the register-counter path needs K <= 5");
     PRB_REQUIRE(n_seg >= 1 && n_st >= 1 && C >= 1 && sx != nullptr, "bad segment plan");
     PRB_REQUIRE(item_off && item_row0 && item_vg0 && n_items >= 1, "bad item plan");
     PRB_REQUIRE(max_tile_cells <= v_span() - 32, "super-tile spans too many cells");
-    PRB_CUDA(cudaMemsetAsync(counters, 0, sizeof(int32_t) * n_st, S(stream)));
+    if (!counters_clean)  // (prb_pick_scatter zeroes them in the greedy step)
+        PRB_CUDA(cudaMemsetAsync(counters, 0, sizeof(int32_t) * n_st, S(stream)));
     const int64_t PV = P * K1;
     auto launch = [&](auto kern, int smem, int warps) -> int {
         const int grid = (int)hmax(1, hmin(devinfo().sm_count, ceil_div(n_items, warps)));
@@ -696,11 +698,12 @@ extern "C" int prb_stream_v(const uint32_t *vpacked, const int32_t *run_end,
                             const int32_t *seg_class, int n_st, int64_t max_tile_cells,
                             const uint8_t *sx, int C, int32_t *hits, int32_t *counters,
                             const int32_t *item_off, const int32_t *item_row0,
-                            const int32_t *item_vg0, int64_t n_items, prb_stream_t stream)
+                            const int32_t *item_vg0, int64_t n_items, int counters_clean,
+                            prb_stream_t stream)
 {
     return stream_v_impl<1>(vpacked, run_end, tile_row0, n_seg, P, K1, v_rows, st_seg0, seg_cell0,
                             seg_class, n_st, max_tile_cells, sx, C, hits, counters, item_off,
-                            item_row0, item_vg0, n_items, stream);
+                            item_row0, item_vg0, n_items, counters_clean, stream);
 }
 
 // EXPERIMENTAL (PRB_V16=1, staged for round 2): the same pass over the V16 layout built by
@@ -711,10 +714,11 @@ extern "C" int prb_stream_v16(const uint32_t *vpacked, const int32_t *run_end,
                               const int32_t *seg_class, int n_st, int64_t max_tile_cells,
                               const uint8_t *sx, int C, int32_t *hits, int32_t *counters,
                               const int32_t *item_off, const int32_t *item_row0,
-                              const int32_t *item_vg0, int64_t n_items, prb_stream_t stream)
+                              const int32_t *item_vg0, int64_t n_items, int counters_clean,
+                              prb_stream_t stream)
 {
     PRB_REQUIRE(v_span() == 65536, "16-bit entries need 64 K-cell tiles");
     return stream_v_impl<2>(vpacked, run_end, tile_row0, n_seg, P, K1, v_rows, st_seg0, seg_cell0,
                             seg_class, n_st, max_tile_cells, sx, C, hits, counters, item_off,
-                            item_row0, item_vg0, n_items, stream);
+                            item_row0, item_vg0, n_items, counters_clean, stream);
 }

@@ -9,10 +9,11 @@ Reference being replaced (picturedrocks/markers/mutualinformation/infoset.py):
   entropy_wrt :251-303, _sparse_entropy_wrt :306-410, _sparse_entropy :413-428,
   _sparse_make_master_col :431-442.
 
-Multi-GPU: an Engine may hold only the genes [gene_lo, gene_lo + P) of a
-P_total-gene matrix (one process per GPU).  Per-cell state is replicated; the
-only exchanges are a max-all-reduce of the selected gene's dense code vector
-and the (score, index) all-gather of the argmax — see dist.py.
+Multi-GPU: an Engine streams only the genes [gene_lo, gene_lo + P) of a
+P_total-gene matrix (one process per GPU), but keeps a replicated copy of the
+whole packed CSC (one all-gather over NVLink at set-up), so the selected gene's
+column is always read locally; the only per-step exchange is the 16-byte
+(score, index) all-gather of the argmax — see dist.py.
 """
 import ctypes
 import os
@@ -28,6 +29,7 @@ _I16_MAX_BINS = 65536
 # PRB_NO_VLAYOUT=1 forces the generic shared-histogram kernel (csrc/stream.cu) everywhere
 USE_VLAYOUT = os.environ.get("PRB_NO_VLAYOUT", "0") != "1"
 PACKED_PAD = 4  # words of slack after the last stored entry
+SX_NONE = 64    # csrc/common.cuh PRB_SX_NONE: shift code of a cell with x_j = 0
 
 
 def _i32(x):
@@ -64,6 +66,7 @@ class Engine:
         if packed.numel() < self.nnz + PACKED_PAD:  # keep 16 bytes of slack behind the stream
             packed = torch.cat([packed[: self.nnz], packed.new_zeros(PACKED_PAD)])
             self.packed = packed
+        self._replicate_columns()
         sm = ctypes.c_int()
         smem = ctypes.c_int()
         nat.call("prb_device_info", ctypes.byref(sm), ctypes.byref(smem))
@@ -76,6 +79,9 @@ class Engine:
         # per-cell joint state (uint8 or uint16 view), padded for 128-bit tile copies
         self.state_buf = torch.zeros(2 * self.N + 64, dtype=torch.uint8, device=dev)
         self.xj = torch.zeros(self.N + 16, dtype=torch.uint8, device=dev)  # + slack: 16-byte copies
+        # V path: per-cell shift code of the selected gene (csrc/vstream.cu), all "x_j = 0"
+        # between steps: prb_pick_scatter writes a column, the step's tail resets it
+        self.sx = torch.full((self.N + 64,), SX_NONE, dtype=torch.uint8, device=dev)
         self.mpacked = None
         self.hsize = torch.zeros(_I16_MAX_BINS, dtype=torch.int32, device=dev)
         self.hs_y = torch.zeros(_I16_MAX_BINS, dtype=torch.int32, device=dev)
@@ -88,9 +94,9 @@ class Engine:
         self._plans = {}
         self._tps = {}
         self.vmode = USE_VLAYOUT and self.K1 <= 4
-        # EXPERIMENTAL (staged for round 2, not yet run on hardware): the V layout with
-        # 16-bit entries, 64 per row (prb_v_scatter16 / prb_stream_v16)
-        self.v16 = self.vmode and os.environ.get("PRB_V16", "0") == "1"
+        # the V layout with 16-bit entries, 64 per row (prb_v_scatter16 / prb_stream_v16);
+        # PRB_V16=0 selects the 32-bit entries of round 1 (1.40 vs 1.80 ms at config 4)
+        self.v16 = self.vmode and os.environ.get("PRB_V16", "1") == "1"
         self.v = None  # V layout (csrc/vstream.cu), built lazily for the current labels
         self.newpos = None    # V path: int32[N] new position of every cell (None = identity)
         self.y_sorted = None  # V path: labels in the new order
@@ -100,6 +106,7 @@ class Engine:
         self._table = None
         self.epoch = 0  # bumped whenever device buffers a captured graph points at change
         self.clsz_all = torch.tensor([self.N], dtype=torch.int64, device=dev)
+        self._cnt_rep = {}  # replicated count tables (all genes), by "labels or not"
         # labels
         self.has_y = False
         self.y = None
@@ -107,7 +114,40 @@ class Engine:
         self.classsizes = None
         self.cnt_y = None
         self._cnt_x = None  # label-free count table, built on first use
-        self.peer_step = False  # True while a selector runs a step with the peer-memory exchange
+
+    def _replicate_columns(self):
+        """col_packed / col_begin / col_end: the packed CSC of ALL genes, addressed by the
+        global gene id.  One GPU: the local arrays.  Gene-sharded: every rank's shard is
+        all-gathered once (in place, equal slots) over NVLink, so that the column of the
+        selected gene (infoset.py:289 -> 431-442) never has to be exchanged per step."""
+        if self.comm is None or self.comm.world == 1:
+            self.col_packed = self.packed
+            self.col_begin, self.col_end = self.indptr[:-1], self.indptr[1:]
+            return
+        comm = self.comm
+        slot = (comm.max_int(self.nnz) + PACKED_PAD + 3) & ~3
+        full = torch.empty(comm.world * slot + PACKED_PAD, dtype=torch.int32, device=self.device)
+        mine = full[comm.rank * slot: (comm.rank + 1) * slot]
+        mine[: self.nnz] = self.packed[: self.nnz]
+        mine[self.nnz:].zero_()
+        full[comm.world * slot:].zero_()
+        comm.all_gather_slots(full, slot)
+        self.packed = mine  # the local shard is a view of the replicated copy
+        bounds = comm.all_gather_shards(self.indptr[:-1] + comm.rank * slot), \
+            comm.all_gather_shards(self.indptr[1:] + comm.rank * slot)
+        self.col_packed = full
+        self.col_begin, self.col_end = bounds[0].contiguous(), bounds[1].contiguous()
+
+    def cnt_all(self, with_y):
+        """Count table of ALL genes [P_total][C][K-1] (replicated over the ranks)."""
+        cnt = self.cnt_y if with_y else self.cnt_x
+        if self.comm is None or self.comm.world == 1:
+            return cnt
+        key = bool(with_y)
+        if key not in self._cnt_rep:
+            width = (self.C if with_y else 1) * self.K1
+            self._cnt_rep[key] = self.comm.all_gather_shards(cnt[: self.P * width], width)
+        return self._cnt_rep[key]
 
     @staticmethod
     def host_term_table(N):
@@ -186,6 +226,7 @@ class Engine:
         that path (x_j, its shift codes, y_sorted) live in the new order."""
         self.epoch += 1
         self.v = None  # new labels: new segments
+        self._cnt_rep.pop(True, None)
         if y is None:
             self.has_y, self.y, self.C, self.classsizes, self.cnt_y = False, None, 1, None, None
             self.classsizes_host = self.newpos = self.y_sorted = None
@@ -301,6 +342,7 @@ class Engine:
                       item_rows=R, n_items=item_off[-1], item_vg0=item_vg0.contiguous(),
                       item_row0=row0_d,
                       item_off=torch.tensor(item_off, dtype=torch.int32, device=dev))
+        self.sx.fill_(SX_NONE)
         self.epoch += 1
         return self.v
 
@@ -325,19 +367,20 @@ class Engine:
         cnt = cnt.permute(0, 2, 1).contiguous().view(-1)
         return cnt if cnt.numel() else torch.zeros(1, dtype=torch.int32, device=dev)
 
-    def _stream_v(self, with_y, sx, C, hits):
+    def _stream_v(self, with_y, C, hits):
+        """The streaming pass (counters were zeroed by prb_pick_scatter)."""
         ev = getattr(self, "profile_events", None)
         if ev is not None:
             e0 = torch.cuda.Event(enable_timing=True)
             e1 = torch.cuda.Event(enable_timing=True)
             e0.record()
-            self._stream_v_launch(with_y, sx, C, hits)
+            self._stream_v_launch(with_y, C, hits)
             e1.record()
             ev.append((e0, e1))
         else:
-            self._stream_v_launch(with_y, sx, C, hits)
+            self._stream_v_launch(with_y, C, hits)
 
-    def _stream_v_launch(self, with_y, sx, C, hits):
+    def _stream_v_launch(self, with_y, C, hits):
         v = self._v()
         pl = v["plan"]
         nat.call("prb_stream_v16" if self.v16 else "prb_stream_v", nat.ptr(v["vpacked"]),
@@ -345,9 +388,51 @@ class Engine:
                  nat.ptr(v["tile_row0"]), pl["n_seg"], self.P, self.K1, v["rows"],
                  nat.ptr(pl["st_seg0"]),
                  nat.ptr(pl["seg_cell0"]), nat.ptr(pl["seg_class"]) if with_y else None,
-                 pl["n_st"], pl["max_cells"], nat.ptr(sx), C, nat.ptr(hits),
+                 pl["n_st"], pl["max_cells"], nat.ptr(self.sx), C, nat.ptr(hits),
                  nat.ptr(self.counters), nat.ptr(v["item_off"]), nat.ptr(v["item_row0"]),
-                 nat.ptr(v["item_vg0"]), v["n_items"], nat.stream())
+                 nat.ptr(v["item_vg0"]), v["n_items"], 1, nat.stream())
+
+    def _pick_scatter(self, with_y, records, n_rec, sel):
+        """Head of a V-path step (csrc/step.cu): winner of the candidate records (n_rec = 0:
+        the gene already in gene_ptr), commit, state sizes, work counters, column -> sx."""
+        v = self._v()
+        C = self.C if with_y else 1
+        newpos = self.newpos if v["relabelled"] else None
+        nat.call("prb_pick_scatter", nat.ptr(records), n_rec, nat.ptr(self.gene_ptr),
+                 nat.ptr(sel.S_dev) if sel else None, nat.ptr(sel.n_sel) if sel else None,
+                 nat.ptr(sel.selected) if sel else None, _i32(self.gene_lo), self.P,
+                 nat.ptr(self.col_packed), nat.ptr(self.col_begin), nat.ptr(self.col_end),
+                 nat.ptr(newpos), nat.ptr(self.sx), nat.ptr(self.cnt_all(with_y)), C, self.K,
+                 nat.ptr(self.hsize), nat.ptr(self.hs_ysum), nat.ptr(self.ha),
+                 nat.ptr(self.counters), v["plan"]["n_st"], nat.stream())
+
+    def fused_step(self, sel, kind, is_remove, pick):
+        """One greedy step of a selector on the V path, three launches, no host sync:
+        prb_pick_scatter -> prb_stream_v -> prb_finalize_update (entropies of INFOSET:392-397,
+        the score update of ITER:48-59 / 76-87 / 112-121, this rank's argmax record and the
+        reset of sx).  pick = False: add(ind) / remove(ind) with the gene in gene_ptr."""
+        with_y = sel.supervised
+        C, y, cnt, clsz = self._labels(with_y)
+        n_bins = C * self.K1 * self.K1
+        if n_bins > _I16_MAX_BINS:
+            raise NotImplementedError("C*(K-1)^2 exceeds 65536 histogram bins")
+        self.cnt_all(with_y)  # (collective on first use: before any kernel of the step)
+        v = self._v()
+        if self.P == 0:
+            return
+        self._pick_scatter(with_y, sel.records, sel.n_rec if pick else 0, sel)
+        hits = self.hits_buffer(n_bins)
+        self._stream_v(with_y, C, hits)
+        newpos = self.newpos if v["relabelled"] else None
+        nat.call("prb_finalize_update", nat.ptr(hits), nat.ptr(cnt), nat.ptr(clsz),
+                 nat.ptr(self.hsize), nat.ptr(self.hs_ysum), nat.ptr(self.ha), C, self.K,
+                 nat.ptr(self.term), self.N, self.P, kind, int(is_remove), nat.ptr(sel.base),
+                 nat.ptr(sel.penalty), nat.ptr(sel.score), nat.ptr(sel.selected),
+                 nat.ptr(sel.Hx_all), nat.ptr(sel.Hyx_all), nat.ptr(self.gene_ptr),
+                 nat.ptr(sel.n_sel), _i32(self.gene_lo), nat.ptr(sel.cand_score),
+                 nat.ptr(sel.cand_idx), nat.ptr(sel.best), nat.ptr(self.ticket),
+                 nat.ptr(self.col_packed), nat.ptr(self.col_begin), nat.ptr(self.col_end),
+                 nat.ptr(newpos), nat.ptr(self.sx), nat.stream())
 
     # --------------------------------------------------------------- primitives
     def hits_buffer(self, n_bins):
@@ -402,28 +487,12 @@ class Engine:
         return 1, None, self.cnt_x, self.clsz_all
 
     def scatter_selected_gene(self):
-        """x_j[N] <- dense codes of gene *gene_ptr (owner rank), replicated to all ranks.
-        (V path: prb_state_v hands x_j back all-zero, so no memset is needed.)"""
-        newpos = None
-        if self.vmode:
-            newpos = self.newpos if self._v()["relabelled"] else None
-        else:
-            self.xj.zero_()
-        peer = self.comm.peer if (self.comm is not None and self.peer_step) else None
-        if peer is not None:
-            # greedy step with the peer-memory exchange (csrc/peer.cu): the owner scatters
-            # into the x_j area of its symmetric buffer, everyone pulls it from there
-            peer.clean()
-            target = peer.col
-        else:
-            target = self.xj
-        nat.call("prb_scatter_gene_u8", nat.ptr(self.packed), nat.ptr(self.indptr),
-                 nat.ptr(self.gene_ptr), _i32(self.gene_lo), self.P, nat.ptr(newpos),
-                 nat.ptr(target), nat.stream())
-        if peer is not None:
-            peer.fetch_column(self.gene_ptr, self.xj)
-        elif self.comm is not None:
-            self.comm.allreduce_max_(self.xj)
+        """Generic path: x_j[N] <- dense codes of gene *gene_ptr, read from the replicated
+        packed CSC (no exchange)."""
+        self.xj.zero_()
+        nat.call("prb_scatter_gene_u8", nat.ptr(self.col_packed), nat.ptr(self.col_begin),
+                 nat.ptr(self.col_end), nat.ptr(self.gene_ptr), self.P_total, None,
+                 nat.ptr(self.xj), nat.stream())
 
     def direct_step(self, with_y, out_full, out_marg):
         """One fused pass for the gene in gene_ptr:
@@ -433,18 +502,20 @@ class Engine:
         n_bins = n_hs * self.K1
         if n_bins > _I16_MAX_BINS:
             raise NotImplementedError("C*(K-1)^2 exceeds 65536 histogram bins")
-        self.scatter_selected_gene()
         if self.vmode:
-            if with_y:
-                y = self.y_sorted  # x_j was scattered in the V layout's cell order
-            nat.call("prb_state_v", nat.ptr(self.xj), nat.ptr(y), self.N, C, self.K,
-                     nat.ptr(self.state_buf), nat.ptr(self.hsize), nat.ptr(self.hs_begin),
-                     nat.ptr(self.hs_y), nat.ptr(self.hs_ysum), nat.ptr(self.ha),
-                     nat.ptr(self.ticket), nat.stream())
+            if self.P == 0:
+                return
+            v = self._v()
+            self._pick_scatter(with_y, None, 0, None)
             hits = self.hits_buffer(n_bins)
-            self._stream_v(with_y, self.state_buf, C, hits)
+            self._stream_v(with_y, C, hits)
             self._finalize(hits, cnt, clsz, C, n_hs, None, out_full, out_marg, True)
+            nat.call("prb_v_unscatter", nat.ptr(self.gene_ptr), nat.ptr(self.col_packed),
+                     nat.ptr(self.col_begin), nat.ptr(self.col_end),
+                     nat.ptr(self.newpos if v["relabelled"] else None), nat.ptr(self.sx),
+                     nat.stream())
             return
+        self.scatter_selected_gene()
         sb = self._plan(n_hs)[3]
         nat.call("prb_state_direct", nat.ptr(self.xj), nat.ptr(y), self.N, C, self.K,
                  nat.ptr(self.state_buf), sb, nat.ptr(self.hsize), nat.ptr(self.hs_begin),
@@ -464,12 +535,9 @@ class Engine:
             self.mpacked = torch.zeros(self.N, dtype=torch.int32, device=self.device)
         self.mpacked.zero_()
         for pos, c in enumerate(cols):
-            local = c - self.gene_lo
-            if 0 <= local < self.P:
-                nat.call("prb_scatter_gene_or32", nat.ptr(self.packed), nat.ptr(self.indptr),
-                         local, self.shift * (m - 1 - pos), nat.ptr(self.mpacked), nat.stream())
-        if self.comm is not None:
-            self.comm.allreduce_sum_(self.mpacked)  # disjoint bit fields: sum == or
+            nat.call("prb_scatter_gene_or32", nat.ptr(self.col_packed), nat.ptr(self.col_begin),
+                     nat.ptr(self.col_end), c, self.shift * (m - 1 - pos), nat.ptr(self.mpacked),
+                     nat.stream())
         return mbits
 
     def _table_scratch(self, n_keys):

@@ -5,10 +5,12 @@ Class names, constructor signature, attributes (`infoset`, `S`, `base_score`,
 `penalty`, `score`) and methods (`add`, `remove`, `autoselect`) follow the
 reference.  Scores live on the GPU; `score` / `penalty` / `base_score` are
 materialised as float64 ndarrays on access, `S` as a Python list.
-`autoselect(n)` runs n greedy steps without any host synchronisation:
+`autoselect(n)` runs n greedy steps without any host synchronisation; on the V-layout
+path (K <= 5) a step is three launches (+ one 16-byte all-gather when genes are sharded):
 
-    argmax (device)  ->  commit winner  ->  scatter x_j / build per-cell state
-    ->  one streaming pass (joint histograms)  ->  entropies  ->  score update
+    prb_pick_scatter   argmax of the candidate records, commit, column of the winner
+    prb_stream_v       one streaming pass (joint histograms)
+    prb_finalize_update  entropies, score update, this rank's next candidate record
 
 Score algebra is evaluated in the reference's order (iterative.py:29-33, 50-58,
 78-86, 114-120) so results are bit-identical given bit-identical entropies.
@@ -74,13 +76,26 @@ class _DeviceScores:
         self.penalty = torch.zeros(self.P, **f64)
         self.score = self.base.clone()
         self.selected = torch.zeros(max(self.P, 1), dtype=torch.uint8, device=self.dev)
+        # V-layout path: the whole step runs in engine.fused_step (three launches)
+        self.fused = (e.vmode and self.be.ycol is None
+                      and (self.comm is None or min(self.comm.shard_sizes) > 0))
         self.n_blocks = max(1, -(-self.P // 256))
-        self.cand_score = torch.zeros(self.n_blocks, **f64)
-        self.cand_idx = torch.full((self.n_blocks,), -1, dtype=torch.int64, device=self.dev)
+        n_cand = self.n_blocks
+        if self.fused:
+            C = e.C if supervised else 1
+            n_cand = max(n_cand, int(nat.load().prb_finalize_update_blocks(self.P, C)))
+        self.cand_score = torch.zeros(n_cand, **f64)
+        self.cand_idx = torch.full((n_cand,), -1, dtype=torch.int64, device=self.dev)
         # one 16-byte (score, idx) record: a single all-gather moves both
         self.best = torch.zeros(2, **f64)
+        self.best.view(torch.int64)[1] = -1
         self.best_score = self.best[0:1]
         self.best_idx = self.best.view(torch.int64)[1:2]
+        # fused path: the candidate records the next pick reduces — this rank's own, or one
+        # per rank (all-gathered at the end of every step)
+        self.n_rec = 1 if self.comm is None else self.comm.world
+        self.records = self.best if self.comm is None else torch.zeros(2 * self.n_rec, **f64)
+        self.records_valid = False
         self.S_dev = torch.zeros(self.P_total + 1, dtype=torch.int32, device=self.dev)
         self.n_sel = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.cand_valid = False
@@ -96,6 +111,30 @@ class _DeviceScores:
         return v.cpu().numpy()
 
     # -- device steps ---------------------------------------------------------
+    def _share_best(self):
+        """records <- every rank's (score, index) record."""
+        if self.comm is not None:
+            import torch.distributed as dist
+
+            dist.all_gather_into_tensor(self.records, self.best, group=self.comm.group)
+        self.records_valid = True
+
+    def fused_step(self, kind, is_remove=False, pick=True):
+        """V-layout path: one greedy step (pick = True) or one add / remove of the gene in
+        engine.gene_ptr, see Engine.fused_step."""
+        if pick and not self.records_valid:
+            # first step after construction: candidates straight from the score vector
+            s = nat.stream()
+            if self.P:
+                nat.call("prb_argmax_blocks", nat.ptr(self.score), self.P,
+                         ctypes.c_int32(self.gene_lo), nat.ptr(self.cand_score),
+                         nat.ptr(self.cand_idx), s)
+                nat.call("prb_best_record", nat.ptr(self.cand_score), nat.ptr(self.cand_idx),
+                         self.n_blocks, nat.ptr(self.best), s)
+            self._share_best()
+        self.engine.fused_step(self, _KIND[kind], is_remove, pick)
+        self._share_best()
+
     def pick_and_commit(self):
         """best_idx <- argmax(score) (global index; lowest index on ties), then commit it:
         gene_ptr <- best, S.append(best), selected[best] = 1."""
@@ -110,19 +149,17 @@ class _DeviceScores:
             nat.call("prb_argmax_commit", nat.ptr(self.cand_score), nat.ptr(self.cand_idx),
                      self.n_blocks, 1, nat.ptr(self.best_score), nat.ptr(self.best_idx), *commit)
             return
-        peer = self.comm.enable_peer(e.N)
-        if peer is not None:
-            # one kernel over NVLink peer memory instead of argmax_final + NCCL all-gather
-            g = peer.gather_candidates(self.cand_score, self.cand_idx, self.n_blocks)
-        else:
-            nat.call("prb_argmax_final", nat.ptr(self.cand_score), nat.ptr(self.cand_idx),
-                     self.n_blocks, 1, nat.ptr(self.best_score), nat.ptr(self.best_idx), s)
-            g = self.comm.all_gather_cat(self.best)  # [world][score, idx]
+        nat.call("prb_argmax_final", nat.ptr(self.cand_score), nat.ptr(self.cand_idx),
+                 self.n_blocks, 1, nat.ptr(self.best_score), nat.ptr(self.best_idx), s)
+        g = self.comm.all_gather_cat(self.best)  # [world][score, idx]
         nat.call("prb_argmax_commit", nat.ptr(g), nat.ptr(g) + 8, self.comm.world, 2,
                  nat.ptr(self.best_score), nat.ptr(self.best_idx), *commit)
 
     def apply(self, kind, is_remove, host_ind=None):
         """penalty/score update for the gene in engine.gene_ptr."""
+        if self.fused:
+            self.fused_step(kind, is_remove, pick=False)
+            return
         Hij, Hyij = self.be.step(self.supervised, host_ind)
         nat.call("prb_selector_update", _KIND[kind], int(is_remove), nat.ptr(self.base),
                  nat.ptr(self.penalty), nat.ptr(self.score), nat.ptr(self.selected), nat.ptr(Hij),
@@ -214,13 +251,11 @@ class _GreedyDevice(IterativeFeatureSelection):
 
     def _one_step(self):
         d = self._d
+        if d.fused:
+            d.fused_step(self._kind)
+            return
         d.pick_and_commit()
-        # (the column exchange may go over peer memory only in steps whose candidates did)
-        d.engine.peer_step = d.comm is not None and d.comm.peer is not None
-        try:
-            d.apply(self._kind, False)
-        finally:
-            d.engine.peer_step = False
+        d.apply(self._kind, False)
 
     def _capture(self):
         """Capture one greedy step (kernels + collectives) on a side stream."""

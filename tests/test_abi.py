@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), "libprb200.so does not export %s" % name
     # the ctypes table binds exactly the declared entry points
     assert sorted(_native.EXPORTED) == declared_symbols()
-    assert lib.prb_abi_version() == 1
+    assert lib.prb_abi_version() == 2
 
 
 def test_term_table_is_host_side_and_matches_libm():
@@ -66,17 +66,3 @@ def test_no_cpu_fallback():
                 src += open(os.path.join(dirpath, f)).read()
     assert "oracle" not in src.replace("the oracle check", "").replace("lets the oracle", ""), \
         "product code must not reference oracle/"
-
-
-def test_peer_layout_is_host_side():
-    """prb_peer_layout (symmetric-buffer layout of csrc/peer.cu) needs no GPU: records and
-    flags for both parities, then the 16-byte-aligned x_j area."""
-    from picturedrocks_b200 import _native
-
-    for N, W in ((1306127, 8), (2730, 2), (16, 1), (17, 64)):
-        nbytes, off_col, n_pad = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
-        _native.call("prb_peer_layout", N, W, ctypes.byref(nbytes), ctypes.byref(off_col),
-                     ctypes.byref(n_pad))
-        assert n_pad.value % 16 == 0 and N <= n_pad.value < N + 16
-        assert off_col.value % 128 == 0 and off_col.value >= 2 * W * 16 + 2 * W * 4 + 4
-        assert nbytes.value == off_col.value + n_pad.value

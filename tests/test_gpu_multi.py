@@ -16,12 +16,10 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, ret, peer=False):
+def _worker(rank, world, port, ret):
     import torch
     import torch.distributed as dist
 
-    if peer:
-        os.environ["PRB_PEER_EXCHANGE"] = "1"
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -57,21 +55,18 @@ def _worker(rank, world, port, ret, peer=False):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("peer", [False, True], ids=["nccl", "peer-memory"])
-def test_two_rank_selection_equals_single_gpu(peer):
+def test_two_rank_selection_equals_single_gpu():
     import torch
     import torch.multiprocessing as mp
 
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    if peer and os.environ.get("PRB_TEST_PEER", "0") != "1":
-        pytest.skip("experimental peer-memory exchange (csrc/peer.cu): set PRB_TEST_PEER=1")
     import picturedrocks_b200 as pr
     from picturedrocks_b200.synth import DiscretisedSpec
 
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(2, _free_port(), ret, peer), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
     spec = DiscretisedSpec(N=40000, P=1203, C=9, K=5, mean_density=0.08, seed=21)
     eng, yd = spec.device_engine()
     inf = pr.markers.SparseInformationSet._from_engine(eng, yd)

@@ -39,7 +39,7 @@ def test_native_library_is_loaded(pr):
     from picturedrocks_b200 import _native
 
     lib = _native.load()
-    assert lib.prb_abi_version() == 1
+    assert lib.prb_abi_version() == 2
     with open("/proc/self/maps") as f:
         assert "libprb200.so" in f.read()
 
@@ -360,21 +360,20 @@ def test_class_sorted_cells_and_v_layout(pr, O, monkeypatch, tile_cells, vlayout
     assert np.array_equal(Xg.indices, Xs.indices) and np.array_equal(Xg.data, Xs.data)
 
 
+@pytest.mark.parametrize("v16", ["1", "0"])
 @pytest.mark.parametrize("tile_cells", [None, 4096])
-def test_v16_layout_staged(pr, O, monkeypatch, tile_cells):
-    """EXPERIMENTAL V layout with 16-bit entries (PRB_V16=1: prb_v_scatter16 / prb_stream_v16),
-    staged in round 1 without a hardware run: opt in with PRB_TEST_V16=1.  Same checks as the
-    32-bit layout: entropies, scores and sequences bit-identical to the oracle."""
-    if os.environ.get("PRB_TEST_V16", "0") != "1":
-        pytest.skip("staged V16 layout: set PRB_TEST_V16=1")
+def test_v_layout_entry_widths(pr, O, monkeypatch, tile_cells, v16):
+    """Both entry widths of the V layout — 16-bit entries, 64 per row (the default:
+    prb_v_scatter16 / prb_stream_v16) and the 32-bit words of round 1 (PRB_V16=0): entropies,
+    scores and sequences bit-identical to the oracle."""
     from picturedrocks_b200.synth import DiscretisedSpec
 
-    monkeypatch.setenv("PRB_V16", "1")
+    monkeypatch.setenv("PRB_V16", v16)
     if tile_cells:
         monkeypatch.setenv("PRB_V_TILE_CELLS", str(tile_cells))
     spec = DiscretisedSpec(N=70001, P=301, C=7, K=5, mean_density=0.09, seed=12)  # two 64 K tiles
     eng, yd = spec.device_engine()
-    assert eng.v16
+    assert eng.v16 == (v16 == "1")
     inf = pr.markers.SparseInformationSet._from_engine(eng, yd)
     y = spec.cpu_labels()
     ora = O.SparseInformationSet(spec.cpu_csc(range(spec.P), y), y)
