@@ -114,7 +114,7 @@ int prb_stream_hits(const uint32_t *packed, const int64_t *tp, int64_t P, int64_
  *                 s are seg_pad[s] = 0xFF000000 | ((first cell after the segment's
  *                 super-tile) mod tile span): a slot the kernel keeps at "x_j = 0"
  *  4. prb_pick_scatter (below) writes the per-cell shift code of the selected gene,
- *     sx uint8[N] (+16 bytes of padding) = 8*(x_j-1), 64 where x_j = 0 — sx is all 64
+ *     sx uint8[N] (+16 bytes of padding) = 8*(x_j-1), 255 where x_j = 0 — sx is all 255
  *     between steps —, and the hsize / hs_ysum / ha tables (taken from the count table of
  *     the selected gene).
  *  5. prb_stream_v adds the joint counts to hits int32[P][C][K-1][K-1]
@@ -160,6 +160,47 @@ int prb_stream_v(const uint32_t *vpacked, const int32_t *run_end, const int32_t 
 int prb_v_warps(void);
 /* cells per super-tile modulus (power of two) of the active kernel configuration */
 int prb_v_tile_span(void);
+
+/* ---- the hot loop on the LANE-RUN layout (vell.cu): one lane = one run, K <= 21 ----------
+ * Same job and same segment plan as prb_stream_v; the default of the Python engine.  A
+ * lane-run is a piece of at most CAP entries of one run (virtual gene vg, segment s); 32
+ * lane-runs of one super-tile, sorted by length, form a BUNDLE stored transposed:
+ * L = ceil(longest / 2) data rows whose word l holds entries 2r, 2r+1 of lane-run l (16-bit
+ * cell ids inside the super-tile; missing entries = the tile's "x_j = 0" slot), and a header
+ * row in a separate array bhdr uint32[n_bundles][32] (lane l: (segment index inside the
+ * tile) << 24 | vg, 0xFFFFFFFF = empty lane).
+ *   prb_v_count          run lengths seglen[P*(K-1)][n_seg] (as for the V layout)
+ *   prb_v_scatter_flat   relabelled 16-bit entries, run-major, flat: run (vg, s) at
+ *                        tmp16[run_start[vg*n_seg + s] ..) (run_start: caller's exclusive scan)
+ *   (caller: split runs into lane-runs, sort by (tile, -length), cut bundles:
+ *    lr_src int64 / lr_len int32 / lr_hdr uint32 [32 * n_bundles], brow0 int32[n_bundles+1],
+ *    bundle_pad uint16[n_bundles])
+ *   prb_ell_build        tmp16 -> ell uint32[32 * brow0[n_bundles]], bhdr
+ *   prb_stream_ell       adds the joint counts to hits int32[P][C][K-1][K-1].  Work items are
+ *                        ranges of whole bundles of one super-tile: item_off int32[n_st+1];
+ *                        item_b0 int32[n_items + n_st] = first bundle of every item, the items
+ *                        of tile t followed by one sentinel (first bundle of tile t+1).
+ *                        PV = P*(K-1); a header word that names no run of its tile is never
+ *                        written through: it is counted in dbg[0] (device int32[16], may be
+ *                        NULL; dbg[1..15] describe the first one).
+ * prb_v_check_smem_base(): 0 when dynamic shared memory starts at the window offset the
+ * V-layout kernels assume (they address the cell tile by the bare cell index). */
+int prb_v_scatter_flat(const uint32_t *packed, const int64_t *indptr, int64_t P,
+                       const uint32_t *cellmap, const uint16_t *seg16, int n_seg, int K1,
+                       const int32_t *seglen, const int64_t *run_start, uint16_t *tmp16,
+                       int32_t *queue, prb_stream_t stream);
+int prb_ell_build(const uint16_t *tmp16, const int64_t *lr_src, const int32_t *lr_len,
+                  const uint32_t *lr_hdr, const int32_t *brow0, const uint16_t *bundle_pad,
+                  int64_t n_bundles, uint32_t *ell, uint32_t *bhdr, prb_stream_t stream);
+int prb_stream_ell(const uint32_t *ell, const uint32_t *bhdr, const int32_t *brow0,
+                   int64_t n_bundles, int K1,
+                   const int32_t *st_seg0, const int32_t *seg_cell0, const int32_t *seg_class,
+                   int n_st, int64_t max_tile_cells, const uint8_t *sx, int C, int32_t *hits,
+                   int32_t *counters, const int32_t *item_off, const int32_t *item_b0,
+                   int64_t n_items, int counters_clean, int64_t PV, int32_t *dbg,
+                   prb_stream_t stream);
+int prb_ell_warps(void);
+int prb_v_check_smem_base(void);
 
 /* ---- joint-state build ("master column", _sparse_make_master_col INFOSET:431-442) */
 /* Columns are addressed through col_begin / col_end int64[P]: first / past-the-last word of
@@ -266,19 +307,20 @@ int prb_commit_add(const int64_t *best_idx, int32_t *gene_ptr, int32_t *S, int32
  * block with np.argmax's rule.  n_rec = 0: the gene already in *gene_ptr (add(ind) /
  * remove(ind) / entropy_wrt([j]) — nothing is committed).  Commit: *gene_ptr <- j,
  * S[(*n_sel_ptr)++] <- j, selected[j - gene_lo] <- 1 when local.  cnt_all int32[P_total][C][K-1]
- * (count table of ALL genes) gives hsize[y][a] = cnt_all[j][y][a], hs_ysum[y], ha[a].
+ * (count table of ALL genes) gives hsize[y][a] = cnt_all[j][y][a], hs_ysum[y], ha[a] (and the
+ * hs_begin / hs_y view of the same layout that prb_finalize reads).
  * counters[n_counters] <- 0.  Column j (col_packed / col_begin / col_end, global gene ids)
- * is scattered into sx (all 64 on entry) at newpos[cell]. */
+ * is scattered into sx (all 255 on entry) at newpos[cell]. */
 int prb_pick_scatter(const double *records, int n_rec, int32_t *gene_ptr, int32_t *S,
                      int32_t *n_sel_ptr, uint8_t *selected, int32_t gene_lo, int64_t P_local,
                      const uint32_t *col_packed, const int64_t *col_begin, const int64_t *col_end,
                      const int32_t *newpos, uint8_t *sx, const int32_t *cnt_all, int C, int K,
-                     int32_t *hsize, int32_t *hs_ysum, int32_t *ha, int32_t *counters,
-                     int n_counters, prb_stream_t stream);
+                     int32_t *hsize, int32_t *hs_begin, int32_t *hs_y, int32_t *hs_ysum,
+                     int32_t *ha, int32_t *counters, int n_counters, prb_stream_t stream);
 /* prb_finalize_direct + prb_selector_update + the reduction of the block candidates to ONE
  * record best double[2] = (score, index bits) of this rank (done by the last block; ticket:
  * device int32, zero on entry and exit; cand_score / cand_idx: scratch of
- * prb_finalize_update_blocks(P, C) entries) + the reset of column *gene_ptr of sx to 64.
+ * prb_finalize_update_blocks(P, C) entries) + the reset of column *gene_ptr of sx to 255.
  * Supervised kinds use H(y,x_j,x_g) and H(x_j,x_g); PRB_SEL_CIFE_UNSUP (C = 1) H(x_j,x_g). */
 int64_t prb_finalize_update_blocks(int64_t P, int C);
 int prb_finalize_update(int32_t *hits, const int32_t *cnt, const int64_t *classsizes,
@@ -291,7 +333,7 @@ int prb_finalize_update(int32_t *hits, const int32_t *cnt, const int64_t *classs
                         const uint32_t *col_packed, const int64_t *col_begin,
                         const int64_t *col_end, const int32_t *newpos, uint8_t *sx,
                         prb_stream_t stream);
-/* sx <- 64 at the stored entries of gene *gene_ptr (after a stand-alone streaming pass). */
+/* sx <- 255 at the stored entries of gene *gene_ptr (after a stand-alone streaming pass). */
 int prb_v_unscatter(const int32_t *gene_ptr, const uint32_t *col_packed, const int64_t *col_begin,
                     const int64_t *col_end, const int32_t *newpos, uint8_t *sx,
                     prb_stream_t stream);

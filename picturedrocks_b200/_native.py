@@ -46,7 +46,13 @@ _SIGS = {
     "prb_scatter_gene_u8": [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
     "prb_scatter_gene_or32": [_vp, _vp, _vp, _i64, _int, _vp, _vp],
     "prb_pick_scatter": [_vp, _int, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
-                         _int, _int, _vp, _vp, _vp, _vp, _int, _vp],
+                         _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp],
+    "prb_v_scatter_flat": [_vp, _vp, _i64, _vp, _vp, _int, _int, _vp, _vp, _vp, _vp, _vp],
+    "prb_ell_build": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
+    "prb_stream_ell": [_vp, _vp, _vp, _i64, _int, _vp, _vp, _vp, _int, _i64, _vp, _int, _vp, _vp, _vp,
+                       _vp, _i64, _int, _i64, _vp, _vp],
+    "prb_ell_warps": [],
+    "prb_v_check_smem_base": [],
     "prb_finalize_update_blocks": [_i64, _int],
     "prb_finalize_update": [_vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _vp, _i64, _i64, _int, _int,
                             _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp,
@@ -128,7 +134,8 @@ KERNELS = {
     "prb_pack_csc": 1, "prb_unpack_csc": 1, "prb_dense_count_nnz": 1, "prb_dense_fill_csc": 1,
     "prb_tile_ptrs": 1, "prb_stream_hits": 1,
     "prb_argmax_commit": 1, "prb_pick_scatter": 1, "prb_finalize_update": 1,
-    "prb_v_unscatter": 1, "prb_best_record": 1, "prb_v_count": 1, "prb_v_scatter": 1,
+    "prb_v_unscatter": 1, "prb_best_record": 1, "prb_v_scatter_flat": 1, "prb_ell_build": 1,
+    "prb_stream_ell": 1, "prb_v_count": 1, "prb_v_scatter": 1,
     "prb_stream_v": 1, "prb_scatter_gene_u8": 1,
     "prb_scatter_gene_or32": 1, "prb_state_direct": 2, "prb_state_table": 2, "prb_state_assign": 1, "prb_finalize": 1, "prb_finalize_direct": 1,
     "prb_entropy_keys": 2, "prb_mi_base": 1, "prb_selector_update": 1, "prb_argmax_blocks": 1,

@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["stream.cu", "vstream.cu", "state.cu", "finalize.cu", "selector.cu", "discretize.cu", "synth.cu",
+SOURCES = ["stream.cu", "vstream.cu", "vell.cu", "state.cu", "finalize.cu", "selector.cu", "discretize.cu", "synth.cu",
            "step.cu", "host.cu"]
 LIB = os.path.join(HERE, "libprb200.so")
 OBJ = os.path.join(HERE, "_obj")
@@ -18,6 +18,7 @@ def needs_build():
     deps = [os.path.join(CSRC, s) for s in SOURCES] + [
         os.path.join(CSRC, "common.cuh"),
         os.path.join(CSRC, "select.cuh"),
+        os.path.join(CSRC, "vcommon.cuh"),
         os.path.join(HERE, "..", "include", "prb200.h"),
     ]
     return any(os.path.getmtime(d) > t for d in deps)
@@ -45,7 +46,7 @@ def build(force=False, verbose=False):
             if verbose:
                 flags += ["-Xptxas", "-v"]
             os.makedirs(OBJ, exist_ok=True)
-            headers = [os.path.join(CSRC, h) for h in ("common.cuh", "select.cuh")] + [
+            headers = [os.path.join(CSRC, h) for h in ("common.cuh", "select.cuh", "vcommon.cuh")] + [
                 os.path.join(HERE, "..", "include", "prb200.h")]
             hdr_t = max(os.path.getmtime(h) for h in headers)
 

@@ -46,8 +46,10 @@ inline int64_t hmin(int64_t a, int64_t b) { return a < b ? a : b; }
 inline int64_t hmax(int64_t a, int64_t b) { return a > b ? a : b; }
 
 constexpr uint32_t ROW_MASK = 0x00FFFFFFu;
-// vstream.cu: shift code of a cell whose selected-gene code is 0 (>= 32: 1 << it == 0)
-constexpr int PRB_SX_NONE = 64;
+// vstream.cu / vell.cu: shift code of a cell whose selected-gene code is 0.  Counter register r
+// adds 1 << (code - 32 r) with PTX's clamping shift: any amount >= 32 (also a wrapped negative
+// one) contributes 0, and 255 - 32 r >= 32 for the up to five registers of K <= 21.
+constexpr int PRB_SX_NONE = 255;
 
 // np.argmax ordering: NaN is maximal; first index wins ties.
 __device__ __forceinline__ bool better(double sa, int64_t ia, double sb, int64_t ib)

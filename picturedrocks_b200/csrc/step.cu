@@ -29,7 +29,8 @@ k_pick_scatter(const double *__restrict__ rec, int n_rec, int32_t *gene_ptr, int
                const uint32_t *__restrict__ col_packed, const int64_t *__restrict__ col_begin,
                const int64_t *__restrict__ col_end, const int32_t *__restrict__ newpos,
                uint8_t *__restrict__ sx, const int32_t *__restrict__ cnt_all, int C, int K1,
-               int32_t *hsize, int32_t *hs_ysum, int32_t *ha, int *counters, int n_counters)
+               int32_t *hsize, int32_t *hs_begin, int32_t *hs_y, int32_t *hs_ysum, int32_t *ha,
+               int *counters, int n_counters)
 {
     __shared__ int s_j;
     if (threadIdx.x == 0) {
@@ -64,7 +65,11 @@ k_pick_scatter(const double *__restrict__ rec, int n_rec, int32_t *gene_ptr, int
         }
         const int n_hs = C * K1;
         const int32_t *cj = cnt_all + j * n_hs;
-        for (int i = threadIdx.x; i < n_hs; i += PICK_THREADS) hsize[i] = cj[i];
+        for (int i = threadIdx.x; i < n_hs; i += PICK_THREADS) {
+            hsize[i] = cj[i];
+            hs_y[i] = i / K1;  // the generic finalize kernel's view of the direct layout
+        }
+        for (int yy = threadIdx.x; yy <= C; yy += PICK_THREADS) hs_begin[yy] = yy * K1;
         for (int yy = threadIdx.x; yy < C; yy += PICK_THREADS) {
             int s = 0;
             for (int a = 0; a < K1; ++a) s += cj[yy * K1 + a];
@@ -134,19 +139,20 @@ extern "C" int prb_pick_scatter(const double *records, int n_rec, int32_t *gene_
                                 int64_t P_local, const uint32_t *col_packed,
                                 const int64_t *col_begin, const int64_t *col_end,
                                 const int32_t *newpos, uint8_t *sx, const int32_t *cnt_all, int C,
-                                int K, int32_t *hsize, int32_t *hs_ysum, int32_t *ha,
-                                int32_t *counters, int n_counters, prb_stream_t stream)
+                                int K, int32_t *hsize, int32_t *hs_begin, int32_t *hs_y,
+                                int32_t *hs_ysum, int32_t *ha, int32_t *counters, int n_counters,
+                                prb_stream_t stream)
 {
     PRB_REQUIRE(n_rec >= 0 && (n_rec == 0 || records != nullptr), "bad candidate records");
-    PRB_REQUIRE(C >= 1 && K >= 2 && K <= 5, "the V-layout path needs 2 <= K <= 5");
+    PRB_REQUIRE(C >= 1 && K >= 2 && K <= 21, "the V-layout path needs 2 <= K <= 21");
     PRB_REQUIRE(gene_ptr && col_packed && col_begin && col_end && sx && cnt_all && hsize &&
-                    hs_ysum && ha,
+                    hs_begin && hs_y && hs_ysum && ha,
                 "null pointer");
     PRB_REQUIRE(n_rec == 0 || (S_out && n_sel_ptr && selected), "commit targets are required");
     k_pick_scatter<<<devinfo().sm_count * 4, PICK_THREADS, 0, S(stream)>>>(
         records, n_rec, gene_ptr, S_out, n_sel_ptr, selected, gene_lo, P_local, col_packed,
-        col_begin, col_end, newpos, sx, cnt_all, C, K - 1, hsize, hs_ysum, ha, counters,
-        counters ? n_counters : 0);
+        col_begin, col_end, newpos, sx, cnt_all, C, K - 1, hsize, hs_begin, hs_y, hs_ysum, ha,
+        counters, counters ? n_counters : 0);
     PRB_LAUNCH_CHECK("k_pick_scatter");
     return 0;
 }

@@ -25,7 +25,7 @@
 // CTA per SM; (super-tile, fixed-size row range) work items claimed dynamically per warp.
 #include <stdlib.h>
 
-#include "common.cuh"
+#include "vcommon.cuh"
 
 namespace prb {
 
@@ -40,60 +40,6 @@ struct VCfg {
     static constexpr int ctl_bytes = 256;  // s_flag + per-segment class offsets
     static constexpr int smem_bytes = SPAN + ring_bytes + WARPS * STAGES * 8 + ctl_bytes;
 };
-
-__device__ __forceinline__ uint32_t v_smem_u32(const void *p)
-{
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void v_mbar_init(uint32_t bar, int count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void v_bulk_load(uint32_t dst, const void *src, uint32_t bytes,
-                                            uint32_t bar)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
-                 : "memory");
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-        ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
-        : "memory");
-}
-__device__ __forceinline__ void v_mbar_wait(uint32_t bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(bar), "r"(parity)
-        : "memory");
-}
-
-// Shared-window address of the first byte of dynamic shared memory in a kernel without
-// static shared memory (sm_100: 1 KB of the window is reserved by the system).  The kernel
-// traps if the assumption does not hold.
-constexpr int V_SMEM_BASE = 1024;
-
-// shift code of the cell whose index (< SPAN) is idx: the tile is the first SPAN bytes of
-// dynamic shared memory, so the address is idx + an immediate (no add instruction)
-__device__ __forceinline__ uint32_t v_probe(uint32_t idx)
-{
-    uint32_t r;
-    asm volatile("ld.shared.u8 %0, [%1 + %2];" : "=r"(r) : "r"(idx), "n"(V_SMEM_BASE));
-    return r;
-}
-
-// PTX shl clamps: a shift amount >= 32 gives 0 (the shift code of a cell with x_j = 0).
-__device__ __forceinline__ uint32_t v_shl1(uint32_t s)
-{
-    uint32_t r;
-    asm("shl.b32 %0, 1, %1;" : "=r"(r) : "r"(s));
-    return r;
-}
 
 // the two 16-bit entries of a V16 word
 __device__ __forceinline__ uint32_t v_pair(uint32_t w)
@@ -409,8 +355,11 @@ __global__ void __launch_bounds__(VL_THREADS)
 k_vscatter(const uint32_t *__restrict__ packed, const int64_t *__restrict__ indptr, int64_t P,
            const uint32_t *__restrict__ cellmap, const uint16_t *__restrict__ seg16, int n_seg,
            int K1, const int32_t *__restrict__ seglen, const int32_t *__restrict__ run_end,
-           const uint32_t *__restrict__ seg_pad, uint32_t *__restrict__ vpacked, int *queue)
+           const uint32_t *__restrict__ seg_pad, uint32_t *__restrict__ vpacked, int *queue,
+           const int64_t *__restrict__ run_start)
 {
+    // run_start != NULL (E16 only): FLAT output for vell.cu — run (vg, s) starts at entry
+    // run_start[vg * n_seg + s] of a 16-bit array, runs back to back, no padding
     extern __shared__ __align__(8) unsigned char vs_raw[];
     __shared__ int s_gene;
     __shared__ int s_wsum[VL_WARPS];
@@ -431,8 +380,12 @@ k_vscatter(const uint32_t *__restrict__ packed, const int64_t *__restrict__ indp
         const int64_t b = indptr[g], e = indptr[g + 1];
         constexpr int EPR_LOG = E16 ? 6 : 5, EPR = 1 << EPR_LOG;  // entries per 128-byte row
         for (int i = tid; i < nk; i += VL_THREADS) {
-            const int nr = (seglen[g * nk + i] + EPR - 1) >> EPR_LOG;
-            next[i] = (int64_t)(run_end[g * nk + i] - nr) * EPR;
+            if (run_start) {
+                next[i] = run_start[g * nk + i];
+            } else {
+                const int nr = (seglen[g * nk + i] + EPR - 1) >> EPR_LOG;
+                next[i] = (int64_t)(run_end[g * nk + i] - nr) * EPR;
+            }
             ccnt[i] = 0;
         }
         __syncthreads();
@@ -504,6 +457,7 @@ k_vscatter(const uint32_t *__restrict__ packed, const int64_t *__restrict__ indp
             __syncthreads();
         }
         // padding up to the end of the run's last row
+        if (!run_start)
         for (int i = tid; i < nk; i += VL_THREADS) {
             const int s = i % n_seg;
             const int64_t end = (int64_t)run_end[g * nk + i] * EPR;
@@ -587,7 +541,7 @@ extern "C" int prb_v_count(const uint32_t *packed, const int64_t *indptr, int64_
                            int32_t *queue, prb_stream_t stream)
 {
     if (P == 0) return 0;
-    PRB_REQUIRE(K1 >= 1 && K1 <= 4 && n_seg >= 1, "bad arguments");
+    PRB_REQUIRE(K1 >= 1 && K1 <= 20 && n_seg >= 1, "bad arguments");
     PRB_REQUIRE(n_seg == 1 || seg16 != nullptr || (cellmap != nullptr && n_seg <= 256),
                 "the segment of every cell is required (cellmap bits 24..31, or seg16)");
     PRB_REQUIRE(n_seg <= 65536, "too many segments");
@@ -606,10 +560,11 @@ template <bool E16>
 static int v_scatter_impl(const uint32_t *packed, const int64_t *indptr, int64_t P,
                           const uint32_t *cellmap, const uint16_t *seg16, int n_seg, int K1,
                           const int32_t *seglen, const int32_t *run_end, const uint32_t *seg_pad,
-                          uint32_t *vpacked, int32_t *queue, prb_stream_t stream)
+                          uint32_t *vpacked, int32_t *queue, prb_stream_t stream,
+                          const int64_t *run_start = nullptr)
 {
     if (P == 0) return 0;
-    PRB_REQUIRE(K1 >= 1 && K1 <= 4 && n_seg >= 1, "bad arguments");
+    PRB_REQUIRE(K1 >= 1 && K1 <= (run_start ? 20 : 4) && n_seg >= 1, "bad arguments");
     PRB_REQUIRE(n_seg == 1 || seg16 != nullptr || (cellmap != nullptr && n_seg <= 256),
                 "the segment of every cell is required (cellmap bits 24..31, or seg16)");
     PRB_REQUIRE(n_seg <= 65536 / K1, "too many segments");
@@ -622,7 +577,7 @@ static int v_scatter_impl(const uint32_t *packed, const int64_t *indptr, int64_t
     const int grid = (int)hmin(P, (int64_t)devinfo().sm_count * 8);
     k_vscatter<E16><<<grid, VL_THREADS, smem, S(stream)>>>(packed, indptr, P, cellmap, seg16, n_seg,
                                                            K1, seglen, run_end, seg_pad, vpacked,
-                                                           queue);
+                                                           queue, run_start);
     PRB_LAUNCH_CHECK("k_vscatter");
     return 0;
 }
@@ -646,6 +601,18 @@ extern "C" int prb_v_scatter16(const uint32_t *packed, const int64_t *indptr, in
 {
     return v_scatter_impl<true>(packed, indptr, P, cellmap, seg16, n_seg, K1, seglen, run_end,
                                 seg_pad, vpacked, queue, stream);
+}
+
+// FLAT variant for the lane-run layout (vell.cu): relabelled 16-bit entries (the cell id inside
+// its super-tile) of run (vg, s) at tmp16[run_start[vg * n_seg + s] ..), in arbitrary order.
+extern "C" int prb_v_scatter_flat(const uint32_t *packed, const int64_t *indptr, int64_t P,
+                                  const uint32_t *cellmap, const uint16_t *seg16, int n_seg,
+                                  int K1, const int32_t *seglen, const int64_t *run_start,
+                                  uint16_t *tmp16, int32_t *queue, prb_stream_t stream)
+{
+    PRB_REQUIRE(run_start != nullptr && tmp16 != nullptr, "null pointer");
+    return v_scatter_impl<true>(packed, indptr, P, cellmap, seg16, n_seg, K1, seglen, nullptr,
+                                nullptr, (uint32_t *)tmp16, queue, stream, run_start);
 }
 
 template <int EPW>

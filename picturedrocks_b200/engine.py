@@ -25,11 +25,14 @@ from . import _native as nat
 from . import vplan
 
 _I16_MAX_BINS = 65536
-# K <= 5: the V layout (cells relabelled by class) + register counters (csrc/vstream.cu);
-# PRB_NO_VLAYOUT=1 forces the generic shared-histogram kernel (csrc/stream.cu) everywhere
+# K <= 21: the V layouts (cells relabelled by class, register counters): the lane-run layout
+# of csrc/vell.cu (default) or, for K <= 5, the warp-per-run layout of csrc/vstream.cu
+# (PRB_V_KERNEL=rows).  PRB_NO_VLAYOUT=1 forces the generic shared-histogram kernel
+# (csrc/stream.cu) everywhere.
 USE_VLAYOUT = os.environ.get("PRB_NO_VLAYOUT", "0") != "1"
+ELL_MAX_K1 = 20
 PACKED_PAD = 4  # words of slack after the last stored entry
-SX_NONE = 64    # csrc/common.cuh PRB_SX_NONE: shift code of a cell with x_j = 0
+SX_NONE = 255   # csrc/common.cuh PRB_SX_NONE: shift code of a cell with x_j = 0
 
 
 def _i32(x):
@@ -91,12 +94,17 @@ class Engine:
         self.n_hs_dev = torch.zeros(1, dtype=torch.int32, device=dev)
         self.counters = torch.zeros(8192, dtype=torch.int32, device=dev)
         self.ticket = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.ell_dbg = torch.zeros(16, dtype=torch.int32, device=dev)  # see prb_stream_ell
         self._plans = {}
         self._tps = {}
-        self.vmode = USE_VLAYOUT and self.K1 <= 4
-        # the V layout with 16-bit entries, 64 per row (prb_v_scatter16 / prb_stream_v16);
+        kern = os.environ.get("PRB_V_KERNEL", "ell")
+        self.ell = USE_VLAYOUT and self.K1 <= ELL_MAX_K1 and (kern != "rows" or self.K1 > 4)
+        self.vmode = USE_VLAYOUT and (self.ell or self.K1 <= 4)
+        # warp-per-run layout: 16-bit entries, 64 per row (prb_v_scatter16 / prb_stream_v16);
         # PRB_V16=0 selects the 32-bit entries of round 1 (1.40 vs 1.80 ms at config 4)
-        self.v16 = self.vmode and os.environ.get("PRB_V16", "1") == "1"
+        self.v16 = self.vmode and not self.ell and os.environ.get("PRB_V16", "1") == "1"
+        if self.vmode:
+            nat.call("prb_v_check_smem_base")
         self.v = None  # V layout (csrc/vstream.cu), built lazily for the current labels
         self.newpos = None    # V path: int32[N] new position of every cell (None = identity)
         self.y_sorted = None  # V path: labels in the new order
@@ -273,6 +281,8 @@ class Engine:
         P, K1, n_seg, dev = self.P, self.K1, pl["n_seg"], self.device
         newpos = self.newpos if self.has_y else None
         PV = max(P * K1, 1)
+        if n_seg * K1 > 65536:
+            raise NotImplementedError("too many cell segments")
         seglen = torch.zeros(PV * n_seg, dtype=torch.int32, device=dev)
         # per-cell table of the two layout kernels, indexed by the ORIGINAL cell id:
         # bits 0..23 relabelled position, bits 24..31 segment (seg16 when there are > 256)
@@ -291,6 +301,8 @@ class Engine:
                     seg16 = seg.to(torch.int16)  # bit pattern of a uint16
         nat.call("prb_v_count", nat.ptr(self.packed), nat.ptr(self.indptr), P, nat.ptr(cellmap),
                  nat.ptr(seg16), n_seg, K1, nat.ptr(seglen), nat.ptr(self.counters), nat.stream())
+        if self.ell:
+            return self._build_ell(pl, seglen, cellmap, seg16)
         # rows of every run, scanned in storage order: (super-tile, virtual gene, segment)
         span = nat.load().prb_v_tile_span()
         cell0, st = pl["cell0"], pl["st"]
@@ -346,6 +358,57 @@ class Engine:
         self.epoch += 1
         return self.v
 
+    def _build_ell(self, pl, seglen, cellmap, seg16):
+        """The lane-run layout of csrc/vell.cu from the run lengths seglen[P*K1][n_seg]: flat
+        run-major scratch -> runs cut into lane-runs of at most CAP entries -> sorted by
+        (super-tile, length descending) -> bundles of 32 -> transposed rows; work items =
+        ranges of whole bundles."""
+        P, K1, n_seg, dev = self.P, self.K1, pl["n_seg"], self.device
+        n_st, st, cell0 = pl["n_st"], pl["st"], pl["cell0"]
+        i64 = dict(dtype=torch.int64, device=dev)
+        span = 1 << 16
+        lens = seglen[: P * K1 * n_seg].to(torch.int64)
+        n_runs = lens.numel()
+        run_start = torch.cumsum(lens, 0) - lens
+        total = int(lens.sum().item()) if n_runs else 0
+        assert total == self.nnz
+        tmp = torch.empty(total + 16, dtype=torch.int16, device=dev)
+        nat.call("prb_v_scatter_flat", nat.ptr(self.packed), nat.ptr(self.indptr), P,
+                 nat.ptr(cellmap), nat.ptr(seg16), n_seg, K1, nat.ptr(seglen), nat.ptr(run_start),
+                 nat.ptr(tmp), nat.ptr(self.counters), nat.stream())
+        warps = nat.load().prb_ell_warps()
+        R = vplan.item_rows(total // 64 + 1, warps, int(os.environ.get("PRB_V_ITEM_ROWS", 0)))
+        cap = int(os.environ.get("PRB_ELL_CAP", 0)) or 1024
+        cap = min(cap, 32768) & ~1
+        ep = vplan.ell_plan(lens, run_start, n_seg, st, cap)
+        n_bundles, brow0, nb_t, tile_b0 = ep["n_bundles"], ep["brow0"], ep["nb_t"], ep["tile_b0"]
+        lr_src, lr_len, lr_hdr = ep["lr_src"], ep["lr_len"], ep["lr_hdr"]
+        del ep
+        rows = int(brow0[-1].item())
+        if rows >= (1 << 31):
+            raise NotImplementedError("more than 2^31 rows in the lane-run layout")
+        brow0 = brow0.to(torch.int32)
+        # padding entries point at the cell slot just past the bundle's super-tile
+        pad_t = torch.tensor([cell0[st[t + 1]] & (span - 1) for t in range(n_st)], **i64)
+        bundle_pad = torch.repeat_interleave(pad_t, nb_t).to(torch.int16)
+        ell = torch.empty(rows * 32 + PACKED_PAD, dtype=torch.int32, device=dev)
+        bhdr = torch.empty(max(n_bundles, 1) * 32, dtype=torch.int32, device=dev)
+        nat.call("prb_ell_build", nat.ptr(tmp), nat.ptr(lr_src), nat.ptr(lr_len), nat.ptr(lr_hdr),
+                 nat.ptr(brow0), nat.ptr(bundle_pad), n_bundles, nat.ptr(ell), nat.ptr(bhdr),
+                 nat.stream())
+        # work items: ranges of whole bundles with about R rows (large first, small last)
+        tb = torch.cat([tile_b0, tile_b0.new_tensor([n_bundles])]).cpu().numpy()
+        item_off, item_b0 = vplan.ell_items(brow0.cpu().numpy().astype(np.int64), tb, R)
+        torch.cuda.current_stream().synchronize()  # tmp / lr_* are released below
+        del tmp, lr_src, lr_len, lr_hdr
+        self.v = dict(plan=pl, kind="ell", ell=ell, bhdr=bhdr, brow0=brow0, n_bundles=n_bundles, seglen=seglen,
+                      rows=rows, relabelled=self.has_y, item_rows=R, cap=cap, n_items=int(item_off[-1]),
+                      item_b0=torch.from_numpy(item_b0).to(dev),
+                      item_off=torch.from_numpy(item_off).to(dev))
+        self.sx.fill_(SX_NONE)
+        self.epoch += 1
+        return self.v
+
     def _v(self):
         return self.v if self.v is not None else self._build_v()
 
@@ -383,6 +446,15 @@ class Engine:
     def _stream_v_launch(self, with_y, C, hits):
         v = self._v()
         pl = v["plan"]
+        if self.ell:
+            nat.call("prb_stream_ell", nat.ptr(v["ell"]), nat.ptr(v["bhdr"]), nat.ptr(v["brow0"]),
+                     v["n_bundles"],
+                     self.K1, nat.ptr(pl["st_seg0"]), nat.ptr(pl["seg_cell0"]),
+                     nat.ptr(pl["seg_class"]) if with_y else None, pl["n_st"], pl["max_cells"],
+                     nat.ptr(self.sx), C, nat.ptr(hits), nat.ptr(self.counters),
+                     nat.ptr(v["item_off"]), nat.ptr(v["item_b0"]), v["n_items"], 1,
+                     self.P * self.K1, nat.ptr(self.ell_dbg), nat.stream())
+            return
         nat.call("prb_stream_v16" if self.v16 else "prb_stream_v", nat.ptr(v["vpacked"]),
                  nat.ptr(v["run_end"]),
                  nat.ptr(v["tile_row0"]), pl["n_seg"], self.P, self.K1, v["rows"],
@@ -403,8 +475,9 @@ class Engine:
                  nat.ptr(sel.selected) if sel else None, _i32(self.gene_lo), self.P,
                  nat.ptr(self.col_packed), nat.ptr(self.col_begin), nat.ptr(self.col_end),
                  nat.ptr(newpos), nat.ptr(self.sx), nat.ptr(self.cnt_all(with_y)), C, self.K,
-                 nat.ptr(self.hsize), nat.ptr(self.hs_ysum), nat.ptr(self.ha),
-                 nat.ptr(self.counters), v["plan"]["n_st"], nat.stream())
+                 nat.ptr(self.hsize), nat.ptr(self.hs_begin), nat.ptr(self.hs_y),
+                 nat.ptr(self.hs_ysum), nat.ptr(self.ha), nat.ptr(self.counters),
+                 v["plan"]["n_st"], nat.stream())
 
     def fused_step(self, sel, kind, is_remove, pick):
         """One greedy step of a selector on the V path, three launches, no host sync:

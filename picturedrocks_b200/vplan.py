@@ -65,3 +65,79 @@ def item_cuts(lo, hi, R):
             pos = int(parts[-1][-1]) + size
     return np.concatenate(parts) if parts else np.zeros(0, dtype=np.int64)
 
+
+
+def ell_plan(lens, run_start, n_seg, st, cap):
+    """Index plan of the lane-run layout (csrc/vell.cu), torch tensors on the device of `lens`.
+    lens int64[n_runs]: entries of run (vg, s) at index vg * n_seg + s; run_start int64[n_runs]:
+    its first entry in the flat run-major scratch; st: super-tile t = segments [st[t], st[t+1]);
+    cap: entries per lane-run (even).
+    Every run is cut into ceil(len / cap) lane-runs of nearly equal length; the lane-runs of a
+    super-tile are sorted by length (descending) and grouped 32 at a time into bundles of
+    ceil(longest / 2) rows.  Returns a dict: n_bundles; brow0 int64
+    [n_bundles+1] first row of every bundle; nb_t / tile_b0 int64[n_st] bundles per tile and
+    the first one; lr_src int64 / lr_len int32 / lr_hdr int32 [32 * n_bundles] per lane: first
+    entry in the scratch, length, header word (segment-in-tile << 24 | vg; -1 = empty lane)."""
+    import torch
+
+    dev = lens.device
+    i64 = dict(dtype=torch.int64, device=dev)
+    n_st = len(st) - 1
+    n_runs = lens.numel()
+    nsub = (lens + (cap - 1)) // cap
+    n_lr = int(nsub.sum().item()) if n_runs else 0
+    first = torch.cumsum(nsub, 0) - nsub
+    run_of = torch.repeat_interleave(torch.arange(n_runs, **i64), nsub)
+    sub = torch.arange(n_lr, **i64) - first[run_of]
+    ln, ns = lens[run_of], nsub[run_of]
+    base = ln // torch.clamp(ns, min=1)
+    rem = ln - base * ns
+    sublen = base + (sub < rem).to(torch.int64)
+    src = run_start[run_of] + sub * base + torch.minimum(sub, rem)
+    seg = run_of % n_seg
+    st_t = torch.tensor(list(st), **i64)
+    seg_tile = torch.repeat_interleave(torch.arange(n_st, **i64), st_t[1:] - st_t[:-1])
+    tile = seg_tile[seg]
+    hdr = ((seg - st_t[tile]) << 24) | (run_of // n_seg)
+    del run_of, sub, ln, ns, base, rem, seg
+    order = torch.argsort((tile << 32) | ((1 << 32) - 1 - sublen))
+    tile_s = tile[order]
+    cnt_t = torch.bincount(tile, minlength=n_st)
+    nb_t = (cnt_t + 31) // 32
+    tile_b0 = torch.cumsum(nb_t, 0) - nb_t
+    n_bundles = int(nb_t.sum().item())
+    lr0_t = torch.cumsum(cnt_t, 0) - cnt_t
+    slot = tile_b0[tile_s] * 32 + (torch.arange(n_lr, **i64) - lr0_t[tile_s])
+    n_slots = max(n_bundles, 1) * 32
+    lr_src = torch.zeros(n_slots, **i64)
+    lr_len = torch.zeros(n_slots, dtype=torch.int32, device=dev)
+    lr_hdr = torch.full((n_slots,), -1, dtype=torch.int32, device=dev)
+    lr_src[slot] = src[order]
+    lr_len[slot] = sublen[order].to(torch.int32)
+    lr_hdr[slot] = hdr[order].to(torch.int32)
+    L = (lr_len.view(-1, 32)[:n_bundles, 0].to(torch.int64) + 1) // 2  # lane 0 is the longest
+    brow0 = torch.zeros(n_bundles + 1, **i64)
+    torch.cumsum(L, 0, out=brow0[1:])
+    return dict(n_bundles=n_bundles, brow0=brow0, nb_t=nb_t, tile_b0=tile_b0, lr_src=lr_src,
+                lr_len=lr_len, lr_hdr=lr_hdr)
+
+
+def ell_items(brow0, tile_b, R):
+    """Work items of the lane-run kernel: ranges of whole bundles of one super-tile with about R
+    rows (item_cuts: large first, small last).  brow0 int64[n_bundles+1] (host), tile_b
+    [n_st+1] first bundle of every tile.  Returns (item_off int32[n_st+1], item_b0 int32
+    [n_items + n_st]): the first bundles of tile t's items, then one sentinel (= tile_b[t+1])."""
+    item_off, item_b0 = [0], []
+    for t in range(len(tile_b) - 1):
+        b_lo, b_hi = int(tile_b[t]), int(tile_b[t + 1])
+        bcut = np.zeros(0, dtype=np.int64)
+        if b_hi > b_lo:
+            cuts = item_cuts(int(brow0[b_lo]), int(brow0[b_hi]), R)
+            bcut = np.unique(np.searchsorted(brow0[b_lo:b_hi], cuts, side="left") + b_lo)
+            bcut = bcut[bcut < b_hi]
+            if bcut.size == 0 or bcut[0] != b_lo:
+                bcut = np.concatenate([[b_lo], bcut])
+        item_b0.append(bcut)
+        item_b0.append(np.array([b_hi], dtype=np.int64))
+        item_off.append(item_off[-1] + bcut.size)
+    return np.asarray(item_off, dtype=np.int32), np.concatenate(item_b0).astype(np.int32)

@@ -32,11 +32,11 @@ def main():
     eng, yd = make_spec(w).device_engine(0, w["P"])
     ref_S = None
     for knobs in sets:
-        for k in [k for k in os.environ if k.startswith("PRB_V_")]:
+        for k in [k for k in os.environ if k.startswith("PRB_V_") or k.startswith("PRB_ELL_")]:
             del os.environ[k]
         for kv in filter(None, knobs.split(",")):
             k, v = kv.split("=")
-            os.environ["PRB_V_" + k] = v
+            os.environ[("PRB_" if k.startswith("ELL_") else "PRB_V_") + k] = v
         eng.v = None
         eng.epoch += 1
         inf = pr.markers.SparseInformationSet._from_engine(eng, yd)
@@ -58,9 +58,10 @@ def main():
         if ref_S is None:
             ref_S = S
         v = eng.v
-        print("%-44s step %.4f ms  k_stream_v %.4f ms  rows %d items %d R %d tiles %d segs %d %s"
+        print("%-44s step %.4f ms  kernel %.4f ms  rows %d items %d R %d cap %s tiles %d segs %d %s"
               % (knobs or "(default)", step_ms, k_ms, v["rows"], v["n_items"], v["item_rows"],
-                 v["plan"]["n_st"], v["plan"]["n_seg"], "same S" if S == ref_S else "S DIFFERS"),
+                 v.get("cap"), v["plan"]["n_st"], v["plan"]["n_seg"],
+                 "same S" if S == ref_S else "S DIFFERS"),
               flush=True)
         del fs, inf
 

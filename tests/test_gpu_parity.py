@@ -360,20 +360,23 @@ def test_class_sorted_cells_and_v_layout(pr, O, monkeypatch, tile_cells, vlayout
     assert np.array_equal(Xg.indices, Xs.indices) and np.array_equal(Xg.data, Xs.data)
 
 
-@pytest.mark.parametrize("v16", ["1", "0"])
+@pytest.mark.parametrize("layout", ["ell", "ell-cap64", "rows16", "rows32"])
 @pytest.mark.parametrize("tile_cells", [None, 4096])
-def test_v_layout_entry_widths(pr, O, monkeypatch, tile_cells, v16):
-    """Both entry widths of the V layout — 16-bit entries, 64 per row (the default:
-    prb_v_scatter16 / prb_stream_v16) and the 32-bit words of round 1 (PRB_V16=0): entropies,
-    scores and sequences bit-identical to the oracle."""
+def test_v_layout_variants(pr, O, monkeypatch, tile_cells, layout):
+    """The streamed layouts of the K <= 5 path — lane-runs (csrc/vell.cu, the default; also with
+    lane-runs cut at 64 entries) and warp-per-run rows with 16- or 32-bit entries
+    (csrc/vstream.cu): entropies, scores and sequences bit-identical to the oracle."""
     from picturedrocks_b200.synth import DiscretisedSpec
 
-    monkeypatch.setenv("PRB_V16", v16)
+    monkeypatch.setenv("PRB_V_KERNEL", "ell" if layout.startswith("ell") else "rows")
+    monkeypatch.setenv("PRB_V16", "0" if layout == "rows32" else "1")
+    if layout == "ell-cap64":
+        monkeypatch.setenv("PRB_ELL_CAP", "64")
     if tile_cells:
         monkeypatch.setenv("PRB_V_TILE_CELLS", str(tile_cells))
     spec = DiscretisedSpec(N=70001, P=301, C=7, K=5, mean_density=0.09, seed=12)  # two 64 K tiles
     eng, yd = spec.device_engine()
-    assert eng.v16 == (v16 == "1")
+    assert eng.ell == layout.startswith("ell") and eng.v16 == (layout == "rows16")
     inf = pr.markers.SparseInformationSet._from_engine(eng, yd)
     y = spec.cpu_labels()
     ora = O.SparseInformationSet(spec.cpu_csc(range(spec.P), y), y)
@@ -381,6 +384,29 @@ def test_v_layout_entry_widths(pr, O, monkeypatch, tile_cells, v16):
         c = np.array(cols, dtype=np.int64)
         assert np.array_equal(inf.entropy_wrt(c), ora.entropy_wrt(c)), cols
     for kind in ("CIFE", "JMI", "CIFEUnsup"):
+        a, b = getattr(pr.markers, kind)(inf), getattr(O, kind)(ora)
+        a.autoselect(9)
+        b.autoselect(9)
+        assert a.S == [int(s) for s in b.S], kind
+        assert np.array_equal(a.score, b.score), kind
+
+
+@pytest.mark.parametrize("K,C", [(6, 3), (10, 20), (17, 5), (20, 20), (21, 2)])
+def test_lane_run_layout_more_bins(pr, O, K, C):
+    """K = 6..21 bins on the lane-run layout (2..5 counter registers per lane, csrc/vell.cu):
+    the K > 5 points of BASELINE config 5 no longer go through the shared-histogram kernel."""
+    from picturedrocks_b200.synth import DiscretisedSpec
+
+    spec = DiscretisedSpec(N=30011, P=211, C=C, K=K, mean_density=0.12, seed=K)
+    eng, yd = spec.device_engine()
+    assert eng.ell and eng.vmode
+    inf = pr.markers.SparseInformationSet._from_engine(eng, yd)
+    y = spec.cpu_labels()
+    ora = O.SparseInformationSet(spec.cpu_csc(range(spec.P), y), y)
+    for cols in ([], [-1], [3], [-1, 3], [3, 7]):
+        c = np.array(cols, dtype=np.int64)
+        assert np.array_equal(inf.entropy_wrt(c), ora.entropy_wrt(c)), cols
+    for kind in ("JMI", "CIFEUnsup"):
         a, b = getattr(pr.markers, kind)(inf), getattr(O, kind)(ora)
         a.autoselect(9)
         b.autoselect(9)

@@ -72,3 +72,79 @@ def test_item_cuts_cover_the_block(lo, hi, R):
     if hi - lo > 64 * R:
         assert sizes[0] == R and sizes[-2] <= max(128, R // 4)
 
+
+
+def _emulate_lane_run_layout(lens, n_seg, st, cap, R, rng):
+    """numpy emulation of prb_v_scatter_flat + vplan.ell_plan + prb_ell_build + the item walk
+    of k_stream_ell: every entry of every run must be visited exactly once, by a lane whose
+    header names the run, through items that cover every bundle exactly once."""
+    import torch
+
+    lens_t = torch.from_numpy(lens.astype(np.int64))
+    run_start = torch.cumsum(lens_t, 0) - lens_t
+    total = int(lens.sum())
+    tmp = np.arange(total, dtype=np.int64)  # entry e of the scratch "is" the number e
+    ep = vplan.ell_plan(lens_t, run_start, n_seg, st, cap)
+    nb, brow0 = ep["n_bundles"], ep["brow0"].numpy()
+    lr_src, lr_len, lr_hdr = ep["lr_src"].numpy(), ep["lr_len"].numpy(), ep["lr_hdr"].numpy()
+    assert brow0[0] == 0 and np.all(np.diff(brow0) >= 1)
+    rows = int(brow0[-1])
+    ell = np.full((rows, 32, 2), -7, dtype=np.int64)  # prb_ell_build
+    hdr_rows = np.zeros((max(nb, 1), 32), dtype=np.int64)
+    for b in range(nb):
+        L = brow0[b + 1] - brow0[b]
+        n = lr_len[b * 32:(b + 1) * 32]
+        assert L == (n[0] + 1) // 2 and np.all(n <= n[0]) and n[0] <= cap
+        hdr_rows[b] = lr_hdr[b * 32:(b + 1) * 32]
+        for l in range(32):
+            e = tmp[lr_src[b * 32 + l]: lr_src[b * 32 + l] + n[l]]
+            col = np.full(2 * L, -1, dtype=np.int64)
+            col[: n[l]] = e
+            ell[brow0[b]: brow0[b + 1], l, :] = col.reshape(L, 2)
+    assert not np.any(ell == -7)
+    # items
+    tile_b = np.concatenate([ep["tile_b0"].numpy(), [nb]])
+    item_off, item_b0 = vplan.ell_items(brow0, tile_b, R)
+    seen_b = np.zeros(nb, dtype=np.int64)
+    owner = np.full(total, -1, dtype=np.int64)
+    n_st = len(st) - 1
+    for t in range(n_st):
+        for k in range(item_off[t + 1] - item_off[t]):
+            b0, b1 = item_b0[item_off[t] + t + k], item_b0[item_off[t] + t + k + 1]
+            assert tile_b[t] <= b0 < b1 <= tile_b[t + 1]
+            for b in range(b0, b1):
+                seen_b[b] += 1
+                for l in range(32):
+                    h = hdr_rows[b, l]
+                    ents = ell[brow0[b]: brow0[b + 1], l].reshape(-1)
+                    ents = ents[ents >= 0]
+                    if h == -1:
+                        assert ents.size == 0
+                        continue
+                    vg, seg_local = h & 0xFFFFFF, h >> 24
+                    run = vg * n_seg + st[t] + seg_local
+                    assert st[t] + seg_local < st[t + 1]
+                    assert np.all(owner[ents] == -1)
+                    owner[ents] = run
+    assert np.all(seen_b == 1)
+    want = np.repeat(np.arange(lens.size), lens)
+    assert np.array_equal(owner, want)
+    return rows, nb
+
+
+@pytest.mark.parametrize("cap,R", [(2, 32), (8, 32), (64, 96), (128, 32), (1024, 992)])
+def test_lane_run_plan_covers_every_entry_once(cap, R):
+    rng = np.random.RandomState(cap + R)
+    n_seg, st = 7, [0, 3, 4, 7]
+    PV = 53
+    lens = (rng.gamma(0.4, 60.0, PV * n_seg)).astype(np.int64)
+    lens[rng.rand(lens.size) < 0.3] = 0
+    lens[5] = 3000  # a run much longer than the cap
+    _emulate_lane_run_layout(lens, n_seg, st, cap, R, rng)
+
+
+def test_lane_run_plan_degenerate():
+    rng = np.random.RandomState(0)
+    _emulate_lane_run_layout(np.zeros(12, dtype=np.int64), 3, [0, 3], 64, 32, rng)  # empty matrix
+    _emulate_lane_run_layout(np.array([0, 0, 1, 0], dtype=np.int64), 2, [0, 1, 2], 64, 32, rng)
+    _emulate_lane_run_layout(np.full(40, 1, dtype=np.int64), 1, [0, 1], 2, 32, rng)
