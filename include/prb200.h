@@ -57,6 +57,18 @@ int prb_pack_csc(const int32_t *rows, const uint8_t *codes, int64_t nnz, uint32_
                  prb_stream_t stream);
 int prb_unpack_csc(const uint32_t *packed, int64_t nnz, int32_t *rows, uint8_t *codes,
                    prb_stream_t stream);
+/* Ingestion of a caller-held canonical CSC (csrc/ingest.cu): a range of n stored entries,
+ * row ids int32 | int64 (row_bytes 4 | 8), codes of any integer width (code_bytes 1|2|4|8,
+ * code_signed) -> packed words.  *flags (device int32, OR-ed): 1 row outside [0, N),
+ * 2 code outside [0, 255], 4 a stored zero (the reference's eliminate_zeros would drop it),
+ * 8 (prb_check_columns) rows not strictly ascending inside a gene (unsorted or duplicate:
+ * sum_duplicates would merge them).  Any flag: canonicalise on the host as the reference does
+ * (INFOSET:191-196) and pack again. */
+int prb_pack_chunk(const void *rows, int row_bytes, const void *codes, int code_bytes,
+                   int code_signed, int64_t n, int64_t N, uint32_t *packed, int32_t *flags,
+                   prb_stream_t stream);
+int prb_check_columns(const uint32_t *packed, const int64_t *indptr, int64_t P, int32_t *flags,
+                      prb_stream_t stream);
 /* column-major uint8 codes[P][ld] -> per-gene nnz (pass 1) and packed words (pass 2). */
 int prb_dense_count_nnz(const uint8_t *codes, int64_t N, int64_t P, int64_t ld,
                         int64_t *nnz_per_gene, prb_stream_t stream);

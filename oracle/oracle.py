@@ -292,13 +292,18 @@ class FlatSparseInformationSet(SparseInformationSet):
         self.set_y(y)
 
 
-def synth_csc(spec, gene_lo=0, gene_hi=None, nthreads=None):
-    """Genes [gene_lo, gene_hi) of a picturedrocks_b200.synth.DiscretisedSpec through
-    synth_cpu.c: (indptr int64, row ids int32, codes uint8, labels int64)."""
+def synth_csc(spec, gene_lo=0, gene_hi=None, nthreads=None, genes=None):
+    """Genes [gene_lo, gene_hi) — or the listed `genes` — of a
+    picturedrocks_b200.synth.DiscretisedSpec through synth_cpu.c:
+    (indptr int64, row ids int32, codes uint8, labels int64)."""
     L = lib()
     nthreads = host_cores() if nthreads is None else int(nthreads)
     gene_hi = spec.P if gene_hi is None else int(gene_hi)
     P = gene_hi - int(gene_lo)
+    ids = None
+    if genes is not None:
+        ids = np.ascontiguousarray(genes, dtype=np.int64)
+        P = ids.size
     y = np.empty(spec.N, dtype=np.int64)
     seed = ctypes.c_uint64(spec.seed & ((1 << 64) - 1))
     L.orc_synth_labels(_p(y, _i64p), ctypes.c_int64(spec.N), ctypes.c_int64(spec.C), seed)
@@ -307,14 +312,15 @@ def synth_csc(spec, gene_lo=0, gene_hi=None, nthreads=None):
     args = (_p(y, _i64p), ctypes.c_int64(spec.N), ctypes.c_int64(gene_lo), ctypes.c_int64(P),
             ctypes.c_int64(spec.C), ctypes.c_int64(spec.K), ctypes.c_uint32(spec.mean_q24), seed,
             _p(cum, u32p))
+    idp = _p(ids, _i64p) if ids is not None else None
     counts = np.zeros(P, dtype=np.int64)
-    assert L.orc_synth_count(*args, _p(counts, _i64p), ctypes.c_int(nthreads)) == 0
+    assert L.orc_synth_count(*args, _p(counts, _i64p), ctypes.c_int(nthreads), idp) == 0
     indptr = np.zeros(P + 1, dtype=np.int64)
     np.cumsum(counts, out=indptr[1:])
     rows = np.empty(int(indptr[-1]), dtype=np.int32)
     codes = np.empty(int(indptr[-1]), dtype=np.uint8)
     assert L.orc_synth_fill(*args, _p(indptr, _i64p), _p(rows, _i32p), _p(codes, _u8p),
-                            ctypes.c_int(nthreads)) == 0
+                            ctypes.c_int(nthreads), idp) == 0
     return indptr, rows, codes, y
 
 

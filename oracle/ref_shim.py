@@ -1,10 +1,11 @@
-"""Import shim for the REAL reference hot-path modules (build container only).
+"""Import shim for the REAL reference hot-path modules.
 
-TEST INFRASTRUCTURE — not part of the product.  `/root/reference` exists only in
-the authoring container; nothing run on the GPU box may import this module.  It
-is used by `tests/golden/make_golden.py` to generate golden vectors from the
-unmodified reference and by `tests/test_oracle_vs_reference.py` (skipped when
-the reference is absent) to pin the oracle restatement.
+TEST / BASELINE INFRASTRUCTURE — not part of the product.  The files are loaded from
+`/root/reference` (the authoring container) or, where that does not exist (the GPU box), from
+the travelling copy `oracle/_ref/` that `oracle/make_ref.py` makes of the same three files,
+unmodified.  Used by `tests/golden/make_golden.py` to generate golden vectors from the
+unmodified reference, by `tests/test_oracle_vs_reference.py` to pin the oracle restatement,
+and by `bench.py`'s CPU legs to time the reference's own numba path (`kind: "reference"`).
 
 `import picturedrocks` itself fails here (anndata/scanpy/plotly/umap absent,
 picturedrocks/__init__.py:7-10), so the three hot-path files are loaded with
@@ -27,13 +28,22 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("PRB_REFERENCE_ROOT", "/root/reference")
+_PROBE = "picturedrocks/markers/mutualinformation/infoset.py"
+
+
+def _find_root():
+    for root in (os.environ.get("PRB_REFERENCE_ROOT"), "/root/reference",
+                 os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")):
+        if root and os.path.isfile(os.path.join(root, _PROBE)):
+            return root
+    return "/root/reference"
+
+
+REF_ROOT = _find_root()
 
 
 def available():
-    return os.path.isfile(
-        os.path.join(REF_ROOT, "picturedrocks/markers/mutualinformation/infoset.py")
-    )
+    return os.path.isfile(os.path.join(REF_ROOT, _PROBE))
 
 
 def _stub(name, path):

@@ -79,17 +79,18 @@ static inline uint32_t code_at(const gene_params *gp, int64_t cell, int64_t c, i
     return code;
 }
 
-/* pass 1: stored entries of genes [gene_lo, gene_lo + P) */
+/* pass 1: stored entries of genes [gene_lo, gene_lo + P), or of the P listed genes when
+ * gene_ids is not NULL */
 int orc_synth_count(const int64_t *y, int64_t N, int64_t gene_lo, int64_t P, int64_t C, int64_t K,
                     uint32_t mean_q24, uint64_t seed, const uint32_t *cum, int64_t *nnz_per_gene,
-                    int nthreads)
+                    int nthreads, const int64_t *gene_ids)
 {
     if (C < 1 || C > 256 || K < 2 || K > 256) return 2;
     (void)nthreads;
 #pragma omp parallel for schedule(dynamic, 8) num_threads(nthreads > 0 ? nthreads : 1)
     for (int64_t g = 0; g < P; ++g) {
         gene_params gp;
-        gene_setup(&gp, gene_lo + g, C, mean_q24, seed);
+        gene_setup(&gp, gene_ids ? gene_ids[g] : gene_lo + g, C, mean_q24, seed);
         int64_t n = 0;
         for (int64_t i = 0; i < N; ++i) n += code_at(&gp, i, y[i], (int)K, cum) != 0;
         nnz_per_gene[g] = n;
@@ -100,14 +101,14 @@ int orc_synth_count(const int64_t *y, int64_t N, int64_t gene_lo, int64_t P, int
 /* pass 2: rows[indptr[g] ..] ascending cell ids, codes[..] their codes */
 int orc_synth_fill(const int64_t *y, int64_t N, int64_t gene_lo, int64_t P, int64_t C, int64_t K,
                    uint32_t mean_q24, uint64_t seed, const uint32_t *cum, const int64_t *indptr,
-                   int32_t *rows, uint8_t *codes, int nthreads)
+                   int32_t *rows, uint8_t *codes, int nthreads, const int64_t *gene_ids)
 {
     if (C < 1 || C > 256 || K < 2 || K > 256) return 2;
     (void)nthreads;
 #pragma omp parallel for schedule(dynamic, 8) num_threads(nthreads > 0 ? nthreads : 1)
     for (int64_t g = 0; g < P; ++g) {
         gene_params gp;
-        gene_setup(&gp, gene_lo + g, C, mean_q24, seed);
+        gene_setup(&gp, gene_ids ? gene_ids[g] : gene_lo + g, C, mean_q24, seed);
         int64_t o = indptr[g];
         for (int64_t i = 0; i < N; ++i) {
             const uint32_t c = code_at(&gp, i, y[i], (int)K, cum);

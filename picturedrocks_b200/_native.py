@@ -27,6 +27,8 @@ _SIGS = {
     "prb_term_table": [_i64, _vp],
     "prb_pack_csc": [_vp, _vp, _i64, _vp, _vp],
     "prb_unpack_csc": [_vp, _i64, _vp, _vp, _vp],
+    "prb_pack_chunk": [_vp, _int, _vp, _int, _int, _i64, _i64, _vp, _vp, _vp],
+    "prb_check_columns": [_vp, _vp, _i64, _vp, _vp],
     "prb_dense_count_nnz": [_vp, _i64, _i64, _i64, _vp, _vp],
     "prb_dense_fill_csc": [_vp, _i64, _i64, _i64, _vp, _vp, _vp],
     "prb_stream_plan": [_i64, _i64, _int, ctypes.POINTER(_i64), ctypes.POINTER(_int),
@@ -131,7 +133,7 @@ class PrbError(RuntimeError):
 
 # kernels launched per entry point (for bench.py's gpu_launches claim)
 KERNELS = {
-    "prb_pack_csc": 1, "prb_unpack_csc": 1, "prb_dense_count_nnz": 1, "prb_dense_fill_csc": 1,
+    "prb_pack_csc": 1, "prb_unpack_csc": 1, "prb_pack_chunk": 1, "prb_check_columns": 1, "prb_dense_count_nnz": 1, "prb_dense_fill_csc": 1,
     "prb_tile_ptrs": 1, "prb_stream_hits": 1,
     "prb_argmax_commit": 1, "prb_pick_scatter": 1, "prb_finalize_update": 1,
     "prb_v_unscatter": 1, "prb_best_record": 1, "prb_v_scatter_flat": 1, "prb_ell_build": 1,

@@ -39,6 +39,16 @@ def _i32(x):
     return ctypes.c_int32(int(x))
 
 
+class NotCanonical(ValueError):
+    """The CSC arrays handed to Engine.from_csc_arrays are not a canonical matrix of bin codes
+    (flags of csrc/ingest.cu: 1 row id out of range, 2 code outside [0, 255], 4 stored zero,
+    8 rows of a gene not strictly ascending)."""
+
+    def __init__(self, flags):
+        super().__init__("CSC arrays are not canonical (flags %d)" % flags)
+        self.flags = flags
+
+
 class Engine:
     def __init__(self, indptr, packed, N, K, gene_lo=0, P_total=None, comm=None, term=None):
         """indptr: int64[P+1] device tensor (local offsets, indptr[0] == 0);
@@ -683,28 +693,79 @@ class Engine:
 
     # ------------------------------------------------------------ constructors
     @classmethod
-    def from_csc_arrays(cls, indptr, indices, data, N, **kw):
-        """indptr int64[P+1], indices int32[nnz], data uint8[nnz]: host (numpy / pinned
-        torch) or device arrays of a canonical CSC matrix of bin codes."""
+    def from_csc_arrays(cls, indptr, indices, data, N, chunk_entries=None, **kw):
+        """A CSC matrix of bin codes as the caller holds it — indptr[P+1], row ids (int32 or
+        int64) and codes (any integer dtype) of the stored entries; numpy arrays / CPU tensors
+        (pinned or pageable) or device tensors — packed on the device (csrc/ingest.cu).
+        Host arrays are uploaded in chunks on a copy stream, double-buffered, and every chunk is
+        packed and validated while the next one is on the bus; the canonical-form check of
+        infoset.py:191-196 (sorted rows, no duplicates, no stored zeros) runs on the device too.
+        Raises NotCanonical when the caller has to canonicalise on the host first."""
         nat.require_cuda()
         dev = torch.device("cuda", torch.cuda.current_device())
 
-        def up(a, dt):
-            t = torch.from_numpy(np.ascontiguousarray(a)) if isinstance(a, np.ndarray) else a
-            return t.to(device=dev, dtype=dt, non_blocking=True).contiguous()
+        def as_tensor(a):
+            if isinstance(a, torch.Tensor):
+                return a
+            a = np.ascontiguousarray(a)
+            if a.dtype.kind == "u" and a.dtype.itemsize > 1:  # torch has no uint16/32/64 copies
+                a = a.view(np.dtype("i%d" % a.dtype.itemsize))
+            if a.dtype == np.bool_:
+                a = a.view(np.uint8)
+            return torch.from_numpy(a)
 
-        indptr_d = up(indptr, torch.int64)
-        rows_d = up(indices, torch.int32)
-        codes_d = up(data, torch.uint8)
-        nnz = rows_d.numel()
+        code_signed = int(not (isinstance(data, np.ndarray) and data.dtype.kind in "ub")
+                          and not (isinstance(data, torch.Tensor) and data.dtype == torch.uint8))
+        indptr_d = as_tensor(indptr).to(device=dev, dtype=torch.int64, non_blocking=True).contiguous()
+        rows_h, codes_h = as_tensor(indices), as_tensor(data)
+        if rows_h.dtype not in (torch.int32, torch.int64):
+            rows_h = rows_h.to(torch.int64)
+        if codes_h.dtype.is_floating_point:
+            raise AssertionError("X should be integer dtype")
+        nnz = rows_h.numel()
+        if nnz == 0:  # infoset.py:199 int(np.log2(X.max()) + 1) of an all-zero matrix
+            raise OverflowError("cannot convert float infinity to integer")
+        rb, cb = rows_h.element_size(), codes_h.element_size()
         packed = torch.empty(nnz + PACKED_PAD, dtype=torch.int32, device=dev)
         packed[nnz:].zero_()  # the slack words; everything below is written by the pack kernel
-        nat.call("prb_pack_csc", nat.ptr(rows_d), nat.ptr(codes_d), nnz, nat.ptr(packed),
-                 nat.stream())
+        flags = torch.zeros(1, dtype=torch.int32, device=dev)
+        ms = torch.cuda.current_stream()
+        if rows_h.is_cuda:
+            nat.call("prb_pack_chunk", nat.ptr(rows_h), rb, nat.ptr(codes_h), cb, code_signed, nnz,
+                     N, nat.ptr(packed), nat.ptr(flags), nat.stream())
+        else:
+            ce = int(chunk_entries or os.environ.get("PRB_INGEST_CHUNK", 1 << 25))
+            cs = torch.cuda.Stream()
+            stage = [(torch.empty(min(ce, nnz), dtype=rows_h.dtype, device=dev),
+                      torch.empty(min(ce, nnz), dtype=codes_h.dtype, device=dev)) for _ in range(2)]
+            copied = [torch.cuda.Event() for _ in range(2)]
+            packed_ev = [torch.cuda.Event() for _ in range(2)]
+            cs.wait_stream(ms)
+            for k, a in enumerate(range(0, nnz, ce)):
+                b, buf = min(a + ce, nnz), k % 2
+                sr, sc = stage[buf]
+                if k >= 2:
+                    cs.wait_event(packed_ev[buf])  # the staging buffer is free again
+                with torch.cuda.stream(cs):
+                    sr[: b - a].copy_(rows_h[a:b], non_blocking=True)
+                    sc[: b - a].copy_(codes_h[a:b], non_blocking=True)
+                    copied[buf].record(cs)
+                ms.wait_event(copied[buf])
+                nat.call("prb_pack_chunk", nat.ptr(sr), rb, nat.ptr(sc), cb, code_signed, b - a, N,
+                         nat.ptr(packed) + 4 * a, nat.ptr(flags), nat.stream())
+                packed_ev[buf].record(ms)
+            for t in stage:  # (the allocator must not hand the buffers out before the copies ran)
+                t[0].record_stream(cs)
+                t[1].record_stream(cs)
+        nat.call("prb_check_columns", nat.ptr(packed), nat.ptr(indptr_d), indptr_d.numel() - 1,
+                 nat.ptr(flags), nat.stream())
         # host work while the (asynchronous) upload is in flight
         kw.setdefault("term", cls.host_term_table(N))
-        K = (int(codes_d.max().item()) + 1) if nnz else 1
-        return cls(indptr_d, packed, N, K, **kw)
+        kmax = packed.view(torch.uint8)[3: 4 * nnz: 4].max()
+        f = int(flags.item())
+        if f:
+            raise NotCanonical(f)
+        return cls(indptr_d, packed, N, int(kmax.item()) + 1, **kw)
 
     @classmethod
     def from_dense_codes(cls, codes, N, **kw):

@@ -16,7 +16,7 @@ import scipy.sparse
 import torch
 
 from ... import _native as nat
-from ...engine import Engine
+from ...engine import Engine, NotCanonical
 
 _DT = {np.dtype(np.float32): (0, torch.float32, torch.float32),
        np.dtype(np.float64): (1, torch.float64, torch.float64),
@@ -40,6 +40,8 @@ def discretize_to_device(X, k=5, gene_block=None):
     if isinstance(X, torch.Tensor):
         Xh = None
         Xd_full = X.to(dev)
+        if Xd_full.dtype.is_floating_point and Xd_full.dtype not in (torch.float32, torch.float64):
+            Xd_full = Xd_full.to(torch.float32)  # half / bfloat16: never truncate to integers
         np_dt = {torch.float32: np.float32, torch.float64: np.float64}.get(Xd_full.dtype, np.int64)
         N, P = Xd_full.shape
     else:
@@ -259,17 +261,27 @@ class SparseInformationSet:
     """
 
     def __init__(self, X, y=None, gene_lo=0, P_total=None, comm=None):
-        Xc = scipy.sparse.csc_matrix(X)
-        assert np.issubdtype(Xc.dtype, np.integer), "X should be integer dtype"
-        Xc.sum_duplicates()
-        Xc.eliminate_zeros()
-        assert Xc.has_canonical_format, "Sparse matrix not in canonical format"
-        _check_codes_u8(Xc.data)
-        self._X = Xc
+        # infoset.py:191-196.  A matrix that already is canonical CSC (the normal case) is
+        # taken as it is — its arrays are uploaded, packed and CHECKED on the device
+        # (csrc/ingest.cu); only a matrix that fails the check goes through scipy's
+        # sum_duplicates / eliminate_zeros on the host, as in the reference.
+        Xc = X if scipy.sparse.issparse(X) and X.format == "csc" else scipy.sparse.csc_matrix(X)
+        assert np.issubdtype(Xc.dtype, np.integer) or Xc.dtype == np.bool_, \
+            "X should be integer dtype"
         N, P = Xc.shape
-        eng = Engine.from_csc_arrays(Xc.indptr.astype(np.int64), Xc.indices.astype(np.int32),
-                                     Xc.data.astype(np.uint8), N, gene_lo=gene_lo,
-                                     P_total=P_total, comm=comm)
+        kw = dict(gene_lo=gene_lo, P_total=P_total, comm=comm)
+        try:
+            eng = Engine.from_csc_arrays(Xc.indptr, Xc.indices, Xc.data, N, **kw)
+        except NotCanonical as e:
+            if e.flags & 1:
+                raise ValueError("row index out of range")
+            Xc = Xc.copy()
+            Xc.sum_duplicates()
+            Xc.eliminate_zeros()
+            assert Xc.has_canonical_format, "Sparse matrix not in canonical format"
+            _check_codes_u8(Xc.data)
+            eng = Engine.from_csc_arrays(Xc.indptr, Xc.indices, Xc.data, N, **kw)
+        self._X = Xc
         self._attach(eng)
         self.set_y(y)
 

@@ -27,7 +27,10 @@ def test_reference_arm_prints_one_json_line():
     assert d["steps"] == 2 and d["warmup"] == 1 and d["n_gpus"] == 1
     assert d["value"] > 0 and d["ms_per_step"] > 0
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] == 1
+    assert cb["value"] == d["value"] and cb["sample"]
+    assert d["port_all_cores"]["cores"] >= 1 and d["port_all_cores"]["value"] > 0
+    assert set(d["config"]) == {"workload", "selector", "bins", "k"}
     e2e = d["e2e"]
     assert e2e["value"] == d["value"] and e2e["unit"] == d["unit"]
     assert e2e["h2d_bytes_per_step"] == 0 and e2e["d2h_bytes_per_step"] == 0

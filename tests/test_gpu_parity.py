@@ -558,3 +558,61 @@ def test_sparse_discretiser_pbmc_shaped_sample(pr, O):
     fs = pr.markers.CIFE(inf)
     fs.autoselect(3)
     assert len(set(fs.S)) == 3
+
+
+def test_ingestion_accepts_what_the_reference_accepts(pr, O, monkeypatch):
+    """SparseInformationSet(X, y): canonical CSC of any index / data width goes to the device
+    as it is (chunked upload, packed and checked there, csrc/ingest.cu); unsorted indices,
+    duplicates and stored zeros take the reference's host canonicalisation (infoset.py:191-196);
+    same entropies either way.  Codes above 255 are rejected."""
+    from picturedrocks_b200.synth import DiscretisedSpec
+
+    monkeypatch.setenv("PRB_INGEST_CHUNK", "50000")  # many chunks, both staging buffers reused
+    spec = DiscretisedSpec(N=20000, P=300, C=12, K=5, mean_density=0.06, seed=7)
+    y = spec.cpu_labels()
+    X = spec.cpu_csc(range(spec.P), y)  # canonical, int64 data, int32 indices
+    ora = O.SparseInformationSet(X, y)
+    cols = [np.array(c, dtype=np.int64) for c in ([], [-1], [5], [-1, 5])]
+    want = [ora.entropy_wrt(c) for c in cols]
+
+    def check(Xin):
+        inf = pr.markers.SparseInformationSet(Xin, y)
+        for c, w in zip(cols, want):
+            assert np.array_equal(inf.entropy_wrt(c), w)
+        return inf
+
+    inf = check(X)
+    assert inf.X is X  # canonical CSC is not copied
+    X8 = scipy.sparse.csc_matrix((X.data.astype(np.uint8), X.indices.astype(np.int64),
+                                  X.indptr.astype(np.int64)), shape=X.shape)
+    check(X8)
+    check(scipy.sparse.csr_matrix(X))  # cells-major input: converted by scipy
+    check(np.asarray(X.todense()))     # dense ndarray
+    # unsorted rows inside the genes
+    Xu = X.copy()
+    for g in range(0, spec.P, 7):
+        a, b = Xu.indptr[g], Xu.indptr[g + 1]
+        Xu.indices[a:b] = Xu.indices[a:b][::-1].copy()
+        Xu.data[a:b] = Xu.data[a:b][::-1].copy()
+    Xu.has_sorted_indices = False
+    inf = check(Xu)
+    assert inf.X.has_canonical_format
+    # duplicates (summed by the reference) and stored zeros (dropped)
+    coo = X.tocoo()
+    half = coo.data // 2
+    rows = np.concatenate([coo.row, coo.row, coo.row[:50]])
+    colsi = np.concatenate([coo.col, coo.col, coo.col[:50]])
+    vals = np.concatenate([coo.data - half, half, np.zeros(50, dtype=coo.data.dtype)])
+    Xd = scipy.sparse.csc_matrix(scipy.sparse.coo_matrix((vals, (rows, colsi)), shape=X.shape))
+    Xd2 = scipy.sparse.csc_matrix((np.concatenate([X.data, [0]]), np.concatenate([X.indices, [3]]),
+                                   np.concatenate([X.indptr[:-1], [X.indptr[-1] + 1]])),
+                                  shape=X.shape)  # an explicit zero at the end of the last gene
+    check(Xd)
+    if Xd2.indices[-2] < 3:
+        check(Xd2)
+    Xbig = X.copy()
+    Xbig.data[0] = 300
+    with pytest.raises(ValueError):
+        pr.markers.SparseInformationSet(Xbig, y)
+    with pytest.raises(OverflowError):
+        pr.markers.SparseInformationSet(scipy.sparse.csc_matrix((50, 4), dtype=np.int64))

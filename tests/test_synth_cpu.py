@@ -18,6 +18,11 @@ def test_c_generator_equals_numpy_recipe(K, C, lo, hi):
     assert np.array_equal(X.indptr, indptr)
     assert np.array_equal(X.indices, rows) and np.array_equal(X.data, codes)
     assert codes.min() >= 1 and codes.max() <= K - 1
+    pick = [hi - 1, lo, lo + 7]
+    ip2, r2, c2, _ = O.synth_csc(spec, genes=pick, nthreads=2)
+    X2 = spec.cpu_csc(pick, y)
+    assert np.array_equal(X2.indptr, ip2) and np.array_equal(X2.indices, r2)
+    assert np.array_equal(X2.data, c2)
 
 
 def test_flat_set_equals_scipy_set():
