@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define PRB_ABI_VERSION 2
+#define PRB_ABI_VERSION 3
 #define PRB_MAX_ROWS (1 << 24) /* cell id field of the packed CSC word */
 #define PRB_MAX_CODES 256      /* K <= 256 */
 
@@ -203,7 +203,8 @@ int prb_v_scatter_flat(const uint32_t *packed, const int64_t *indptr, int64_t P,
                        int32_t *queue, prb_stream_t stream);
 int prb_ell_build(const uint16_t *tmp16, const int64_t *lr_src, const int32_t *lr_len,
                   const uint32_t *lr_hdr, const int32_t *brow0, const uint16_t *bundle_pad,
-                  int64_t n_bundles, uint32_t *ell, uint32_t *bhdr, prb_stream_t stream);
+                  int64_t n_bundles, uint32_t *ell, uint32_t *bhdr, int hdr_in_stream,
+                  prb_stream_t stream);
 int prb_stream_ell(const uint32_t *ell, const uint32_t *bhdr, const int32_t *brow0,
                    int64_t n_bundles, int K1,
                    const int32_t *st_seg0, const int32_t *seg_cell0, const int32_t *seg_class,
@@ -213,6 +214,38 @@ int prb_stream_ell(const uint32_t *ell, const uint32_t *bhdr, const int32_t *bro
                    prb_stream_t stream);
 int prb_ell_warps(void);
 int prb_v_check_smem_base(void);
+
+/* ---- the hot loop on the STREAMED lane-run layout (vell2.cu) — the default ------------------
+ * Same lane-runs and bundles as above, laid out so that a warp needs nothing but its ring of
+ * bulk copies:
+ *  - super-tiles hold at most `tile_cells` cells (prb_ell2_geometry) and tile t owns the
+ *    positions [t * 32768, t * 32768 + cells) of a PADDED cell space: pos int32[N] replaces
+ *    newpos in prb_pick_scatter / prb_finalize_update / prb_v_unscatter, sx has n_st * 32768
+ *    slots, slot 32767 of every tile stays "x_j = 0" (what padding entries point at), and a
+ *    16-bit entry = pos & 0xFFFF addresses a 64 KB window of two consecutive tiles;
+ *  - prb_ell_build(.., hdr_in_stream = 1): brow0 counts STREAM rows — per bundle one header row
+ *    followed by its L data rows; header word of lane l = bit 31: bit l of L, bit 30: the
+ *    lane-run is a piece of a longer run, bits id_shift..29: the run's slot in a gene's block
+ *    of hits (its segment or its class), bits 0..id_shift-1: virtual gene (all ones = empty
+ *    lane); bhdr unused;
+ *  - the stream is cut on the host into one chunk of bundles per CTA, a chunk into phases
+ *    (the bundles of at most two consecutive tiles) and a phase into at most `max_items` work
+ *    items of decreasing size: item_row0 int32[n_items + 1] (first stream row of every item, the
+ *    items of all phases back to back), phase int32[n_phases][4] = {first tile, tiles (1 or 2),
+ *    first item, items}, cta_ph0 int32[n_ctas + 1].
+ * prb_stream_ell2, vmajor = 0: adds the joint counts to hits int32[P][n_slot][K-1][K-1];
+ * vmajor = 1: hits int32[P][n_slot][K-1][4 * ceil((K-1)/4)], x_j - 1 in the last dimension, all
+ * zero on entry — a lane-run that holds a whole run STORES its counts (16-byte writes), only
+ * the pieces of longer runs are added (and everything when always_add != 0: several runs share
+ * a slot).  The slot of a run is the id field of its header when n_slot > 1, else 0.
+ * PV = P*(K-1) < 2^id_shift - 1.
+ * timing: NULL, or device int64[n_items][2] that receives the start / end time (ns) of every
+ * work item (tuning runs, K <= 5). */
+int prb_ell2_geometry(int *tile_cells, int *ctas, int *warps, int *max_items);
+int prb_stream_ell2(const uint32_t *ell, const int32_t *item_row0, const int32_t *phase,
+                    const int32_t *cta_ph0, int n_ctas, const uint8_t *sx, int K1, int n_slot,
+                    int id_shift, int always_add, int32_t *hits, int vmajor, int64_t PV,
+                    int64_t *timing, prb_stream_t stream);
 
 /* ---- joint-state build ("master column", _sparse_make_master_col INFOSET:431-442) */
 /* Columns are addressed through col_begin / col_end int64[P]: first / past-the-last word of
@@ -256,11 +289,15 @@ int prb_finalize(int32_t *hits, const int32_t *cnt, const int64_t *classsizes,
                  double *out_full, double *out_marg, prb_stream_t stream);
 /* Same result for the DIRECT single-gene layout (state id = y*(K-1) + x_j - 1, as
  * written by prb_state_direct), one thread per gene; hits int32[P][C][K-1][K-1] or
- * NULL (then out_full = H(y, x_g), out_marg = H(x_g)). */
+ * NULL (then out_full = H(y, x_g), out_marg = H(x_g)).  vmajor != 0 (K <= 5): hits is
+ * int32[P][n_slot][K-1][4] with x_j - 1 in the last, padded dimension (what prb_stream_ell2
+ * stores); the slots of class y are [cls_slot0[y], cls_slot0[y+1]) — one per segment of the
+ * class, summed here — or the single slot y when cls_slot0 is NULL. */
 int prb_finalize_direct(int32_t *hits, const int32_t *cnt, const int64_t *classsizes,
                         const int32_t *hsize, const int32_t *hs_ysum, const int32_t *ha, int C,
                         int K, const double *table, int64_t N, int64_t P, double *out_full,
-                        double *out_marg, prb_stream_t stream);
+                        double *out_marg, int vmajor, const int32_t *cls_slot0, int n_slot,
+                        prb_stream_t stream);
 /* scalar entropy of a per-cell key vector through a count table (INFOSET:218-249,
  * 413-428): table int32[n_keys] scratch; out: device double. */
 int prb_entropy_keys(const uint32_t *mpacked, const int32_t *y, int64_t N, int mbits,
@@ -343,8 +380,8 @@ int prb_finalize_update(int32_t *hits, const int32_t *cnt, const int64_t *classs
                         const int32_t *gene_ptr, const int32_t *n_sel_ptr, int32_t gene_lo,
                         double *cand_score, int64_t *cand_idx, double *best, int32_t *ticket,
                         const uint32_t *col_packed, const int64_t *col_begin,
-                        const int64_t *col_end, const int32_t *newpos, uint8_t *sx,
-                        prb_stream_t stream);
+                        const int64_t *col_end, const int32_t *newpos, uint8_t *sx, int vmajor,
+                        const int32_t *cls_slot0, int n_slot, prb_stream_t stream);
 /* sx <- 255 at the stored entries of gene *gene_ptr (after a stand-alone streaming pass). */
 int prb_v_unscatter(const int32_t *gene_ptr, const uint32_t *col_packed, const int64_t *col_begin,
                     const int64_t *col_end, const int32_t *newpos, uint8_t *sx,

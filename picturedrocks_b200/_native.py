@@ -50,7 +50,11 @@ _SIGS = {
     "prb_pick_scatter": [_vp, _int, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
                          _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp],
     "prb_v_scatter_flat": [_vp, _vp, _i64, _vp, _vp, _int, _int, _vp, _vp, _vp, _vp, _vp],
-    "prb_ell_build": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
+    "prb_ell_build": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _int, _vp],
+    "prb_ell2_geometry": [ctypes.POINTER(_int), ctypes.POINTER(_int), ctypes.POINTER(_int),
+                          ctypes.POINTER(_int)],
+    "prb_stream_ell2": [_vp, _vp, _vp, _vp, _int, _vp, _int, _int, _int, _int, _vp, _int, _i64, _vp,
+                        _vp],
     "prb_stream_ell": [_vp, _vp, _vp, _i64, _int, _vp, _vp, _vp, _int, _i64, _vp, _int, _vp, _vp, _vp,
                        _vp, _i64, _int, _i64, _vp, _vp],
     "prb_ell_warps": [],
@@ -58,7 +62,7 @@ _SIGS = {
     "prb_finalize_update_blocks": [_i64, _int],
     "prb_finalize_update": [_vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _vp, _i64, _i64, _int, _int,
                             _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp,
-                            _vp, _vp, _vp, _vp, _vp, _vp],
+                            _vp, _vp, _vp, _vp, _vp, _int, _vp, _int, _vp],
     "prb_v_unscatter": [_vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "prb_best_record": [_vp, _vp, _i64, _vp, _vp],
     "prb_state_direct": [_vp, _vp, _i64, _int, _int, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp],
@@ -67,7 +71,7 @@ _SIGS = {
     "prb_finalize": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _vp, _i64, _i64,
                      _vp, _vp, _vp],
     "prb_finalize_direct": [_vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _vp, _i64, _i64, _vp, _vp,
-                            _vp],
+                            _int, _vp, _int, _vp],
     "prb_entropy_keys": [_vp, _vp, _i64, _int, _i64, _vp, _vp, _vp, _vp],
     "prb_mi_base": [_vp, _f64, _vp, _i64, _vp, _vp],
     "prb_selector_update": [_int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64,
@@ -121,7 +125,7 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = _RESTYPES.get(name, _int)
-    if lib.prb_abi_version() != 2:
+    if lib.prb_abi_version() != 3:
         raise ImportError("libprb200.so ABI version mismatch")
     _LIB = lib
     return lib
@@ -137,7 +141,7 @@ KERNELS = {
     "prb_tile_ptrs": 1, "prb_stream_hits": 1,
     "prb_argmax_commit": 1, "prb_pick_scatter": 1, "prb_finalize_update": 1,
     "prb_v_unscatter": 1, "prb_best_record": 1, "prb_v_scatter_flat": 1, "prb_ell_build": 1,
-    "prb_stream_ell": 1, "prb_v_count": 1, "prb_v_scatter": 1,
+    "prb_stream_ell": 1, "prb_stream_ell2": 1, "prb_v_count": 1, "prb_v_scatter": 1,
     "prb_stream_v": 1, "prb_scatter_gene_u8": 1,
     "prb_scatter_gene_or32": 1, "prb_state_direct": 2, "prb_state_table": 2, "prb_state_assign": 1, "prb_finalize": 1, "prb_finalize_direct": 1,
     "prb_entropy_keys": 2, "prb_mi_base": 1, "prb_selector_update": 1, "prb_argmax_blocks": 1,

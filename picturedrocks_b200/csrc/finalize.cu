@@ -374,16 +374,23 @@ struct SelFuse {
     uint8_t *sx;
 };
 
-template <int TK1, int L, bool SEL>
+// VM: hits is v-major, hits[g][slot][v][4] (x_j - 1 in the last, padded dimension: what the
+// streamed lane-run kernel of vell2.cu stores with one 16-byte write per run) instead of
+// hits[g][y][x_j - 1][v]; the slots of class y are [cls_slot0[y], cls_slot0[y+1]) — one per
+// segment of the class — or just y when cls_slot0 is NULL.
+template <int TK1, int L, bool SEL, bool VM>
 __global__ void __launch_bounds__(256)
 k_finalize_direct_grp(int32_t *__restrict__ hits, int64_t hits_stride,
                       const int32_t *__restrict__ cnt, const int64_t *__restrict__ clsz,
                       const int32_t *__restrict__ hsize, const int32_t *__restrict__ hs_ysum,
                       const int32_t *__restrict__ ha, int C, const double *__restrict__ term,
                       int64_t N, int64_t P, double *__restrict__ out_full,
-                      double *__restrict__ out_marg, int want_marg, SelFuse sel)
+                      double *__restrict__ out_marg, int want_marg, SelFuse sel,
+                      const int32_t *__restrict__ cls_slot0)
 {
     constexpr int TK = TK1, KK = TK1 * TK1, NT = 1 + TK + TK * (TK + 1);
+    constexpr int SQ = VM ? TK * 4 : KK;  // ints of one class's hit square in memory
+    auto at = [](int a, int v) { return VM ? v * 4 + a : a * TK + v; };
     const int lane = threadIdx.x & 31;
     const int sub = lane & (L - 1);
     const int grp0 = lane & ~(L - 1);
@@ -414,25 +421,44 @@ k_finalize_direct_grp(int32_t *__restrict__ hits, int64_t hits_stride,
         const int y = y0 + sub;
         double t[NT];
         if (y < C) {
-            int x[KK], c0[TK];
+            int x[SQ], c0[TK];
 #pragma unroll
             for (int v = 0; v < TK; ++v) c0[v] = crow[y * TK + v];
             bool any = false;
+            const int sl0 = (VM && cls_slot0) ? cls_slot0[y] : y;
+            const int sl1 = (VM && cls_slot0) ? cls_slot0[y + 1] : y + 1;
             if (hrow) {
-                int32_t *hr = hrow + (int64_t)y * KK;
-                if (KK % 4 == 0) {
+                int32_t *hr = hrow + (int64_t)sl0 * SQ;
+                if (SQ % 4 == 0) {
 #pragma unroll
-                    for (int q = 0; q < KK / 4; ++q) {
+                    for (int q = 0; q < SQ / 4; ++q) {
                         const int4 w = *reinterpret_cast<const int4 *>(hr + 4 * q);
                         x[4 * q] = w.x, x[4 * q + 1] = w.y, x[4 * q + 2] = w.z, x[4 * q + 3] = w.w;
                     }
+                    if (VM) {
+                        for (int sl = sl0 + 1; sl < sl1; ++sl) {  // further segments of the class
+                            int32_t *h2 = hrow + (int64_t)sl * SQ;
+                            bool nz = false;
+#pragma unroll
+                            for (int q = 0; q < SQ / 4; ++q) {
+                                const int4 w = *reinterpret_cast<const int4 *>(h2 + 4 * q);
+                                x[4 * q] += w.x, x[4 * q + 1] += w.y, x[4 * q + 2] += w.z, x[4 * q + 3] += w.w;
+                                nz |= (w.x | w.y | w.z | w.w) != 0;
+                            }
+                            if (nz && active) {
+#pragma unroll
+                                for (int q = 0; q < SQ / 4; ++q)
+                                    *reinterpret_cast<int4 *>(h2 + 4 * q) = make_int4(0, 0, 0, 0);
+                            }
+                        }
+                    }
                 } else {
 #pragma unroll
-                    for (int i = 0; i < KK; ++i) x[i] = hr[i];
+                    for (int i = 0; i < SQ; ++i) x[i] = hr[i];
                 }
             } else {
 #pragma unroll
-                for (int i = 0; i < KK; ++i) x[i] = 0;
+                for (int i = 0; i < SQ; ++i) x[i] = 0;
             }
             int cs[TK], rs[TK];
 #pragma unroll
@@ -442,7 +468,7 @@ k_finalize_direct_grp(int32_t *__restrict__ hits, int64_t hits_stride,
                 rs[a] = 0;
 #pragma unroll
                 for (int v = 0; v < TK; ++v) {
-                    const int q = x[a * TK + v];
+                    const int q = x[at(a, v)];
                     rs[a] += q;
                     cs[v] += q;
                     any |= q != 0;
@@ -462,17 +488,17 @@ k_finalize_direct_grp(int32_t *__restrict__ hits, int64_t hits_stride,
             for (int a = 0; a < TK; ++a) {
                 t[1 + TK + a * (TK + 1)] = T((hrow ? hsize[y * TK + a] : 0) - rs[a]);
 #pragma unroll
-                for (int v = 0; v < TK; ++v) t[2 + TK + a * (TK + 1) + v] = T(x[a * TK + v]);
+                for (int v = 0; v < TK; ++v) t[2 + TK + a * (TK + 1) + v] = T(x[at(a, v)]);
             }
             if (any && active) {  // leave the buffer clean for the next pass
-                int32_t *hr = hrow + (int64_t)y * KK;
-                if (KK % 4 == 0) {
+                int32_t *hr = hrow + (int64_t)sl0 * SQ;
+                if (SQ % 4 == 0) {
 #pragma unroll
-                    for (int q = 0; q < KK / 4; ++q)
+                    for (int q = 0; q < SQ / 4; ++q)
                         *reinterpret_cast<int4 *>(hr + 4 * q) = make_int4(0, 0, 0, 0);
                 } else {
 #pragma unroll
-                    for (int i = 0; i < KK; ++i) hr[i] = 0;
+                    for (int i = 0; i < SQ; ++i) hr[i] = 0;
                 }
             }
         } else {
@@ -625,25 +651,36 @@ static int grp_lanes(int64_t P, int C)
 }
 
 template <int TK1>
-static int launch_direct(int32_t *hits, int64_t stride, const int32_t *cnt, const int64_t *clsz,
+static int launch_direct(int32_t *hits, int64_t stride /* x_j-major */, const int32_t *cnt, const int64_t *clsz,
                          const int32_t *hsize, const int32_t *hs_ysum, const int32_t *ha, int C,
                          int K1, const double *table, int64_t N, int64_t P, double *out_full,
-                         double *out_marg, cudaStream_t st)
+                         double *out_marg, int vmajor, const int32_t *cls_slot0, int n_slot,
+                         cudaStream_t st)
 {
     if constexpr (TK1 > 0) {
         const int threads = 256;
         const int L = grp_lanes(P, C);
         const int wm = out_marg != nullptr;
-#define PRB_FG(LL)                                                                                   \
-    k_finalize_direct_grp<TK1, LL, false><<<(unsigned)ceil_div(P * LL, threads), threads, 0, st>>>(  \
-        hits, stride, cnt, clsz, hsize, hs_ysum, ha, C, table, N, P, out_full, out_marg, wm,         \
-        SelFuse{})
-        if (L == 32)
-            PRB_FG(32);
-        else if (L == 16)
-            PRB_FG(16);
-        else
-            PRB_FG(8);
+        if (vmajor) stride = (int64_t)n_slot * TK1 * 4;
+#define PRB_FG(LL, VM)                                                                                  \
+    k_finalize_direct_grp<TK1, LL, false, VM><<<(unsigned)ceil_div(P * LL, threads), threads, 0, st>>>( \
+        hits, stride, cnt, clsz, hsize, hs_ysum, ha, C, table, N, P, out_full, out_marg, wm,            \
+        SelFuse{}, cls_slot0)
+        if (vmajor) {
+            if (L == 32)
+                PRB_FG(32, true);
+            else if (L == 16)
+                PRB_FG(16, true);
+            else
+                PRB_FG(8, true);
+        } else {
+            if (L == 32)
+                PRB_FG(32, false);
+            else if (L == 16)
+                PRB_FG(16, false);
+            else
+                PRB_FG(8, false);
+        }
 #undef PRB_FG
         PRB_LAUNCH_CHECK("k_finalize_direct_grp");
         return 0;
@@ -653,6 +690,7 @@ static int launch_direct(int32_t *hits, int64_t stride, const int32_t *cnt, cons
     const int64_t smem_max = devinfo().smem_optin - 1024;
     while (threads > 32 && per_thread * threads > smem_max) threads >>= 1;
     PRB_REQUIRE(per_thread * threads <= smem_max, "finalize scratch does not fit in shared memory");
+    PRB_REQUIRE(!vmajor, "v-major hits need K <= 5 here");
     // spread genes over all SMs: small blocks when there are few genes
     while (threads > 32 && ceil_div(P, threads) < 2 * devinfo().sm_count) threads >>= 1;
     auto kern = k_finalize_direct<TK1>;
@@ -668,16 +706,18 @@ extern "C" int prb_finalize_direct(int32_t *hits, const int32_t *cnt, const int6
                                    const int32_t *hsize, const int32_t *hs_ysum,
                                    const int32_t *ha, int C, int K, const double *table,
                                    int64_t N, int64_t P, double *out_full, double *out_marg,
+                                   int vmajor, const int32_t *cls_slot0, int n_slot,
                                    prb_stream_t stream)
 {
     if (P == 0) return 0;
+    PRB_REQUIRE(!vmajor || n_slot >= 1, "v-major hits need the number of slots per gene");
     PRB_REQUIRE(C >= 1 && K >= 2 && K <= PRB_MAX_CODES, "bad C or K");
     PRB_REQUIRE(out_full != nullptr, "out_full is required");
     const int K1 = K - 1;
     const int64_t stride = (int64_t)C * K1 * K1;
 #define PRB_FD(T)                                                                              \
     return launch_direct<T>(hits, stride, cnt, classsizes, hsize, hs_ysum, ha, C, K1, table, N, \
-                            P, out_full, out_marg, S(stream))
+                            P, out_full, out_marg, vmajor, cls_slot0, n_slot, S(stream))
     switch (K1) {
         case 1: PRB_FD(1);
         case 2: PRB_FD(2);
@@ -699,21 +739,31 @@ template <int TK1>
 static int launch_update(int32_t *hits, const int32_t *cnt, const int64_t *clsz,
                          const int32_t *hsize, const int32_t *hs_ysum, const int32_t *ha, int C,
                          const double *table, int64_t N, int64_t P, int want_marg,
-                         const SelFuse &sel, cudaStream_t st)
+                         const SelFuse &sel, int vmajor, const int32_t *cls_slot0, int n_slot,
+                         cudaStream_t st)
 {
     const int threads = 256;
     const int L = grp_lanes(P, C);
-    const int64_t stride = (int64_t)C * TK1 * TK1;
-#define PRB_FU(LL)                                                                                  \
-    k_finalize_direct_grp<TK1, LL, true><<<(unsigned)ceil_div(P * LL, threads), threads, 0, st>>>(  \
-        hits, stride, cnt, clsz, hsize, hs_ysum, ha, C, table, N, P, nullptr, nullptr, want_marg,   \
-        sel)
-    if (L == 32)
-        PRB_FU(32);
-    else if (L == 16)
-        PRB_FU(16);
-    else
-        PRB_FU(8);
+    const int64_t stride = vmajor ? (int64_t)n_slot * TK1 * 4 : (int64_t)C * TK1 * TK1;
+#define PRB_FU(LL, VM)                                                                                 \
+    k_finalize_direct_grp<TK1, LL, true, VM><<<(unsigned)ceil_div(P * LL, threads), threads, 0, st>>>( \
+        hits, stride, cnt, clsz, hsize, hs_ysum, ha, C, table, N, P, nullptr, nullptr, want_marg,      \
+        sel, cls_slot0)
+    if (vmajor) {
+        if (L == 32)
+            PRB_FU(32, true);
+        else if (L == 16)
+            PRB_FU(16, true);
+        else
+            PRB_FU(8, true);
+    } else {
+        if (L == 32)
+            PRB_FU(32, false);
+        else if (L == 16)
+            PRB_FU(16, false);
+        else
+            PRB_FU(8, false);
+    }
 #undef PRB_FU
     PRB_LAUNCH_CHECK("k_finalize_update");
     return 0;
@@ -730,9 +780,11 @@ extern "C" int prb_finalize_update(int32_t *hits, const int32_t *cnt, const int6
                                    int64_t *cand_idx, double *best, int32_t *ticket,
                                    const uint32_t *col_packed, const int64_t *col_begin,
                                    const int64_t *col_end, const int32_t *newpos, uint8_t *sx,
+                                   int vmajor, const int32_t *cls_slot0, int n_slot,
                                    prb_stream_t stream)
 {
     PRB_REQUIRE(P >= 1 && C >= 1 && K >= 2 && K <= 5, "the fused step tail needs 2 <= K <= 5");
+    PRB_REQUIRE(!vmajor || n_slot >= 1, "v-major hits need the number of slots per gene");
     PRB_REQUIRE(kind == PRB_SEL_CIFE || kind == PRB_SEL_JMI || kind == PRB_SEL_CIFE_UNSUP,
                 "unknown selector kind");
     PRB_REQUIRE(hits && base && penalty && score && selected && Hx_all && gene_ptr && n_sel_ptr,
@@ -746,7 +798,7 @@ extern "C" int prb_finalize_update(int32_t *hits, const int32_t *cnt, const int6
     const int want_marg = kind != PRB_SEL_CIFE_UNSUP;
 #define PRB_LU(T)                                                                               \
     return launch_update<T>(hits, cnt, classsizes, hsize, hs_ysum, ha, C, table, N, P, want_marg, \
-                            sel, S(stream))
+                            sel, vmajor, cls_slot0, n_slot, S(stream))
     switch (K - 1) {
         case 1: PRB_LU(1);
         case 2: PRB_LU(2);

@@ -24,6 +24,25 @@ __device__ __forceinline__ void v_bulk_load(uint32_t dst, const void *src, uint3
         ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
         : "memory");
 }
+// the same copy, its lines marked "evict first" in L2: a stream that is read exactly once must
+// not push the tables the launch keeps updating (hits) out of the cache
+__device__ __forceinline__ uint64_t v_policy_evict_first()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void v_bulk_load_hint(uint32_t dst, const void *src, uint32_t bytes,
+                                                 uint32_t bar, uint64_t policy)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[%0], [%1], %2, [%3], %4;"
+        ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+        : "memory");
+}
 __device__ __forceinline__ void v_mbar_wait(uint32_t bar, uint32_t parity)
 {
     asm volatile(

@@ -267,22 +267,34 @@ k_stream_ell(const uint32_t *__restrict__ ell, const uint32_t *__restrict__ bhdr
 // entries per row word, padded with the bundle's pad entry (the "x_j = 0" slot of its tile).
 constexpr int EB_WARPS = 8;
 
+// header word of a lane: vell.cu keeps it in the side array bhdr; the streamed layout of
+// vell2.cu (hdr_rows = 1) stores it as the row in front of the bundle's data rows, bit 31 of
+// lane l carrying bit l of the number of data rows L.  `data` = the lane's word of data row 0.
+__device__ __forceinline__ void ell_put_header(uint32_t hdr, int L, int lane, int hdr_rows,
+                                               uint32_t *data, uint32_t *side)
+{
+    if (hdr_rows)
+        *(data - 32) = (hdr & 0x7FFFFFFFu) | ((((uint32_t)L >> lane) & 1u) << 31);
+    else
+        *side = hdr;
+}
+
 __global__ void __launch_bounds__(EB_WARPS * 32)
 k_ell_build(const uint16_t *__restrict__ tmp, const int64_t *__restrict__ lr_src,
             const int32_t *__restrict__ lr_len, const uint32_t *__restrict__ lr_hdr,
             const int32_t *__restrict__ brow0, const uint16_t *__restrict__ bundle_pad,
-            int64_t n_bundles, uint32_t *__restrict__ ell, uint32_t *__restrict__ bhdr)
+            int64_t n_bundles, uint32_t *__restrict__ ell, uint32_t *__restrict__ bhdr, int hdr_rows)
 {
     const int lane = threadIdx.x & 31;
     const int64_t wstride = (int64_t)gridDim.x * EB_WARPS;
     for (int64_t b = blockIdx.x * (int64_t)EB_WARPS + (threadIdx.x >> 5); b < n_bundles; b += wstride) {
         const int64_t src = lr_src[b * 32 + lane];
         const int n = lr_len[b * 32 + lane];
-        const int64_t row0 = brow0[b];
+        const int64_t row0 = brow0[b] + hdr_rows;
         const int L = (int)(brow0[b + 1] - row0);
         const uint32_t pad = bundle_pad[b];
         uint32_t *out = ell + row0 * 32 + lane;
-        bhdr[b * 32 + lane] = lr_hdr[b * 32 + lane];
+        ell_put_header(lr_hdr[b * 32 + lane], L, lane, hdr_rows, out, bhdr + b * 32 + lane);
         const uint16_t *in = tmp + src;
         for (int r = 0; r < L; ++r) {
             const uint32_t e0 = 2 * r < n ? in[2 * r] : pad;
@@ -309,7 +321,8 @@ __global__ void __launch_bounds__(EBB_WARPS * 32)
 k_ell_build_banked(const uint16_t *__restrict__ tmp, const int64_t *__restrict__ lr_src,
                    const int32_t *__restrict__ lr_len, const uint32_t *__restrict__ lr_hdr,
                    const int32_t *__restrict__ brow0, const uint16_t *__restrict__ bundle_pad,
-                   int64_t n_bundles, uint32_t *__restrict__ ell, uint32_t *__restrict__ bhdr)
+                   int64_t n_bundles, uint32_t *__restrict__ ell, uint32_t *__restrict__ bhdr,
+                   int hdr_rows)
 {
     extern __shared__ __align__(16) unsigned char eb_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -321,10 +334,11 @@ k_ell_build_banked(const uint16_t *__restrict__ tmp, const int64_t *__restrict__
     for (int64_t b = blockIdx.x * (int64_t)EBB_WARPS + warp; b < n_bundles; b += wstride) {
         const int64_t src = lr_src[b * 32 + lane];
         const int n = lr_len[b * 32 + lane];
-        const int64_t row0 = brow0[b];
+        const int64_t row0 = brow0[b] + hdr_rows;
         const int L = (int)(brow0[b + 1] - row0);
         const uint32_t pad = bundle_pad[b];
-        bhdr[b * 32 + lane] = lr_hdr[b * 32 + lane];
+        ell_put_header(lr_hdr[b * 32 + lane], L, lane, hdr_rows, ell + row0 * 32 + lane,
+                       bhdr + b * 32 + lane);
         const uint16_t *in = tmp + src;
         for (int c0 = 0; c0 < 2 * L; c0 += EB_CH) {
             const int m = max(0, min(n - c0, EB_CH));  // this lane's entries in the chunk
@@ -423,11 +437,13 @@ extern "C" int prb_v_check_smem_base(void)
 extern "C" int prb_ell_build(const uint16_t *tmp, const int64_t *lr_src, const int32_t *lr_len,
                              const uint32_t *lr_hdr, const int32_t *brow0,
                              const uint16_t *bundle_pad, int64_t n_bundles, uint32_t *ell,
-                             uint32_t *bhdr, prb_stream_t stream)
+                             uint32_t *bhdr, int hdr_in_stream, prb_stream_t stream)
 {
     if (n_bundles == 0) return 0;
-    PRB_REQUIRE(tmp && lr_src && lr_len && lr_hdr && brow0 && bundle_pad && ell && bhdr,
+    PRB_REQUIRE(tmp && lr_src && lr_len && lr_hdr && brow0 && bundle_pad && ell &&
+                    (bhdr || hdr_in_stream),
                 "null pointer");
+    const int hdr_rows = hdr_in_stream ? 1 : 0;
     static const int banked = [] {
         const char *e = getenv("PRB_ELL_BANKED");  // 0: plain transposition (tuning / A-B runs)
         return e ? atoi(e) : 1;
@@ -438,13 +454,13 @@ extern "C" int prb_ell_build(const uint16_t *tmp, const int64_t *lr_src, const i
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         const int grid = (int)hmin(ceil_div(n_bundles, EBB_WARPS), (int64_t)devinfo().sm_count * 3);
         k_ell_build_banked<<<grid, EBB_WARPS * 32, smem, S(stream)>>>(
-            tmp, lr_src, lr_len, lr_hdr, brow0, bundle_pad, n_bundles, ell, bhdr);
+            tmp, lr_src, lr_len, lr_hdr, brow0, bundle_pad, n_bundles, ell, bhdr, hdr_rows);
         PRB_LAUNCH_CHECK("k_ell_build_banked");
         return 0;
     }
     const int grid = (int)hmin(ceil_div(n_bundles, EB_WARPS), (int64_t)devinfo().sm_count * 16);
     k_ell_build<<<grid, EB_WARPS * 32, 0, S(stream)>>>(tmp, lr_src, lr_len, lr_hdr, brow0,
-                                                       bundle_pad, n_bundles, ell, bhdr);
+                                                       bundle_pad, n_bundles, ell, bhdr, hdr_rows);
     PRB_LAUNCH_CHECK("k_ell_build");
     return 0;
 }

@@ -109,6 +109,13 @@ class Engine:
         self._tps = {}
         kern = os.environ.get("PRB_V_KERNEL", "ell")
         self.ell = USE_VLAYOUT and self.K1 <= ELL_MAX_K1 and (kern != "rows" or self.K1 > 4)
+        # streamed lane-run layout (csrc/vell2.cu), the default; PRB_ELL_V=1: the layout of
+        # csrc/vell.cu (global work queue, side arrays for the bundle headers)
+        self.ell2 = (self.ell and os.environ.get("PRB_ELL_V", "2") == "2"
+                     and self.P * self.K1 < (1 << 22) - 1)
+        # ... whose hit table is v-major for K <= 5 (hits[g][segment][v][4], plain 16-byte
+        # stores; the header then carries a 10-bit segment and a 20-bit virtual gene)
+        self.vmajor = self.ell2 and self.K1 <= 4 and self.P * self.K1 < (1 << 20) - 1
         self.vmode = USE_VLAYOUT and (self.ell or self.K1 <= 4)
         # warp-per-run layout: 16-bit entries, 64 per row (prb_v_scatter16 / prb_stream_v16);
         # PRB_V16=0 selects the 32-bit entries of round 1 (1.40 vs 1.80 ms at config 4)
@@ -269,6 +276,10 @@ class Engine:
         classes = self.has_y
         cap, max_segs = ctypes.c_int64(), ctypes.c_int()
         nat.call("prb_v_tile_capacity", ctypes.byref(cap), ctypes.byref(max_segs))
+        if self.ell2:  # tiles of the two-tile window; the class travels in the bundle header
+            tc = ctypes.c_int()
+            nat.call("prb_ell2_geometry", ctypes.byref(tc), None, None, None)
+            cap, max_segs = ctypes.c_int64(tc.value), ctypes.c_int(1 << 30)
         cap = max(128, min(int(os.environ.get("PRB_V_TILE_CELLS", cap.value)), cap.value))
         sizes = self.classsizes_host if classes else [self.N]
         cell0, cls, st = vplan.segment_plan(sizes, cap, max_segs.value)
@@ -297,6 +308,7 @@ class Engine:
         # per-cell table of the two layout kernels, indexed by the ORIGINAL cell id:
         # bits 0..23 relabelled position, bits 24..31 segment (seg16 when there are > 256)
         cellmap = seg16 = None
+        pl["pos"] = newpos
         if n_seg > 1 or newpos is not None:
             pos = newpos if newpos is not None else torch.arange(self.N, dtype=torch.int32,
                                                                  device=dev)
@@ -305,12 +317,24 @@ class Engine:
                 if n_seg * K1 > 65536:
                     raise NotImplementedError("too many cell segments")
                 seg = torch.bucketize(pos, pl["seg_cell0"][1:-1].contiguous(), right=True)
+                if self.ell2 and pl["n_st"] > 1:
+                    # padded cell space: super-tile t owns [t * 32768, t * 32768 + its cells)
+                    st_t = torch.tensor(pl["st"], dtype=torch.int64, device=dev)
+                    seg_tile = torch.repeat_interleave(
+                        torch.arange(pl["n_st"], dtype=torch.int64, device=dev), st_t[1:] - st_t[:-1])
+                    shift = (torch.arange(pl["n_st"], dtype=torch.int64, device=dev) * vplan.ELL2_TILE
+                             - pl["seg_cell0"].to(torch.int64)[st_t[:-1]])
+                    pos = (pos + shift[seg_tile[seg]].to(torch.int32)).contiguous()
+                    pl["pos"] = pos
+                    cellmap = pos & 0xFFFFFF  # (only the low 16 bits reach the layout)
                 if n_seg <= 256:
-                    cellmap = (pos | (seg << 24).to(torch.int32)).contiguous()
+                    cellmap = (cellmap | (seg << 24).to(torch.int32)).contiguous()
                 else:
                     seg16 = seg.to(torch.int16)  # bit pattern of a uint16
         nat.call("prb_v_count", nat.ptr(self.packed), nat.ptr(self.indptr), P, nat.ptr(cellmap),
                  nat.ptr(seg16), n_seg, K1, nat.ptr(seglen), nat.ptr(self.counters), nat.stream())
+        if self.ell2:
+            return self._build_ell2(pl, seglen, cellmap, seg16)
         if self.ell:
             return self._build_ell(pl, seglen, cellmap, seg16)
         # rows of every run, scanned in storage order: (super-tile, virtual gene, segment)
@@ -404,7 +428,7 @@ class Engine:
         ell = torch.empty(rows * 32 + PACKED_PAD, dtype=torch.int32, device=dev)
         bhdr = torch.empty(max(n_bundles, 1) * 32, dtype=torch.int32, device=dev)
         nat.call("prb_ell_build", nat.ptr(tmp), nat.ptr(lr_src), nat.ptr(lr_len), nat.ptr(lr_hdr),
-                 nat.ptr(brow0), nat.ptr(bundle_pad), n_bundles, nat.ptr(ell), nat.ptr(bhdr),
+                 nat.ptr(brow0), nat.ptr(bundle_pad), n_bundles, nat.ptr(ell), nat.ptr(bhdr), 0,
                  nat.stream())
         # work items: ranges of whole bundles with about R rows (large first, small last)
         tb = torch.cat([tile_b0, tile_b0.new_tensor([n_bundles])]).cpu().numpy()
@@ -419,8 +443,114 @@ class Engine:
         self.epoch += 1
         return self.v
 
+    def _build_ell2(self, pl, seglen, cellmap, seg16):
+        """The streamed lane-run layout of csrc/vell2.cu: the lane-runs and bundles of
+        _build_ell, every bundle preceded by its header row, the stream cut into one chunk per
+        CTA / phases of two tiles / guided work items (vplan.ell2_chunks)."""
+        P, K1, n_seg, dev = self.P, self.K1, pl["n_seg"], self.device
+        n_st, st = pl["n_st"], pl["st"]
+        i64 = dict(dtype=torch.int64, device=dev)
+        geo = [ctypes.c_int() for _ in range(4)]
+        nat.call("prb_ell2_geometry", *[ctypes.byref(g) for g in geo])
+        _, n_ctas, warps, max_items = [g.value for g in geo]
+        if self.C > 256:
+            raise NotImplementedError("more than 256 classes")
+        lens = seglen[: P * K1 * n_seg].to(torch.int64)
+        n_runs = lens.numel()
+        run_start = torch.cumsum(lens, 0) - lens
+        total = int(lens.sum().item()) if n_runs else 0
+        assert total == self.nnz
+        tmp = torch.empty(total + 16, dtype=torch.int16, device=dev)
+        nat.call("prb_v_scatter_flat", nat.ptr(self.packed), nat.ptr(self.indptr), P,
+                 nat.ptr(cellmap), nat.ptr(seg16), n_seg, K1, nat.ptr(seglen), nat.ptr(run_start),
+                 nat.ptr(tmp), nat.ptr(self.counters), nat.stream())
+        # lane-runs of at most `cap` entries; small matrices get shorter ones so that a CTA's
+        # chunk still holds several bundles
+        cap = int(os.environ.get("PRB_ELL_CAP", 0))
+        if not cap:
+            cap = int(min(1024, max(64, (total // 64 // n_ctas // 4) * 2)))
+        cap = min(cap, 32768) & ~1
+        if self.vmajor and n_seg > 1024:
+            self.vmajor = False
+        if self.vmajor:  # the slot of a run in hits: its segment
+            seg_id, id_shift = torch.arange(n_seg, **i64), 20
+        else:            # ... its class
+            seg_id = (pl["seg_class"].to(torch.int64) if pl["seg_class"] is not None
+                      else torch.zeros(n_seg, **i64))
+            id_shift = 22
+        ep = vplan.ell_plan(lens, run_start, n_seg, st, cap, seg_id=seg_id, id_shift=id_shift)
+        n_bundles, nb_t, tile_b0 = ep["n_bundles"], ep["nb_t"], ep["tile_b0"]
+        lr_src, lr_len, lr_hdr = ep["lr_src"], ep["lr_len"], ep["lr_hdr"]
+        srow0 = ep["brow0"] + torch.arange(n_bundles + 1, **i64)  # + one header row per bundle
+        del ep
+        rows = int(srow0[-1].item())
+        if rows >= (1 << 31):
+            raise NotImplementedError("more than 2^31 rows in the lane-run layout")
+        # padding entries point at slot 32767 of the bundle's half of the tile window
+        pad_t = ((torch.arange(n_st, **i64) & 1) << 15) | (vplan.ELL2_TILE - 1)
+        bundle_pad = torch.repeat_interleave(pad_t, nb_t).to(torch.int16)
+        ell = torch.empty(rows * 32 + PACKED_PAD, dtype=torch.int32, device=dev)
+        srow0_32 = srow0.to(torch.int32)
+        nat.call("prb_ell_build", nat.ptr(tmp), nat.ptr(lr_src), nat.ptr(lr_len), nat.ptr(lr_hdr),
+                 nat.ptr(srow0_32), nat.ptr(bundle_pad), n_bundles, nat.ptr(ell), None, 1,
+                 nat.stream())
+        tb = torch.cat([tile_b0, tile_b0.new_tensor([n_bundles])]).cpu().numpy()
+        env = os.environ.get
+        item_row0, phase, cta_ph0 = vplan.ell2_chunks(
+            srow0.cpu().numpy(), tb, n_ctas, warps, max_items,
+            bundle_cost=int(env("PRB_ELL_BCOST", 16)), min_rows=int(env("PRB_ELL_MIN_ROWS", 40)),
+            guide=float(env("PRB_ELL_GUIDE", 2.0)), max_rows=int(env("PRB_ELL_MAX_ROWS", 512)))
+        torch.cuda.current_stream().synchronize()  # tmp / lr_* are released below
+        del tmp, lr_src, lr_len, lr_hdr
+        cls_slot0 = None
+        if self.vmajor and pl["seg_class"] is not None:  # segments of class y: a slot range
+            cls_slot0 = torch.searchsorted(pl["seg_class"].contiguous(),
+                                           torch.arange(self.C + 1, dtype=torch.int32, device=dev)
+                                           ).to(torch.int32)
+        self.v = dict(plan=pl, kind="ell2", ell=ell, n_bundles=n_bundles, seglen=seglen, rows=rows,
+                      id_shift=id_shift, cls_slot0=cls_slot0,
+                      relabelled=pl["pos"] is not None, pos=pl["pos"], item_rows=0, cap=cap,
+                      n_items=int(item_row0.size - 1), n_ctas=n_ctas,
+                      srow0=srow0_32 if env("PRB_ELL_KEEP_PLAN") else None,
+                      item_row0=torch.from_numpy(item_row0).to(dev),
+                      phase=torch.from_numpy(phase).to(dev).contiguous(),
+                      cta_ph0=torch.from_numpy(cta_ph0).to(dev))
+        need = n_st * vplan.ELL2_TILE + 64
+        if self.sx.numel() < need:
+            self.sx = torch.empty(need, dtype=torch.uint8, device=dev)
+        self.sx.fill_(SX_NONE)
+        self.epoch += 1
+        return self.v
+
     def _v(self):
         return self.v if self.v is not None else self._build_v()
+
+    def _hit_slots(self, with_y, v):
+        """(slots per gene in the hit table of the V path, "several runs share a slot").
+        v-major table: one slot per segment when the call conditions on the labels (the
+        finalize kernels add the segments of a class), a single shared one otherwise."""
+        C = self.C if with_y else 1
+        if not self.vmajor:
+            return C, 0
+        n_seg = v["plan"]["n_seg"]
+        if with_y and v["cls_slot0"] is not None:
+            return n_seg, 0
+        return 1, int(n_seg > 1)
+
+    def _hits_v(self, with_y, v):
+        """The zeroed hit table for one pass of the V path + what the finalize kernels need
+        to read it: (hits, cls_slot0, n_slot)."""
+        n_slot, _ = self._hit_slots(with_y, v)
+        per_slot = self.K1 * (4 if self.vmajor else self.K1)
+        cls_slot0 = v.get("cls_slot0") if (self.vmajor and n_slot > 1) else None
+        return self.hits_buffer(n_slot * per_slot), cls_slot0, n_slot
+
+    def _vpos(self, v):
+        """Position of every cell in the per-cell vectors of the V path (sx): the class-sorted
+        order, for the streamed lane-run layout in its padded cell space; None = identity."""
+        if "pos" in v:
+            return v["pos"]
+        return self.newpos if v["relabelled"] else None
 
     def _count_table_v(self, with_classes, C):
         """cnt[g][c][v-1] from run lengths (no streaming pass over the hot kernel).  Without
@@ -456,6 +586,13 @@ class Engine:
     def _stream_v_launch(self, with_y, C, hits):
         v = self._v()
         pl = v["plan"]
+        if self.ell2:
+            n_slot, always_add = self._hit_slots(with_y, v)
+            nat.call("prb_stream_ell2", nat.ptr(v["ell"]), nat.ptr(v["item_row0"]),
+                     nat.ptr(v["phase"]), nat.ptr(v["cta_ph0"]), v["n_ctas"], nat.ptr(self.sx),
+                     self.K1, n_slot, v["id_shift"], always_add, nat.ptr(hits), int(self.vmajor),
+                     self.P * self.K1, nat.ptr(getattr(self, "ell_timing", None)), nat.stream())
+            return
         if self.ell:
             nat.call("prb_stream_ell", nat.ptr(v["ell"]), nat.ptr(v["bhdr"]), nat.ptr(v["brow0"]),
                      v["n_bundles"],
@@ -479,7 +616,7 @@ class Engine:
         the gene already in gene_ptr), commit, state sizes, work counters, column -> sx."""
         v = self._v()
         C = self.C if with_y else 1
-        newpos = self.newpos if v["relabelled"] else None
+        newpos = self._vpos(v)
         nat.call("prb_pick_scatter", nat.ptr(records), n_rec, nat.ptr(self.gene_ptr),
                  nat.ptr(sel.S_dev) if sel else None, nat.ptr(sel.n_sel) if sel else None,
                  nat.ptr(sel.selected) if sel else None, _i32(self.gene_lo), self.P,
@@ -504,9 +641,9 @@ class Engine:
         if self.P == 0:
             return
         self._pick_scatter(with_y, sel.records, sel.n_rec if pick else 0, sel)
-        hits = self.hits_buffer(n_bins)
+        hits, cls_slot0, n_slot = self._hits_v(with_y, v)
         self._stream_v(with_y, C, hits)
-        newpos = self.newpos if v["relabelled"] else None
+        newpos = self._vpos(v)
         nat.call("prb_finalize_update", nat.ptr(hits), nat.ptr(cnt), nat.ptr(clsz),
                  nat.ptr(self.hsize), nat.ptr(self.hs_ysum), nat.ptr(self.ha), C, self.K,
                  nat.ptr(self.term), self.N, self.P, kind, int(is_remove), nat.ptr(sel.base),
@@ -515,7 +652,8 @@ class Engine:
                  nat.ptr(sel.n_sel), _i32(self.gene_lo), nat.ptr(sel.cand_score),
                  nat.ptr(sel.cand_idx), nat.ptr(sel.best), nat.ptr(self.ticket),
                  nat.ptr(self.col_packed), nat.ptr(self.col_begin), nat.ptr(self.col_end),
-                 nat.ptr(newpos), nat.ptr(self.sx), nat.stream())
+                 nat.ptr(newpos), nat.ptr(self.sx), int(self.vmajor), nat.ptr(cls_slot0), n_slot,
+                 nat.stream())
 
     # --------------------------------------------------------------- primitives
     def hits_buffer(self, n_bins):
@@ -545,7 +683,9 @@ class Engine:
                  nat.ptr(self.state_buf), self.N, n_states, self.K1, direct_C, nat.ptr(hits),
                  nat.ptr(self.counters), nat.stream())
 
-    def _finalize(self, hits, cnt, clsz, C, n_hs_cap, n_hs_ptr, out_full, out_marg, direct):
+    def _finalize(self, hits, cnt, clsz, C, n_hs_cap, n_hs_ptr, out_full, out_marg, direct,
+                  vm=(0, None, 1)):
+        """vm = (v-major hits, cls_slot0, n_slot) of a V-path pass (_hits_v)."""
         wide = os.environ.get("PRB_WIDE_FINALIZE", "1") != "0" and self.K1 > 4
         if hits is None or (direct and not wide):
             # single-gene layout with K <= 5 (or no master column at all): lanes / one
@@ -554,7 +694,7 @@ class Engine:
             nat.call("prb_finalize_direct", nat.ptr(hits), nat.ptr(cnt), nat.ptr(clsz),
                      nat.ptr(self.hsize), nat.ptr(self.hs_ysum), nat.ptr(self.ha), C, self.K,
                      nat.ptr(self.term), self.N, self.P, nat.ptr(out_full), nat.ptr(out_marg),
-                     nat.stream())
+                     int(vm[0]), nat.ptr(vm[1]), vm[2], nat.stream())
             return
         nat.call("prb_finalize", nat.ptr(hits), nat.ptr(cnt), nat.ptr(clsz), nat.ptr(self.hs_begin),
                  nat.ptr(self.hs_y), nat.ptr(self.hsize), nat.ptr(self.hs_ysum),
@@ -590,12 +730,13 @@ class Engine:
                 return
             v = self._v()
             self._pick_scatter(with_y, None, 0, None)
-            hits = self.hits_buffer(n_bins)
+            hits, cls_slot0, n_slot = self._hits_v(with_y, v)
             self._stream_v(with_y, C, hits)
-            self._finalize(hits, cnt, clsz, C, n_hs, None, out_full, out_marg, True)
+            self._finalize(hits, cnt, clsz, C, n_hs, None, out_full, out_marg, True,
+                           vm=(int(self.vmajor), cls_slot0, n_slot))
             nat.call("prb_v_unscatter", nat.ptr(self.gene_ptr), nat.ptr(self.col_packed),
                      nat.ptr(self.col_begin), nat.ptr(self.col_end),
-                     nat.ptr(self.newpos if v["relabelled"] else None), nat.ptr(self.sx),
+                     nat.ptr(self._vpos(v)), nat.ptr(self.sx),
                      nat.stream())
             return
         self.scatter_selected_gene()

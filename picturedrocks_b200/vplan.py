@@ -67,7 +67,11 @@ def item_cuts(lo, hi, R):
 
 
 
-def ell_plan(lens, run_start, n_seg, st, cap):
+ELL2_SPLIT = 1 << 30    # header bit: the lane-run is a piece of a longer run
+ELL2_TILE = 1 << 15     # positions per super-tile in the padded cell space
+
+
+def ell_plan(lens, run_start, n_seg, st, cap, seg_id=None, id_shift=22):
     """Index plan of the lane-run layout (csrc/vell.cu), torch tensors on the device of `lens`.
     lens int64[n_runs]: entries of run (vg, s) at index vg * n_seg + s; run_start int64[n_runs]:
     its first entry in the flat run-major scratch; st: super-tile t = segments [st[t], st[t+1]);
@@ -77,7 +81,10 @@ def ell_plan(lens, run_start, n_seg, st, cap):
     ceil(longest / 2) rows.  Returns a dict: n_bundles; brow0 int64
     [n_bundles+1] first row of every bundle; nb_t / tile_b0 int64[n_st] bundles per tile and
     the first one; lr_src int64 / lr_len int32 / lr_hdr int32 [32 * n_bundles] per lane: first
-    entry in the scratch, length, header word (segment-in-tile << 24 | vg; -1 = empty lane)."""
+    entry in the scratch, length, header word (segment-in-tile << 24 | vg; -1 = empty lane).
+    seg_id (int64[n_seg], the streamed layout of csrc/vell2.cu): header word = seg_id of the
+    segment << id_shift | vg, bit 30 = piece of a run that was cut, all ones below id_shift =
+    empty lane (bit 31 is filled in by prb_ell_build)."""
     import torch
 
     dev = lens.device
@@ -98,7 +105,10 @@ def ell_plan(lens, run_start, n_seg, st, cap):
     st_t = torch.tensor(list(st), **i64)
     seg_tile = torch.repeat_interleave(torch.arange(n_st, **i64), st_t[1:] - st_t[:-1])
     tile = seg_tile[seg]
-    hdr = ((seg - st_t[tile]) << 24) | (run_of // n_seg)
+    if seg_id is None:
+        hdr = ((seg - st_t[tile]) << 24) | (run_of // n_seg)
+    else:
+        hdr = (seg_id[seg] << id_shift) | (run_of // n_seg) | ((ns > 1).to(torch.int64) * ELL2_SPLIT)
     del run_of, sub, ln, ns, base, rem, seg
     order = torch.argsort((tile << 32) | ((1 << 32) - 1 - sublen))
     tile_s = tile[order]
@@ -111,7 +121,8 @@ def ell_plan(lens, run_start, n_seg, st, cap):
     n_slots = max(n_bundles, 1) * 32
     lr_src = torch.zeros(n_slots, **i64)
     lr_len = torch.zeros(n_slots, dtype=torch.int32, device=dev)
-    lr_hdr = torch.full((n_slots,), -1, dtype=torch.int32, device=dev)
+    lr_hdr = torch.full((n_slots,), -1 if seg_id is None else (1 << id_shift) - 1,
+                        dtype=torch.int32, device=dev)
     lr_src[slot] = src[order]
     lr_len[slot] = sublen[order].to(torch.int32)
     lr_hdr[slot] = hdr[order].to(torch.int32)
@@ -141,3 +152,79 @@ def ell_items(brow0, tile_b, R):
         item_b0.append(np.array([b_hi], dtype=np.int64))
         item_off.append(item_off[-1] + bcut.size)
     return np.asarray(item_off, dtype=np.int32), np.concatenate(item_b0).astype(np.int32)
+
+
+def guided_cuts(cost, n_claimers, min_cost, guide=2.0, max_cost=None):
+    """Cut positions (indices into `cost`) of one phase into work items.
+    cost: float64/int64[n+1] ascending cumulative cost at the n+1 bundle boundaries of the phase.
+    Items of max_cost while plenty is left — the warps of a launch then read a compact window of
+    the stream (large items spread the ~4 700 concurrently streamed ranges over gigabytes, which
+    costs a third of the bandwidth, profiles/r01_item_rows_sweep.txt) — then guided
+    self-scheduling: an item takes 1/(guide * n_claimers) of what is left, never less than
+    min_cost, so that the warps of a CTA finish together.  The ideal positions are snapped to
+    bundle boundaries.  Returns the first boundary of every item (ascending, unique, first = 0,
+    all < n)."""
+    n = len(cost) - 1
+    if n <= 0:
+        return np.zeros(0, dtype=np.int64)
+    c0, total = float(cost[0]), float(cost[-1] - cost[0])
+    d = max(float(guide) * n_claimers, 1.0)
+    min_cost = max(float(min_cost), 1.0)
+    max_cost = max(float(max_cost), min_cost) if max_cost else total
+    left = [np.array([total])]
+    if total > max_cost * d:  # items of max_cost until left / d drops below it
+        n_f = int((total - max_cost * d) // max_cost) + 1
+        left.append(total - max_cost * np.arange(1, n_f + 1))
+    cur = float(left[-1][-1])
+    if cur > min_cost * d:    # guided part
+        n_g = int(np.ceil(np.log(min_cost * d / cur) / np.log1p(-1.0 / d)))
+        left.append(cur * np.power(1.0 - 1.0 / d, np.arange(1, n_g + 1)))
+        cur = float(left[-1][-1])
+    left.append(np.arange(cur - min_cost, 0.0, -min_cost))  # tail of min_cost items
+    pos = total - np.concatenate(left)
+    cuts = np.unique(np.searchsorted(np.asarray(cost, dtype=np.float64) - c0, pos, side="left"))
+    cuts = cuts[cuts < n]
+    if cuts.size == 0 or cuts[0] != 0:
+        cuts = np.concatenate([[0], cuts])
+    return cuts.astype(np.int64)
+
+
+def ell2_chunks(srow0, tile_b, n_ctas, warps, max_items, bundle_cost=16, min_rows=40, guide=2.0,
+                max_rows=512):
+    """Work plan of k_stream_ell2 (csrc/vell2.cu).  srow0 int64[nb+1]: first STREAM row of every
+    bundle (header rows included); tile_b int64[n_st+1]: first bundle of every super-tile.
+    The bundles are cut into n_ctas chunks of equal cost (rows + bundle_cost per bundle), a chunk
+    into phases (its bundles of at most two consecutive tiles) and a phase into work items of at
+    most max_rows rows (guided_cuts).
+    Returns (item_row0 int32[n_items+1], phase int32[n_ph][4] = first tile, tiles, first item,
+    items; cta_ph0 int32[n_ctas+1])."""
+    srow0 = np.asarray(srow0, dtype=np.int64)
+    tile_b = np.asarray(tile_b, dtype=np.int64)
+    nb, n_st = len(srow0) - 1, len(tile_b) - 1
+    cost = srow0 + bundle_cost * np.arange(nb + 1, dtype=np.int64)
+    cb = np.searchsorted(cost, cost[-1] * np.arange(n_ctas + 1, dtype=np.float64) / n_ctas, side="left")
+    cb[0], cb[-1] = 0, nb
+    cb = np.maximum.accumulate(np.minimum(cb, nb))
+    item_row0, phases, cta_ph0 = [], [], [0]
+    n_it = 0
+    for c in range(n_ctas):
+        b, b1 = int(cb[c]), int(cb[c + 1])
+        while b < b1:
+            t = int(np.searchsorted(tile_b, b, side="right")) - 1
+            end = min(b1, int(tile_b[min(t + 2, n_st)]))
+            tiles = 2 if (t + 1 < n_st and int(tile_b[t + 1]) < end) else 1
+            mc, xc = float(min_rows), float(max_rows)
+            while True:
+                cuts = guided_cuts(cost[b:end + 1], warps, mc, guide, xc)
+                if cuts.size <= max_items:
+                    break
+                mc, xc = mc * 1.25, xc * 1.25
+            item_row0.append(srow0[b + cuts])
+            phases.append((t, tiles, n_it, cuts.size))
+            n_it += cuts.size
+            b = end
+        cta_ph0.append(len(phases))
+    item_row0.append(srow0[nb: nb + 1])
+    return (np.concatenate(item_row0).astype(np.int32),
+            np.asarray(phases, dtype=np.int32).reshape(-1, 4),
+            np.asarray(cta_ph0, dtype=np.int32))

@@ -39,6 +39,9 @@ def main():
             os.environ[("PRB_" if k.startswith("ELL_") else "PRB_V_") + k] = v
         eng.v = None
         eng.epoch += 1
+        eng.ell2 = eng.ell and os.environ.get("PRB_ELL_V", "2") == "2"
+        eng.vmajor = eng.ell2 and eng.K1 <= 4
+        eng._hits = None
         inf = pr.markers.SparseInformationSet._from_engine(eng, yd)
         fs = pr.markers.CIFE(inf)
         fs.autoselect(3)
@@ -59,7 +62,7 @@ def main():
             ref_S = S
         v = eng.v
         print("%-44s step %.4f ms  kernel %.4f ms  rows %d items %d R %d cap %s tiles %d segs %d %s"
-              % (knobs or "(default)", step_ms, k_ms, v["rows"], v["n_items"], v["item_rows"],
+              % (knobs or "(default)", step_ms, k_ms, v["rows"], v["n_items"], v.get("item_rows", 0),
                  v.get("cap"), v["plan"]["n_st"], v["plan"]["n_seg"],
                  "same S" if S == ref_S else "S DIFFERS"),
               flush=True)

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), "libprb200.so does not export %s" % name
     # the ctypes table binds exactly the declared entry points
     assert sorted(_native.EXPORTED) == declared_symbols()
-    assert lib.prb_abi_version() == 2
+    assert lib.prb_abi_version() == 3
 
 
 def test_term_table_is_host_side_and_matches_libm():

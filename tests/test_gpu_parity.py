@@ -39,7 +39,7 @@ def test_native_library_is_loaded(pr):
     from picturedrocks_b200 import _native
 
     lib = _native.load()
-    assert lib.prb_abi_version() == 2
+    assert lib.prb_abi_version() == 3
     with open("/proc/self/maps") as f:
         assert "libprb200.so" in f.read()
 
