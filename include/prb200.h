@@ -234,18 +234,19 @@ int prb_v_check_smem_base(void);
  *    items of all phases back to back), phase int32[n_phases][4] = {first tile, tiles (1 or 2),
  *    first item, items}, cta_ph0 int32[n_ctas + 1].
  * prb_stream_ell2, vmajor = 0: adds the joint counts to hits int32[P][n_slot][K-1][K-1];
- * vmajor = 1: hits int32[P][n_slot][K-1][4 * ceil((K-1)/4)], x_j - 1 in the last dimension, all
- * zero on entry — a lane-run that holds a whole run STORES its counts (16-byte writes), only
- * the pieces of longer runs are added (and everything when always_add != 0: several runs share
- * a slot).  The slot of a run is the id field of its header when n_slot > 1, else 0.
- * PV = P*(K-1) < 2^id_shift - 1.
+ * vmajor = 1: hits uint16[P][n_slot][K-1][4 * ceil((K-1)/4)] with one slot per SEGMENT (a count
+ * is at most 32 752), the counts of x_j - 1 = 4q, 4q+2, 4q+1, 4q+3 in the last dimension, all
+ * zero on entry — a lane-run that holds a whole run STORES its counts (one 8-byte write per
+ * four values of x_j), only the pieces of longer runs are added (32-bit REDs on pairs of
+ * counts: they cannot carry).  The slot of a run is the id field of its header when
+ * n_slot > 1, else 0.  PV = P*(K-1) < 2^id_shift - 1.
  * timing: NULL, or device int64[n_items][2] that receives the start / end time (ns) of every
  * work item (tuning runs, K <= 5). */
 int prb_ell2_geometry(int *tile_cells, int *ctas, int *warps, int *max_items);
 int prb_stream_ell2(const uint32_t *ell, const int32_t *item_row0, const int32_t *phase,
                     const int32_t *cta_ph0, int n_ctas, const uint8_t *sx, int K1, int n_slot,
-                    int id_shift, int always_add, int32_t *hits, int vmajor, int64_t PV,
-                    int64_t *timing, prb_stream_t stream);
+                    int id_shift, int32_t *hits, int vmajor, int64_t PV, int64_t *timing,
+                    prb_stream_t stream);
 
 /* ---- joint-state build ("master column", _sparse_make_master_col INFOSET:431-442) */
 /* Columns are addressed through col_begin / col_end int64[P]: first / past-the-last word of
@@ -289,10 +290,10 @@ int prb_finalize(int32_t *hits, const int32_t *cnt, const int64_t *classsizes,
                  double *out_full, double *out_marg, prb_stream_t stream);
 /* Same result for the DIRECT single-gene layout (state id = y*(K-1) + x_j - 1, as
  * written by prb_state_direct), one thread per gene; hits int32[P][C][K-1][K-1] or
- * NULL (then out_full = H(y, x_g), out_marg = H(x_g)).  vmajor != 0 (K <= 5): hits is
- * int32[P][n_slot][K-1][4] with x_j - 1 in the last, padded dimension (what prb_stream_ell2
- * stores); the slots of class y are [cls_slot0[y], cls_slot0[y+1]) — one per segment of the
- * class, summed here — or the single slot y when cls_slot0 is NULL. */
+ * NULL (then out_full = H(y, x_g), out_marg = H(x_g)).  vmajor != 0 (K <= 5): hits is the
+ * table prb_stream_ell2 stores, uint16[P][n_slot][K-1][4] with the counts of x_j - 1 = 0, 2,
+ * 1, 3 in the last dimension; the slots of class y are [cls_slot0[y], cls_slot0[y+1]) — one
+ * per segment of the class, added up here — or the single slot y when cls_slot0 is NULL. */
 int prb_finalize_direct(int32_t *hits, const int32_t *cnt, const int64_t *classsizes,
                         const int32_t *hsize, const int32_t *hs_ysum, const int32_t *ha, int C,
                         int K, const double *table, int64_t N, int64_t P, double *out_full,

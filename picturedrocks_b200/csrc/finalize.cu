@@ -374,10 +374,11 @@ struct SelFuse {
     uint8_t *sx;
 };
 
-// VM: hits is v-major, hits[g][slot][v][4] (x_j - 1 in the last, padded dimension: what the
-// streamed lane-run kernel of vell2.cu stores with one 16-byte write per run) instead of
-// hits[g][y][x_j - 1][v]; the slots of class y are [cls_slot0[y], cls_slot0[y+1]) — one per
-// segment of the class — or just y when cls_slot0 is NULL.
+// VM: hits is the v-major table of the streamed lane-run kernel (vell2.cu), uint16
+// hits[g][slot][v][4] with the counts of x_j - 1 = 0, 2, 1, 3 in the last dimension (one
+// 8-byte store per run), instead of int32 hits[g][y][x_j - 1][v]; the slots of class y are
+// [cls_slot0[y], cls_slot0[y+1]) — one per segment of the class, added up here — or just y when
+// cls_slot0 is NULL.  hits_stride counts 32-bit words in both cases.
 template <int TK1, int L, bool SEL, bool VM>
 __global__ void __launch_bounds__(256)
 k_finalize_direct_grp(int32_t *__restrict__ hits, int64_t hits_stride,
@@ -389,7 +390,8 @@ k_finalize_direct_grp(int32_t *__restrict__ hits, int64_t hits_stride,
                       const int32_t *__restrict__ cls_slot0)
 {
     constexpr int TK = TK1, KK = TK1 * TK1, NT = 1 + TK + TK * (TK + 1);
-    constexpr int SQ = VM ? TK * 4 : KK;  // ints of one class's hit square in memory
+    constexpr int SQ = VM ? TK * 4 : KK;  // counts of one class's hit square in registers
+    constexpr int SQW = VM ? TK * 2 : KK; // 32-bit words of one slot's square in memory
     auto at = [](int a, int v) { return VM ? v * 4 + a : a * TK + v; };
     const int lane = threadIdx.x & 31;
     const int sub = lane & (L - 1);
@@ -427,30 +429,48 @@ k_finalize_direct_grp(int32_t *__restrict__ hits, int64_t hits_stride,
             bool any = false;
             const int sl0 = (VM && cls_slot0) ? cls_slot0[y] : y;
             const int sl1 = (VM && cls_slot0) ? cls_slot0[y + 1] : y + 1;
-            if (hrow) {
+            if (hrow && VM) {
+#pragma unroll
+                for (int i = 0; i < SQ; ++i) x[i] = 0;
+                for (int sl = sl0; sl < sl1; ++sl) {  // the segments of the class
+                    uint32_t *hr = reinterpret_cast<uint32_t *>(hrow) + (int64_t)sl * SQW;
+                    uint32_t w[SQW];
+                    if (SQW % 4 == 0) {
+#pragma unroll
+                        for (int q = 0; q < SQW / 4; ++q) {
+                            const uint4 t4 = *reinterpret_cast<const uint4 *>(hr + 4 * q);
+                            w[4 * q] = t4.x, w[4 * q + 1] = t4.y, w[4 * q + 2] = t4.z, w[4 * q + 3] = t4.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < SQW / 2; ++q) {
+                            const uint2 t2 = *reinterpret_cast<const uint2 *>(hr + 2 * q);
+                            w[2 * q] = t2.x, w[2 * q + 1] = t2.y;
+                        }
+                    }
+                    uint32_t nz = 0;
+#pragma unroll
+                    for (int v = 0; v < TK; ++v) {
+                        const uint32_t w02 = w[2 * v], w13 = w[2 * v + 1];
+                        nz |= w02 | w13;
+                        x[v * 4 + 0] += (int)(w02 & 0xFFFFu);
+                        x[v * 4 + 2] += (int)(w02 >> 16);
+                        x[v * 4 + 1] += (int)(w13 & 0xFFFFu);
+                        x[v * 4 + 3] += (int)(w13 >> 16);
+                    }
+                    if (nz && active) {  // leave the buffer clean for the next pass
+#pragma unroll
+                        for (int q = 0; q < SQW / 2; ++q)
+                            *reinterpret_cast<uint2 *>(hr + 2 * q) = make_uint2(0u, 0u);
+                    }
+                }
+            } else if (hrow) {
                 int32_t *hr = hrow + (int64_t)sl0 * SQ;
                 if (SQ % 4 == 0) {
 #pragma unroll
                     for (int q = 0; q < SQ / 4; ++q) {
                         const int4 w = *reinterpret_cast<const int4 *>(hr + 4 * q);
                         x[4 * q] = w.x, x[4 * q + 1] = w.y, x[4 * q + 2] = w.z, x[4 * q + 3] = w.w;
-                    }
-                    if (VM) {
-                        for (int sl = sl0 + 1; sl < sl1; ++sl) {  // further segments of the class
-                            int32_t *h2 = hrow + (int64_t)sl * SQ;
-                            bool nz = false;
-#pragma unroll
-                            for (int q = 0; q < SQ / 4; ++q) {
-                                const int4 w = *reinterpret_cast<const int4 *>(h2 + 4 * q);
-                                x[4 * q] += w.x, x[4 * q + 1] += w.y, x[4 * q + 2] += w.z, x[4 * q + 3] += w.w;
-                                nz |= (w.x | w.y | w.z | w.w) != 0;
-                            }
-                            if (nz && active) {
-#pragma unroll
-                                for (int q = 0; q < SQ / 4; ++q)
-                                    *reinterpret_cast<int4 *>(h2 + 4 * q) = make_int4(0, 0, 0, 0);
-                            }
-                        }
                     }
                 } else {
 #pragma unroll
@@ -490,7 +510,7 @@ k_finalize_direct_grp(int32_t *__restrict__ hits, int64_t hits_stride,
 #pragma unroll
                 for (int v = 0; v < TK; ++v) t[2 + TK + a * (TK + 1) + v] = T(x[at(a, v)]);
             }
-            if (any && active) {  // leave the buffer clean for the next pass
+            if (!VM && any && active) {  // leave the buffer clean for the next pass
                 int32_t *hr = hrow + (int64_t)sl0 * SQ;
                 if (SQ % 4 == 0) {
 #pragma unroll
@@ -661,7 +681,7 @@ static int launch_direct(int32_t *hits, int64_t stride /* x_j-major */, const in
         const int threads = 256;
         const int L = grp_lanes(P, C);
         const int wm = out_marg != nullptr;
-        if (vmajor) stride = (int64_t)n_slot * TK1 * 4;
+        if (vmajor) stride = (int64_t)n_slot * TK1 * 2;
 #define PRB_FG(LL, VM)                                                                                  \
     k_finalize_direct_grp<TK1, LL, false, VM><<<(unsigned)ceil_div(P * LL, threads), threads, 0, st>>>( \
         hits, stride, cnt, clsz, hsize, hs_ysum, ha, C, table, N, P, out_full, out_marg, wm,            \
@@ -744,7 +764,7 @@ static int launch_update(int32_t *hits, const int32_t *cnt, const int64_t *clsz,
 {
     const int threads = 256;
     const int L = grp_lanes(P, C);
-    const int64_t stride = vmajor ? (int64_t)n_slot * TK1 * 4 : (int64_t)C * TK1 * TK1;
+    const int64_t stride = vmajor ? (int64_t)n_slot * TK1 * 2 : (int64_t)C * TK1 * TK1;
 #define PRB_FU(LL, VM)                                                                                 \
     k_finalize_direct_grp<TK1, LL, true, VM><<<(unsigned)ceil_div(P * LL, threads), threads, 0, st>>>( \
         hits, stride, cnt, clsz, hsize, hs_ysum, ha, C, table, N, P, nullptr, nullptr, want_marg,      \

@@ -32,6 +32,19 @@ __device__ __forceinline__ uint64_t v_policy_evict_first()
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
+__device__ __forceinline__ uint64_t v_policy_evict_last()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+// 8-byte store whose line should stay in L2 (a table that the next kernel reads back)
+__device__ __forceinline__ void v_store2_keep(uint32_t *p, uint32_t a, uint32_t b, uint64_t policy)
+{
+    asm volatile("st.global.L2::cache_hint.v2.b32 [%0], {%1, %2}, %3;" ::"l"(p), "r"(a), "r"(b),
+                 "l"(policy)
+                 : "memory");
+}
 __device__ __forceinline__ void v_bulk_load_hint(uint32_t dst, const void *src, uint32_t bytes,
                                                  uint32_t bar, uint64_t policy)
 {

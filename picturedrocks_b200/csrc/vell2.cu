@@ -24,11 +24,14 @@
 //   * The flush of a bundle was 38 % of the launch (measured by leaving it out: 0.81 ms
 //     instead of 1.30 ms at config 4): 27 M scalar REDs to random sectors of the 107 MB hits
 //     table, every one a read-modify-write that usually misses L2 because the stream keeps
-//     flushing the cache.  Now hits is stored v-major — hits[g][y][v][a], the K-1 (padded to a
-//     multiple of 4) values of x_j contiguous — so a lane-run that holds a WHOLE run (nearly
-//     all do) writes its counts with plain 16-byte stores (the table is all zero between
-//     steps, and every run has exactly one writer); only the pieces of a run longer than the
-//     lane-run cap still use REDs.  The stream itself is loaded with an L2 evict-first policy.
+//     flushing the cache.  Now hits is stored v-major with one slot per SEGMENT —
+//     hits[g][segment][v][x_j - 1], 16-bit counts (a segment has at most 32 752 cells), the
+//     values of x_j contiguous — so a lane-run that holds a WHOLE run (nearly all do) writes
+//     its counts with ONE plain 8-byte store (the table is all zero between steps and every run
+//     has exactly one writer; the finalize kernels add the segments of a class); only the
+//     pieces of a run longer than the lane-run cap still use REDs.  The table is half the size
+//     (54 MB at config 4), its stores carry an L2 evict-last policy and the stream is loaded
+//     evict-first, so the table stays in L2 from its first write to the finalize kernel.
 // Counting itself is unchanged: LDS.U8 (shift code of x_j at the entry's cell) -> SHL -> ADD
 // into 8-bit fields of one register per four values of x_j, widened to 16-bit fields every
 // <= 127 rows.
@@ -67,16 +70,18 @@ struct E2Cfg {
 // cta_ph0    int32[gridDim.x + 1]: phases of every CTA
 // sx         uint8[n_st * 32768 (+ slack)]: shift codes in the padded cell space; slot 32767 of
 //            every tile stays PRB_SX_NONE (what padding entries point at)
-// hits       VM: int32[P][n_slot][K1][4 * NREG] (v-major, see above), all zero on entry; the
-//            slot of a run is the id field of its header when n_slot > 1, else 0; always_add:
-//            several runs share a slot (a call without labels on a layout cut by class): add;
+// hits       VM: uint16[P][n_slot][K1][4 * NREG] (v-major, see above; a slot = a segment, so a
+//            count is at most 32 752), all zero on entry; the four counts of register q of a
+//            run sit in the order x_j - 1 = 4q, 4q+2, 4q+1, 4q+3 (two 32-bit words as the lane
+//            holds them);
 //            !VM: int32[P][n_slot][K1][K1] (x_j-major, the layout of vell.cu), added to.
+//            The slot of a run is the id field of its header when n_slot > 1, else 0.
 //            PV = P * K1.
 template <typename CFG, int NREG, bool VM, bool TIMING>
 __global__ void __launch_bounds__(CFG::threads, 1)
 k_stream_ell2(const uint32_t *__restrict__ ell, const int32_t *__restrict__ item_row0,
               const int4 *__restrict__ phase, const int32_t *__restrict__ cta_ph0,
-              const uint8_t *__restrict__ sx, int K1, int n_slot, int id_shift, int always_add,
+              const uint8_t *__restrict__ sx, int K1, int n_slot, int id_shift,
               int32_t *__restrict__ hits, uint32_t PV, long long *timing)
 {
     constexpr int SR = CFG::stage_rows, STAGES = CFG::stages, STAGE_BYTES = CFG::stage_bytes;
@@ -102,6 +107,7 @@ k_stream_ell2(const uint32_t *__restrict__ ell, const int32_t *__restrict__ item
     __syncwarp();
     uint32_t n_issued = 0, n_consumed = 0;  // stages of this warp, over the whole launch
     const uint64_t policy = v_policy_evict_first();
+    const uint64_t policy_last = v_policy_evict_last();
     const int KK = K1 * K1;
     const uint32_t vg_mask = (1u << id_shift) - 1u;
     const int ph0 = cta_ph0[blockIdx.x], ph1 = cta_ph0[blockIdx.x + 1];
@@ -225,22 +231,26 @@ k_stream_ell2(const uint32_t *__restrict__ ell, const int32_t *__restrict__ item
                         if (vg < PV) {
                             const uint32_t g = vg / (uint32_t)K1, v = vg - g * (uint32_t)K1;
                             const uint32_t slot = n_slot > 1 ? (hdr & ~(E2_SPLIT | 0x80000000u)) >> id_shift : 0u;
-                            int32_t *out = VM ? hits + (((int64_t)g * n_slot + slot) * K1 + v) * (4 * NREG)
-                                              : hits + ((int64_t)g * n_slot + slot) * KK + v;
+                            const int64_t row = ((int64_t)g * n_slot + slot) * K1 + v;
 #pragma unroll
                             for (int q = 0; q < NREG; ++q) {
+                                // 16-bit counts of x_j - 1 = 4q (low) | 4q+2 (high) and 4q+1 | 4q+3
                                 const uint32_t w02 = wide[2 * q] + (acc[q] & 0x00FF00FFu);
                                 const uint32_t w13 = wide[2 * q + 1] + ((acc[q] >> 8) & 0x00FF00FFu);
-                                const uint32_t c[4] = {w02 & 0xFFFFu, w13 & 0xFFFFu, w02 >> 16, w13 >> 16};
-                                if (VM && !(hdr & E2_SPLIT) && !always_add) {
-                                    *reinterpret_cast<int4 *>(out + 4 * q) =
-                                        make_int4((int)c[0], (int)c[1], (int)c[2], (int)c[3]);
+                                if (VM) {
+                                    uint32_t *out = reinterpret_cast<uint32_t *>(hits) + row * (2 * NREG) + 2 * q;
+                                    if (!(hdr & E2_SPLIT)) {
+                                        v_store2_keep(out, w02, w13, policy_last);
+                                    } else {  // a piece of a run: the fields cannot carry into each other
+                                        if (w02) atomicAdd(out, w02);
+                                        if (w13) atomicAdd(out + 1, w13);
+                                    }
                                 } else {
+                                    int32_t *out = hits + ((int64_t)g * n_slot + slot) * KK + v;
+                                    const uint32_t c[4] = {w02 & 0xFFFFu, w13 & 0xFFFFu, w02 >> 16, w13 >> 16};
 #pragma unroll
                                     for (int f = 0; f < 4; ++f)
-                                        if (4 * q + f < K1 && c[f])
-                                            atomicAdd(VM ? out + 4 * q + f : out + (4 * q + f) * K1,
-                                                      (int)c[f]);
+                                        if (4 * q + f < K1 && c[f]) atomicAdd(out + (4 * q + f) * K1, (int)c[f]);
                                 }
                             }
                         }
@@ -297,7 +307,7 @@ extern "C" int prb_ell2_geometry(int *tile_cells, int *ctas, int *warps, int *ma
 
 extern "C" int prb_stream_ell2(const uint32_t *ell, const int32_t *item_row0, const int32_t *phase,
                                const int32_t *cta_ph0, int n_ctas, const uint8_t *sx, int K1,
-                               int n_slot, int id_shift, int always_add, int32_t *hits, int vmajor,
+                               int n_slot, int id_shift, int32_t *hits, int vmajor,
                                int64_t PV, int64_t *timing, prb_stream_t stream)
 {
     if (n_ctas == 0) return 0;
@@ -312,7 +322,7 @@ extern "C" int prb_stream_ell2(const uint32_t *ell, const int32_t *item_row0, co
         PRB_REQUIRE(smem <= devinfo().smem_optin, "not enough shared memory per block");
         PRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         kern<<<n_ctas, warps * 32, smem, S(stream)>>>(ell, item_row0, (const int4 *)phase, cta_ph0, sx,
-                                                      K1, n_slot, id_shift, always_add, hits, (uint32_t)PV,
+                                                      K1, n_slot, id_shift, hits, (uint32_t)PV,
                                                       (long long *)timing);
         return 0;
     };

@@ -502,13 +502,16 @@ class Engine:
             guide=float(env("PRB_ELL_GUIDE", 2.0)), max_rows=int(env("PRB_ELL_MAX_ROWS", 512)))
         torch.cuda.current_stream().synchronize()  # tmp / lr_* are released below
         del tmp, lr_src, lr_len, lr_hdr
-        cls_slot0 = None
-        if self.vmajor and pl["seg_class"] is not None:  # segments of class y: a slot range
-            cls_slot0 = torch.searchsorted(pl["seg_class"].contiguous(),
-                                           torch.arange(self.C + 1, dtype=torch.int32, device=dev)
-                                           ).to(torch.int32)
+        cls_slot0 = all_slot0 = None
+        if self.vmajor:  # segments of class y = a range of slots of the hit table
+            all_slot0 = torch.tensor([0, n_seg], dtype=torch.int32, device=dev)
+            cls_slot0 = all_slot0
+            if pl["seg_class"] is not None:
+                cls_slot0 = torch.searchsorted(
+                    pl["seg_class"].contiguous(),
+                    torch.arange(self.C + 1, dtype=torch.int32, device=dev)).to(torch.int32)
         self.v = dict(plan=pl, kind="ell2", ell=ell, n_bundles=n_bundles, seglen=seglen, rows=rows,
-                      id_shift=id_shift, cls_slot0=cls_slot0,
+                      id_shift=id_shift, cls_slot0=cls_slot0, all_slot0=all_slot0,
                       relabelled=pl["pos"] is not None, pos=pl["pos"], item_rows=0, cap=cap,
                       n_items=int(item_row0.size - 1), n_ctas=n_ctas,
                       srow0=srow0_32 if env("PRB_ELL_KEEP_PLAN") else None,
@@ -525,25 +528,17 @@ class Engine:
     def _v(self):
         return self.v if self.v is not None else self._build_v()
 
-    def _hit_slots(self, with_y, v):
-        """(slots per gene in the hit table of the V path, "several runs share a slot").
-        v-major table: one slot per segment when the call conditions on the labels (the
-        finalize kernels add the segments of a class), a single shared one otherwise."""
-        C = self.C if with_y else 1
-        if not self.vmajor:
-            return C, 0
-        n_seg = v["plan"]["n_seg"]
-        if with_y and v["cls_slot0"] is not None:
-            return n_seg, 0
-        return 1, int(n_seg > 1)
-
     def _hits_v(self, with_y, v):
-        """The zeroed hit table for one pass of the V path + what the finalize kernels need
-        to read it: (hits, cls_slot0, n_slot)."""
-        n_slot, _ = self._hit_slots(with_y, v)
-        per_slot = self.K1 * (4 if self.vmajor else self.K1)
-        cls_slot0 = v.get("cls_slot0") if (self.vmajor and n_slot > 1) else None
-        return self.hits_buffer(n_slot * per_slot), cls_slot0, n_slot
+        """The zeroed hit table for one pass of the V path + what the kernels need to address
+        it: (hits, cls_slot0, n_slot).  v-major table (csrc/vell2.cu): one slot per SEGMENT
+        (16-bit counts); the finalize kernels add the slots [cls_slot0[y], cls_slot0[y+1]) of
+        class y — all of them in a call that does not condition on the labels."""
+        if not self.vmajor:
+            C = self.C if with_y else 1
+            return self.hits_buffer(C * self.K1 * self.K1), None, C
+        n_seg = v["plan"]["n_seg"]
+        cls_slot0 = v["cls_slot0"] if with_y else v["all_slot0"]
+        return self.hits_buffer(n_seg * self.K1 * 2), cls_slot0, n_seg
 
     def _vpos(self, v):
         """Position of every cell in the per-cell vectors of the V path (sx): the class-sorted
@@ -587,10 +582,10 @@ class Engine:
         v = self._v()
         pl = v["plan"]
         if self.ell2:
-            n_slot, always_add = self._hit_slots(with_y, v)
+            n_slot = v["plan"]["n_seg"] if self.vmajor else C
             nat.call("prb_stream_ell2", nat.ptr(v["ell"]), nat.ptr(v["item_row0"]),
                      nat.ptr(v["phase"]), nat.ptr(v["cta_ph0"]), v["n_ctas"], nat.ptr(self.sx),
-                     self.K1, n_slot, v["id_shift"], always_add, nat.ptr(hits), int(self.vmajor),
+                     self.K1, n_slot, v["id_shift"], nat.ptr(hits), int(self.vmajor),
                      self.P * self.K1, nat.ptr(getattr(self, "ell_timing", None)), nat.stream())
             return
         if self.ell:
