@@ -437,7 +437,7 @@ def measure_resident(ctx, wname, selector, steps, warmup, skip_stream=False, sam
     nnz_local = eng.nnz
     nnz_total = int(ctx.sum_over_ranks(float(nnz_local)))
     if eng.vmode and eng.v is not None:
-        kernel = "k_stream_ell" if eng.ell else "k_stream_v"
+        kernel = "k_stream_ell2" if eng.ell2 else ("k_stream_ell" if eng.ell else "k_stream_v")
         bytes_entry = 2.0 if (eng.ell or eng.v16) else 4.0
         stream_bytes = 128 * eng.v["rows"]
     else:

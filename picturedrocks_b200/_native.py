@@ -48,7 +48,8 @@ _SIGS = {
     "prb_scatter_gene_u8": [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
     "prb_scatter_gene_or32": [_vp, _vp, _vp, _i64, _int, _vp, _vp],
     "prb_pick_scatter": [_vp, _int, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
-                         _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp],
+                         _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp, _vp, _vp, _vp],
+    "prb_peer_share": [_vp, _vp, _int, _int, _vp, _vp],
     "prb_v_scatter_flat": [_vp, _vp, _i64, _vp, _vp, _int, _int, _vp, _vp, _vp, _vp, _vp],
     "prb_ell_build": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _int, _vp],
     "prb_ell2_geometry": [ctypes.POINTER(_int), ctypes.POINTER(_int), ctypes.POINTER(_int),
@@ -138,7 +139,7 @@ class PrbError(RuntimeError):
 KERNELS = {
     "prb_pack_csc": 1, "prb_unpack_csc": 1, "prb_pack_chunk": 1, "prb_check_columns": 1, "prb_dense_count_nnz": 1, "prb_dense_fill_csc": 1,
     "prb_tile_ptrs": 1, "prb_stream_hits": 1,
-    "prb_argmax_commit": 1, "prb_pick_scatter": 1, "prb_finalize_update": 1,
+    "prb_argmax_commit": 1, "prb_pick_scatter": 1, "prb_peer_share": 1, "prb_finalize_update": 1,
     "prb_v_unscatter": 1, "prb_best_record": 1, "prb_v_scatter_flat": 1, "prb_ell_build": 1,
     "prb_stream_ell": 1, "prb_stream_ell2": 1, "prb_v_count": 1, "prb_v_scatter": 1,
     "prb_stream_v": 1, "prb_scatter_gene_u8": 1,

@@ -81,6 +81,47 @@ class Comm:
         return buf
 
 
+class PeerRecords:
+    """The (score, index) records of all ranks, exchanged through NVLink peer memory instead
+    of an NCCL all-gather (csrc/peer.cu): every rank owns a buffer uint64[2][W][4] that all its
+    peers map through CUDA IPC (torch's own handle exchange) and write into directly.
+    `available(comm)`: NCCL backend, one node, PRB_PEER != 0."""
+
+    @staticmethod
+    def available(comm):
+        import os
+
+        return (comm is not None and comm.world > 1 and dist.get_backend(comm.group) == "nccl"
+                and os.environ.get("PRB_PEER", "1") != "0" and torch.cuda.is_available())
+
+    def __init__(self, comm):
+        W, dev = comm.world, torch.device("cuda", torch.cuda.current_device())
+        self.comm = comm
+        # an allocation of its own (not a slice of a cached block other tensors share)
+        self.local = torch.zeros(2 * W * 4, dtype=torch.int64, device=dev)
+        handle = self.local.untyped_storage()._share_cuda_()
+        handles = [None] * W
+        dist.all_gather_object(handles, handle, group=comm.group)
+        self._peer_storages, ptrs = [], []
+        for r in range(W):
+            if r == comm.rank:
+                ptrs.append(self.local.data_ptr())
+                continue
+            h = handles[r]
+            st = torch.UntypedStorage._new_shared_cuda(dev.index, *h[1:])
+            self._peer_storages.append(st)
+            ptrs.append(st.data_ptr())
+        self.peer_ptrs = torch.tensor(ptrs, dtype=torch.int64, device=dev)
+        self.xtag = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.err = torch.zeros(1, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        dist.barrier(group=comm.group)  # every buffer is mapped and zeroed before the first store
+
+    def check(self):
+        if int(self.err.item()):
+            raise RuntimeError("a peer rank did not deliver its candidate record within 4 s")
+
+
 def shutdown():
     """Release captured graphs, then tear the process group down."""
     import gc

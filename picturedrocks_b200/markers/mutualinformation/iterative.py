@@ -96,6 +96,13 @@ class _DeviceScores:
         self.n_rec = 1 if self.comm is None else self.comm.world
         self.records = self.best if self.comm is None else torch.zeros(2 * self.n_rec, **f64)
         self.records_valid = False
+        # ... or written by the peers straight into this rank's buffer over NVLink (dist.PeerRecords)
+        self.peer = None
+        if self.fused and self.comm is not None:
+            from ...dist import PeerRecords
+
+            if PeerRecords.available(self.comm):
+                self.peer = PeerRecords(self.comm)
         self.S_dev = torch.zeros(self.P_total + 1, dtype=torch.int32, device=self.dev)
         self.n_sel = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.cand_valid = False
@@ -113,7 +120,10 @@ class _DeviceScores:
     # -- device steps ---------------------------------------------------------
     def _share_best(self):
         """records <- every rank's (score, index) record."""
-        if self.comm is not None:
+        if self.peer is not None:
+            nat.call("prb_peer_share", nat.ptr(self.best), nat.ptr(self.peer.peer_ptrs),
+                     self.comm.world, self.comm.rank, nat.ptr(self.peer.xtag), nat.stream())
+        elif self.comm is not None:
             import torch.distributed as dist
 
             dist.all_gather_into_tensor(self.records, self.best, group=self.comm.group)
