@@ -381,7 +381,8 @@ int prb_peer_share(const double *best, const uint64_t *const *peer_bufs, int W, 
  * record best double[2] = (score, index bits) of this rank (done by the last block; ticket:
  * device int32, zero on entry and exit; cand_score / cand_idx: scratch of
  * prb_finalize_update_blocks(P, C) entries) + the reset of column *gene_ptr of sx to 255.
- * Supervised kinds use H(y,x_j,x_g) and H(x_j,x_g); PRB_SEL_CIFE_UNSUP (C = 1) H(x_j,x_g). */
+ * Supervised kinds use H(y,x_j,x_g) and H(x_j,x_g); PRB_SEL_CIFE_UNSUP (C = 1) H(x_j,x_g).
+ * peer_bufs != NULL: the last block also does prb_peer_share(best, peer_bufs, W, rank, xtag). */
 int64_t prb_finalize_update_blocks(int64_t P, int C);
 int prb_finalize_update(int32_t *hits, const int32_t *cnt, const int64_t *classsizes,
                         const int32_t *hsize, const int32_t *hs_ysum, const int32_t *ha, int C,
@@ -392,7 +393,8 @@ int prb_finalize_update(int32_t *hits, const int32_t *cnt, const int64_t *classs
                         double *cand_score, int64_t *cand_idx, double *best, int32_t *ticket,
                         const uint32_t *col_packed, const int64_t *col_begin,
                         const int64_t *col_end, const int32_t *newpos, uint8_t *sx, int vmajor,
-                        const int32_t *cls_slot0, int n_slot, prb_stream_t stream);
+                        const int32_t *cls_slot0, int n_slot, const uint64_t *const *peer_bufs,
+                        int W, int rank, int32_t *xtag, prb_stream_t stream);
 /* sx <- 255 at the stored entries of gene *gene_ptr (after a stand-alone streaming pass). */
 int prb_v_unscatter(const int32_t *gene_ptr, const uint32_t *col_packed, const int64_t *col_begin,
                     const int64_t *col_end, const int32_t *newpos, uint8_t *sx,

@@ -62,7 +62,7 @@ _SIGS = {
     "prb_finalize_update_blocks": [_i64, _int],
     "prb_finalize_update": [_vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _vp, _i64, _i64, _int, _int,
                             _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp,
-                            _vp, _vp, _vp, _vp, _vp, _int, _vp, _int, _vp],
+                            _vp, _vp, _vp, _vp, _vp, _int, _vp, _int, _vp, _int, _int, _vp, _vp],
     "prb_v_unscatter": [_vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "prb_best_record": [_vp, _vp, _i64, _vp, _vp],
     "prb_state_direct": [_vp, _vp, _i64, _int, _int, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp],

@@ -372,7 +372,12 @@ struct SelFuse {
     const int64_t *col_begin, *col_end;
     const int32_t *newpos;
     uint8_t *sx;
+    // gene-sharded run: the record goes straight into the peers' buffers (peer.cu), W > 0
+    unsigned long long *const *peer_bufs;
+    int W, rank;
+    int *xtag;
 };
+
 
 // VM: hits is the v-major table of the streamed lane-run kernel (vell2.cu), uint16
 // hits[g][slot][v][4] with the counts of x_j - 1 = 0, 2, 1, 3 in the last dimension (one
@@ -412,6 +417,8 @@ k_finalize_direct_grp(int32_t *__restrict__ hits, int64_t hits_stride,
     }
     const int32_t *crow = cnt + g * (int64_t)C * TK;
     int32_t *hrow = hits ? hits + g * hits_stride : nullptr;
+    // (a shared-memory copy of the first 4 096 terms was measured: no gain at config 4, where the
+    // gathers then pay bank conflicts instead of L2 sectors, and a loss for small gene counts)
     auto T = [&](int c) -> double { return c ? __ldg(term + c) : 0.0; };
     int m2[KK], xc[TK];
 #pragma unroll
@@ -615,10 +622,32 @@ k_finalize_direct_grp(int32_t *__restrict__ hits, int64_t hits_stride,
             }
         }
         block_argmax<256>(sc, idx);
+        __shared__ double s_sc;
+        __shared__ int64_t s_idx;
         if (threadIdx.x == 0) {
             sel.best[0] = sc;
             ((int64_t *)sel.best)[1] = idx;
             *sel.ticket = 0;
+            s_sc = sc;
+            s_idx = idx;
+        }
+        if (sel.W > 0) {  // k_peer_share (peer.cu), fused in
+            __syncthreads();
+            const int tag = *sel.xtag + 1;
+            if (threadIdx.x < sel.W) {
+                unsigned long long *slot =
+                    sel.peer_bufs[threadIdx.x] + ((size_t)(tag & 1) * sel.W + sel.rank) * 4;
+                asm volatile("st.global.v2.b64 [%0], {%1, %2};" ::"l"(slot),
+                             "l"((unsigned long long)__double_as_longlong(s_sc)),
+                             "l"((unsigned long long)s_idx)
+                             : "memory");
+                __threadfence_system();
+                asm volatile("st.release.sys.global.b64 [%0], %1;" ::"l"(slot + 2),
+                             "l"((unsigned long long)tag)
+                             : "memory");
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) *sel.xtag = tag;
         }
     }
 }
@@ -801,9 +830,12 @@ extern "C" int prb_finalize_update(int32_t *hits, const int32_t *cnt, const int6
                                    const uint32_t *col_packed, const int64_t *col_begin,
                                    const int64_t *col_end, const int32_t *newpos, uint8_t *sx,
                                    int vmajor, const int32_t *cls_slot0, int n_slot,
-                                   prb_stream_t stream)
+                                   const uint64_t *const *peer_bufs, int W, int rank,
+                                   int32_t *xtag, prb_stream_t stream)
 {
     PRB_REQUIRE(P >= 1 && C >= 1 && K >= 2 && K <= 5, "the fused step tail needs 2 <= K <= 5");
+    PRB_REQUIRE(peer_bufs == nullptr || (W >= 1 && W <= 256 && rank >= 0 && rank < W && xtag),
+                "bad peer buffer arguments");
     PRB_REQUIRE(!vmajor || n_slot >= 1, "v-major hits need the number of slots per gene");
     PRB_REQUIRE(kind == PRB_SEL_CIFE || kind == PRB_SEL_JMI || kind == PRB_SEL_CIFE_UNSUP,
                 "unknown selector kind");
@@ -814,7 +846,8 @@ extern "C" int prb_finalize_update(int32_t *hits, const int32_t *cnt, const int6
                 "null pointer");
     SelFuse sel{kind, is_remove, base, penalty, score, selected, Hx_all, Hyx_all, gene_ptr,
                 n_sel_ptr, gene_lo, cand_score, cand_idx, best, ticket, col_packed, col_begin,
-                col_end, newpos, sx};
+                col_end, newpos, sx, (unsigned long long *const *)peer_bufs, peer_bufs ? W : 0,
+                rank, xtag};
     const int want_marg = kind != PRB_SEL_CIFE_UNSUP;
 #define PRB_LU(T)                                                                               \
     return launch_update<T>(hits, cnt, classsizes, hsize, hs_ysum, ha, C, table, N, P, want_marg, \

@@ -642,6 +642,7 @@ class Engine:
         hits, cls_slot0, n_slot = self._hits_v(with_y, v)
         self._stream_v(with_y, C, hits)
         newpos = self._vpos(v)
+        peer = getattr(sel, "peer", None)  # the step's record goes out from the kernel's tail
         nat.call("prb_finalize_update", nat.ptr(hits), nat.ptr(cnt), nat.ptr(clsz),
                  nat.ptr(self.hsize), nat.ptr(self.hs_ysum), nat.ptr(self.ha), C, self.K,
                  nat.ptr(self.term), self.N, self.P, kind, int(is_remove), nat.ptr(sel.base),
@@ -651,6 +652,8 @@ class Engine:
                  nat.ptr(sel.cand_idx), nat.ptr(sel.best), nat.ptr(self.ticket),
                  nat.ptr(self.col_packed), nat.ptr(self.col_begin), nat.ptr(self.col_end),
                  nat.ptr(newpos), nat.ptr(self.sx), int(self.vmajor), nat.ptr(cls_slot0), n_slot,
+                 nat.ptr(peer.peer_ptrs) if peer else None, peer.comm.world if peer else 0,
+                 peer.comm.rank if peer else 0, nat.ptr(peer.xtag) if peer else None,
                  nat.stream())
 
     # --------------------------------------------------------------- primitives

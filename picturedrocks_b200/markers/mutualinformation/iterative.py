@@ -143,7 +143,8 @@ class _DeviceScores:
                          self.n_blocks, nat.ptr(self.best), s)
             self._share_best()
         self.engine.fused_step(self, _KIND[kind], is_remove, pick)
-        self._share_best()
+        if self.peer is None:  # (with peer buffers prb_finalize_update has sent the record)
+            self._share_best()
 
     def pick_and_commit(self):
         """best_idx <- argmax(score) (global index; lowest index on ties), then commit it:
