@@ -232,7 +232,9 @@ int prb_v_check_smem_base(void);
  *    (the bundles of at most two consecutive tiles) and a phase into at most `max_items` work
  *    items of decreasing size: item_row0 int32[n_items + 1] (first stream row of every item, the
  *    items of all phases back to back), phase int32[n_phases][4] = {first tile, tiles (1 or 2),
- *    first item, items}, cta_ph0 int32[n_ctas + 1].
+ *    first item, items}, cta_ph0 int32[n_ctas + 1] = the phases of every CTA's own chunk; the
+ *    phases [pool0, pool1) form a pool that the CTAs draw from once their chunk is done,
+ *    through the device counter *pool_ctr (zero on entry: prb_pick_scatter resets it).
  * prb_stream_ell2, vmajor = 0: adds the joint counts to hits int32[P][n_slot][K-1][K-1];
  * vmajor = 1: hits uint16[P][n_slot][K-1][4 * ceil((K-1)/4)] with one slot per SEGMENT (a count
  * is at most 32 752), the counts of x_j - 1 = 4q, 4q+2, 4q+1, 4q+3 in the last dimension, all
@@ -244,7 +246,8 @@ int prb_v_check_smem_base(void);
  * work item (tuning runs, K <= 5). */
 int prb_ell2_geometry(int *tile_cells, int *ctas, int *warps, int *max_items);
 int prb_stream_ell2(const uint32_t *ell, const int32_t *item_row0, const int32_t *phase,
-                    const int32_t *cta_ph0, int n_ctas, const uint8_t *sx, int K1, int n_slot,
+                    const int32_t *cta_ph0, int n_ctas, int pool0, int pool1, int32_t *pool_ctr,
+                    const uint8_t *sx, int K1, int n_slot,
                     int id_shift, int32_t *hits, int vmajor, int64_t PV, int64_t *timing,
                     prb_stream_t stream);
 

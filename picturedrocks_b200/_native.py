@@ -54,7 +54,8 @@ _SIGS = {
     "prb_ell_build": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _int, _vp],
     "prb_ell2_geometry": [ctypes.POINTER(_int), ctypes.POINTER(_int), ctypes.POINTER(_int),
                           ctypes.POINTER(_int)],
-    "prb_stream_ell2": [_vp, _vp, _vp, _vp, _int, _vp, _int, _int, _int, _vp, _int, _i64, _vp, _vp],
+    "prb_stream_ell2": [_vp, _vp, _vp, _vp, _int, _int, _int, _vp, _vp, _int, _int, _int, _vp, _int,
+                        _i64, _vp, _vp],
     "prb_stream_ell": [_vp, _vp, _vp, _i64, _int, _vp, _vp, _vp, _int, _i64, _vp, _int, _vp, _vp, _vp,
                        _vp, _i64, _int, _i64, _vp, _vp],
     "prb_ell_warps": [],

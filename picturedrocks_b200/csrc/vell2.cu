@@ -67,7 +67,9 @@ struct E2Cfg {
 // item_row0  int32[n_items + 1]: first row of every work item (items are consecutive)
 // phase      int4[n_phases]: x = first super-tile, y = tiles resident (1 or 2), z = first item,
 //            w = number of items (<= E2_MAX_ITEMS)
-// cta_ph0    int32[gridDim.x + 1]: phases of every CTA
+// cta_ph0    int32[gridDim.x + 1]: phases of every CTA's own chunk; the phases [pool0, pool1) are
+//            a pool the CTAs draw from afterwards through *pool_ctr (zero on entry), largest
+//            first: equal cost is not equal time
 // sx         uint8[n_st * 32768 (+ slack)]: shift codes in the padded cell space; slot 32767 of
 //            every tile stays PRB_SX_NONE (what padding entries point at)
 // hits       VM: uint16[P][n_slot][K1][4 * NREG] (v-major, see above; a slot = a segment, so a
@@ -80,8 +82,8 @@ struct E2Cfg {
 template <typename CFG, int NREG, bool VM, bool TIMING>
 __global__ void __launch_bounds__(CFG::threads, 1)
 k_stream_ell2(const uint32_t *__restrict__ ell, const int32_t *__restrict__ item_row0,
-              const int4 *__restrict__ phase, const int32_t *__restrict__ cta_ph0,
-              const uint8_t *__restrict__ sx, int K1, int n_slot, int id_shift,
+              const int4 *__restrict__ phase, const int32_t *__restrict__ cta_ph0, int pool0,
+              int pool1, int *pool_ctr, const uint8_t *__restrict__ sx, int K1, int n_slot, int id_shift,
               int32_t *__restrict__ hits, uint32_t PV, long long *timing)
 {
     constexpr int SR = CFG::stage_rows, STAGES = CFG::stages, STAGE_BYTES = CFG::stage_bytes;
@@ -111,9 +113,26 @@ k_stream_ell2(const uint32_t *__restrict__ ell, const int32_t *__restrict__ item
     const int KK = K1 * K1;
     const uint32_t vg_mask = (1u << id_shift) - 1u;
     const int ph0 = cta_ph0[blockIdx.x], ph1 = cta_ph0[blockIdx.x + 1];
-    for (int ph = ph0; ph < ph1; ++ph) {
+    // the claim of a pool phase is a global atomic: thread 0 issues it one phase ahead
+    int pool_next = 0;
+    if (tid == 0 && pool1 > pool0) pool_next = pool0 + atomicAdd(pool_ctr, 1);
+    bool first_phase = true;
+    for (int ph = ph0;; ++ph) {
+        if (ph >= ph1 && ph < pool0) ph = pool0;  // own chunk done
+        if (ph >= pool0) {
+            if (pool1 <= pool0) break;
+            __syncthreads();  // (also: every warp has left the previous phase)
+            if (tid == 0) {
+                s_ctl[1] = pool_next;
+                if (pool_next < pool1) pool_next = pool0 + atomicAdd(pool_ctr, 1);
+            }
+            __syncthreads();
+            ph = s_ctl[1];
+            if (ph >= pool1) break;
+        }
         const int4 pd = __ldg(phase + ph);
-        if (ph != ph0) __syncthreads();  // every warp has left the previous phase
+        if (!first_phase) __syncthreads();  // every warp has left the previous phase
+        first_phase = false;
         for (int i = tid; i < pd.y * (E2_HALF / 16); i += THREADS) {
             const int t = pd.x + i / (E2_HALF / 16), o = i % (E2_HALF / 16);
             ((uint4 *)smem_raw)[(t & 1) * (E2_HALF / 16) + o] =
@@ -306,7 +325,8 @@ extern "C" int prb_ell2_geometry(int *tile_cells, int *ctas, int *warps, int *ma
 }
 
 extern "C" int prb_stream_ell2(const uint32_t *ell, const int32_t *item_row0, const int32_t *phase,
-                               const int32_t *cta_ph0, int n_ctas, const uint8_t *sx, int K1,
+                               const int32_t *cta_ph0, int n_ctas, int pool0, int pool1,
+                               int32_t *pool_ctr, const uint8_t *sx, int K1,
                                int n_slot, int id_shift, int32_t *hits, int vmajor,
                                int64_t PV, int64_t *timing, prb_stream_t stream)
 {
@@ -318,10 +338,12 @@ extern "C" int prb_stream_ell2(const uint32_t *ell, const int32_t *item_row0, co
     PRB_REQUIRE(PV >= 1 && PV < (int64_t)(1 << id_shift) - 1,
                 "too many virtual genes for the header's gene field");
     PRB_REQUIRE(n_ctas >= 1 && n_ctas <= 65535, "bad grid");
+    PRB_REQUIRE(pool1 <= pool0 || pool_ctr != nullptr, "the pool needs its counter");
     auto launch = [&](auto kern, int smem, int warps) -> int {
         PRB_REQUIRE(smem <= devinfo().smem_optin, "not enough shared memory per block");
         PRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        kern<<<n_ctas, warps * 32, smem, S(stream)>>>(ell, item_row0, (const int4 *)phase, cta_ph0, sx,
+        kern<<<n_ctas, warps * 32, smem, S(stream)>>>(ell, item_row0, (const int4 *)phase, cta_ph0,
+                                                      pool0, pool1, pool_ctr, sx,
                                                       K1, n_slot, id_shift, hits, (uint32_t)PV,
                                                       (long long *)timing);
         return 0;

@@ -496,10 +496,11 @@ class Engine:
                  nat.stream())
         tb = torch.cat([tile_b0, tile_b0.new_tensor([n_bundles])]).cpu().numpy()
         env = os.environ.get
-        item_row0, phase, cta_ph0 = vplan.ell2_chunks(
+        item_row0, phase, cta_ph0, pool0 = vplan.ell2_chunks(
             srow0.cpu().numpy(), tb, n_ctas, warps, max_items,
             bundle_cost=int(env("PRB_ELL_BCOST", 16)), min_rows=int(env("PRB_ELL_MIN_ROWS", 40)),
-            guide=float(env("PRB_ELL_GUIDE", 2.0)), max_rows=int(env("PRB_ELL_MAX_ROWS", 512)))
+            guide=float(env("PRB_ELL_GUIDE", 2.0)), max_rows=int(env("PRB_ELL_MAX_ROWS", 512)),
+            pool_frac=float(env("PRB_ELL_POOL", 0.15)), pool_unit=float(env("PRB_ELL_POOL_UNIT", 8000)))
         torch.cuda.current_stream().synchronize()  # tmp / lr_* are released below
         del tmp, lr_src, lr_len, lr_hdr
         cls_slot0 = all_slot0 = None
@@ -513,7 +514,8 @@ class Engine:
         self.v = dict(plan=pl, kind="ell2", ell=ell, n_bundles=n_bundles, seglen=seglen, rows=rows,
                       id_shift=id_shift, cls_slot0=cls_slot0, all_slot0=all_slot0,
                       relabelled=pl["pos"] is not None, pos=pl["pos"], item_rows=0, cap=cap,
-                      n_items=int(item_row0.size - 1), n_ctas=n_ctas,
+                      n_items=int(item_row0.size - 1), n_ctas=n_ctas, pool0=pool0,
+                      pool1=int(phase.shape[0]),
                       srow0=srow0_32 if env("PRB_ELL_KEEP_PLAN") else None,
                       item_row0=torch.from_numpy(item_row0).to(dev),
                       phase=torch.from_numpy(phase).to(dev).contiguous(),
@@ -584,7 +586,8 @@ class Engine:
         if self.ell2:
             n_slot = v["plan"]["n_seg"] if self.vmajor else C
             nat.call("prb_stream_ell2", nat.ptr(v["ell"]), nat.ptr(v["item_row0"]),
-                     nat.ptr(v["phase"]), nat.ptr(v["cta_ph0"]), v["n_ctas"], nat.ptr(self.sx),
+                     nat.ptr(v["phase"]), nat.ptr(v["cta_ph0"]), v["n_ctas"], v["pool0"],
+                     v["pool1"], nat.ptr(self.counters), nat.ptr(self.sx),
                      self.K1, n_slot, v["id_shift"], nat.ptr(hits), int(self.vmajor),
                      self.P * self.K1, nat.ptr(getattr(self, "ell_timing", None)), nat.stream())
             return

@@ -190,25 +190,50 @@ def guided_cuts(cost, n_claimers, min_cost, guide=2.0, max_cost=None):
 
 
 def ell2_chunks(srow0, tile_b, n_ctas, warps, max_items, bundle_cost=16, min_rows=40, guide=2.0,
-                max_rows=512):
+                max_rows=512, pool_frac=0.15, pool_unit=8000, pool_min=150000):
     """Work plan of k_stream_ell2 (csrc/vell2.cu).  srow0 int64[nb+1]: first STREAM row of every
     bundle (header rows included); tile_b int64[n_st+1]: first bundle of every super-tile.
-    The bundles are cut into n_ctas chunks of equal cost (rows + bundle_cost per bundle), a chunk
-    into phases (its bundles of at most two consecutive tiles) and a phase into work items of at
-    most max_rows rows (guided_cuts).
-    Returns (item_row0 int32[n_items+1], phase int32[n_ph][4] = first tile, tiles, first item,
-    items; cta_ph0 int32[n_ctas+1])."""
+    The bundles are cut into n_ctas stretches of equal cost (rows + bundle_cost per bundle).  The
+    first 1 - pool_frac of a stretch is the CTA's own chunk; the rest goes, in units of about
+    pool_unit cost, into a POOL that CTAs draw from (largest units first) once their own chunk
+    is done — equal cost is not equal time (the same chunk runs up to 25 % faster or slower
+    depending on the SM and on which part of the hit table it writes).  Chunks below pool_min
+    cost get no pool.  A chunk or unit is cut
+    into phases (its bundles of at most two consecutive tiles) and a phase into work items of
+    at most max_rows rows (guided_cuts).
+    Returns (item_row0 int32[n_items+1] in stream order; phase int32[n_ph][4] = first tile,
+    tiles, first item, items — the phases of the chunks CTA by CTA, then the pool's;
+    cta_ph0 int32[n_ctas+1]; pool0 = index of the first pool phase)."""
     srow0 = np.asarray(srow0, dtype=np.int64)
     tile_b = np.asarray(tile_b, dtype=np.int64)
     nb, n_st = len(srow0) - 1, len(tile_b) - 1
     cost = srow0 + bundle_cost * np.arange(nb + 1, dtype=np.int64)
-    cb = np.searchsorted(cost, cost[-1] * np.arange(n_ctas + 1, dtype=np.float64) / n_ctas, side="left")
-    cb[0], cb[-1] = 0, nb
-    cb = np.maximum.accumulate(np.minimum(cb, nb))
-    item_row0, phases, cta_ph0 = [], [], [0]
-    n_it = 0
-    for c in range(n_ctas):
-        b, b1 = int(cb[c]), int(cb[c + 1])
+    total = float(cost[-1])
+
+    # pieces in stream order: (owner CTA or -1 for the pool, first bundle, end bundle)
+    per = total / n_ctas
+    # (a pool phase costs a claim, a tile load and two barriers: measured worth it only for
+    # chunks of >= ~150 000 rows — config 4 on one GPU: -2.5 % —, a loss on a 1/8 gene shard)
+    n_units = int(min(4, round(pool_frac * per / pool_unit))) if (pool_frac > 0 and per >= pool_min) else 0
+    k = np.arange(n_units + 1, dtype=np.float64)
+    rel = np.concatenate([[1.0 - pool_frac + pool_frac * kk / n_units for kk in k[:-1]], [1.0]]) \
+        if n_units else np.array([1.0])
+    ends = (np.arange(n_ctas, dtype=np.float64)[:, None] + rel[None, :]).reshape(-1) * per
+    eb = np.searchsorted(cost.astype(np.float64), ends, side="left")
+    eb = np.maximum.accumulate(np.minimum(eb, nb))
+    eb[-1] = nb
+    pieces, b = [], 0
+    for i, e in enumerate(eb):
+        e = int(e)
+        if e > b:
+            c, u = divmod(i, n_units + 1)
+            pieces.append((c if u == 0 else -1, b, e))
+        b = max(b, e)
+    # phases and items of every piece, items numbered in stream order
+    item_row0, n_it = [], 0
+    own = [[] for _ in range(n_ctas)]
+    pool = []
+    for o, b, b1 in pieces:
         while b < b1:
             t = int(np.searchsorted(tile_b, b, side="right")) - 1
             end = min(b1, int(tile_b[min(t + 2, n_st)]))
@@ -220,11 +245,20 @@ def ell2_chunks(srow0, tile_b, n_ctas, warps, max_items, bundle_cost=16, min_row
                     break
                 mc, xc = mc * 1.25, xc * 1.25
             item_row0.append(srow0[b + cuts])
-            phases.append((t, tiles, n_it, cuts.size))
+            ph = (t, tiles, n_it, cuts.size)
+            if o >= 0:
+                own[o].append(ph)
+            else:
+                pool.append((-(int(cost[end]) - int(cost[b])), len(pool), ph))
             n_it += cuts.size
             b = end
+    phases, cta_ph0 = [], [0]
+    for c in range(n_ctas):
+        phases.extend(own[c])
         cta_ph0.append(len(phases))
+    pool0 = len(phases)
+    phases.extend(ph for _, _, ph in sorted(pool))  # largest first
     item_row0.append(srow0[nb: nb + 1])
     return (np.concatenate(item_row0).astype(np.int32),
             np.asarray(phases, dtype=np.int32).reshape(-1, 4),
-            np.asarray(cta_ph0, dtype=np.int32))
+            np.asarray(cta_ph0, dtype=np.int32), pool0)
