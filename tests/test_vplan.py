@@ -148,3 +148,84 @@ def test_lane_run_plan_degenerate():
     _emulate_lane_run_layout(np.zeros(12, dtype=np.int64), 3, [0, 3], 64, 32, rng)  # empty matrix
     _emulate_lane_run_layout(np.array([0, 0, 1, 0], dtype=np.int64), 2, [0, 1, 2], 64, 32, rng)
     _emulate_lane_run_layout(np.full(40, 1, dtype=np.int64), 1, [0, 1], 2, 32, rng)
+
+
+# ---- the streamed lane-run layout (csrc/vell2.cu): chunks, phases, pool, items ---------------
+def _check_ell2_plan(srow0, tile_b, n_ctas, warps, max_items, **kw):
+    item_row0, phase, cta_ph0, pool0 = vplan.ell2_chunks(srow0, tile_b, n_ctas, warps, max_items, **kw)
+    nb = len(srow0) - 1
+    assert item_row0[0] == srow0[0] and item_row0[-1] == srow0[-1]
+    assert np.all(np.diff(item_row0) > 0) or nb == 0
+    assert set(item_row0.tolist()) <= set(np.asarray(srow0).tolist())  # items start at bundle starts
+    assert len(cta_ph0) == n_ctas + 1 and cta_ph0[0] == 0 and cta_ph0[-1] == pool0 <= len(phase)
+    assert np.all(np.diff(cta_ph0) >= 0)
+    covered = np.zeros(len(item_row0) - 1, dtype=np.int64)
+    for t0, nt, i0, n in phase:
+        assert 1 <= n <= max_items and nt in (1, 2)
+        covered[i0: i0 + n] += 1
+        # every bundle of the phase lies in tile t0 or (nt == 2) t0 + 1
+        b0 = np.searchsorted(srow0, item_row0[i0])
+        b1 = np.searchsorted(srow0, item_row0[i0 + n])
+        assert tile_b[t0] <= b0 and b1 <= tile_b[min(t0 + nt, len(tile_b) - 1)]
+    assert np.all(covered == 1)
+    # pool phases: largest first
+    bc = kw.get("bundle_cost", 16)
+    cost = [int(item_row0[i0 + n] - item_row0[i0])
+            + bc * int(np.searchsorted(srow0, item_row0[i0 + n]) - np.searchsorted(srow0, item_row0[i0]))
+            for _, _, i0, n in phase[pool0:]]
+    assert all(a >= b for a, b in zip(cost, cost[1:]))
+    return phase, cta_ph0, pool0
+
+
+def test_ell2_chunks_cover_every_bundle_once():
+    rng = np.random.RandomState(3)
+    L = rng.randint(1, 300, size=40000)
+    srow0 = np.concatenate([[0], np.cumsum(L + 1)]).astype(np.int64)
+    tile_b = np.array([0, 7000, 7000, 16000, 30000, 40000])
+    ph, cp, p0 = _check_ell2_plan(srow0, tile_b, 148, 32, 624)
+    assert p0 == len(ph)  # chunks of ~40 000 rows: below pool_min, no pool
+    ph, cp, p0 = _check_ell2_plan(srow0, tile_b, 148, 32, 624, pool_min=0, pool_unit=500)
+    assert p0 < len(ph)
+
+
+def test_ell2_chunks_small_and_degenerate():
+    rng = np.random.RandomState(4)
+    for nb in (0, 1, 5, 200, 3000):
+        L = rng.randint(1, 40, size=nb)
+        srow0 = np.concatenate([[0], np.cumsum(L + 1)]).astype(np.int64)
+        # many small tiles: chunks span more than two tiles -> several phases per CTA
+        n_t = 17
+        tile_b = np.unique(np.concatenate([[0, nb], rng.randint(0, nb + 1, size=n_t)]))
+        tile_b = np.sort(np.concatenate([tile_b, tile_b[1:2]]))  # an empty tile
+        _check_ell2_plan(srow0, tile_b, 148, 32, 624, pool_min=0, pool_unit=50)
+        _check_ell2_plan(srow0, tile_b, 4, 32, 16, pool_min=0, pool_unit=50)
+
+
+def test_guided_cuts_sizes():
+    cost = np.arange(0, 300001, 150, dtype=np.int64)  # bundles of 150 rows
+    cuts = vplan.guided_cuts(cost, 32, 40, 2.0, 512)
+    sizes = np.diff(np.concatenate([cost[cuts], cost[-1:]]))
+    assert cuts[0] == 0 and sizes.sum() == 300000
+    assert sizes.max() <= 512 + 150 and sizes[:100].min() >= 450  # capped items first
+    assert sizes[-1] <= 300  # small ones last
+
+
+def test_ell_plan_streamed_headers():
+    import torch
+
+    n_seg, st = 5, [0, 2, 5]
+    lens = torch.tensor([0, 3, 2500, 1, 7, 9, 0, 0, 40, 2], dtype=torch.int64)  # 2 virtual genes
+    run_start = torch.cumsum(lens, 0) - lens
+    seg_id = torch.tensor([4, 5, 6, 7, 8], dtype=torch.int64)
+    ep = vplan.ell_plan(lens, run_start, n_seg, st, 1024, seg_id=seg_id, id_shift=20)
+    hdr = ep["lr_hdr"].numpy().astype(np.int64) & 0xFFFFFFFF
+    ln = ep["lr_len"].numpy()
+    live = ln > 0
+    assert np.all((hdr[~live] & 0xFFFFF) == 0xFFFFF)  # empty lanes
+    vg = hdr[live] & 0xFFFFF
+    sid = (hdr[live] >> 20) & 0x3FF
+    split = (hdr[live] >> 30) & 1
+    assert set(vg.tolist()) <= {0, 1} and set(sid.tolist()) <= {4, 5, 6, 7, 8}
+    # the run of 2 500 entries is cut into three flagged pieces, nothing else is flagged
+    assert split.sum() == 3 and np.all(ln[live][split == 1] >= 833)
+    assert ln[live].sum() == int(lens.sum())
