@@ -385,7 +385,7 @@ struct SelFuse {
 // [cls_slot0[y], cls_slot0[y+1]) — one per segment of the class, added up here — or just y when
 // cls_slot0 is NULL.  hits_stride counts 32-bit words in both cases.
 template <int TK1, int L, bool SEL, bool VM>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 k_finalize_direct_grp(int32_t *__restrict__ hits, int64_t hits_stride,
                       const int32_t *__restrict__ cnt, const int64_t *__restrict__ clsz,
                       const int32_t *__restrict__ hsize, const int32_t *__restrict__ hs_ysum,
