@@ -18,6 +18,7 @@ def needs_build():
     deps = [os.path.join(CSRC, s) for s in SOURCES] + [
         os.path.join(CSRC, "common.cuh"),
         os.path.join(CSRC, "select.cuh"),
+        os.path.join(CSRC, "selfuse.cuh"),
         os.path.join(CSRC, "vcommon.cuh"),
         os.path.join(HERE, "..", "include", "prb200.h"),
     ]
@@ -46,7 +47,7 @@ def build(force=False, verbose=False):
             if verbose:
                 flags += ["-Xptxas", "-v"]
             os.makedirs(OBJ, exist_ok=True)
-            headers = [os.path.join(CSRC, h) for h in ("common.cuh", "select.cuh", "vcommon.cuh")] + [
+            headers = [os.path.join(CSRC, h) for h in ("common.cuh", "select.cuh", "selfuse.cuh", "vcommon.cuh")] + [
                 os.path.join(HERE, "..", "include", "prb200.h")]
             hdr_t = max(os.path.getmtime(h) for h in headers)
 

@@ -113,9 +113,10 @@ class Engine:
         # csrc/vell.cu (global work queue, side arrays for the bundle headers)
         self.ell2 = (self.ell and os.environ.get("PRB_ELL_V", "2") == "2"
                      and self.P * self.K1 < (1 << 22) - 1)
-        # ... whose hit table is v-major for K <= 5 (hits[g][segment][v][4], plain 16-byte
-        # stores; the header then carries a 10-bit segment and a 20-bit virtual gene)
-        self.vmajor = self.ell2 and self.K1 <= 4 and self.P * self.K1 < (1 << 20) - 1
+        # ... whose hit table is v-major for K <= 5 (16-bit counts, hits[g][segment][v][x_j - 1],
+        # plain 8-byte stores); the bundle header then carries the segment beside the virtual gene
+        self.vmajor = (self.ell2 and self.K1 <= 4
+                       and os.environ.get("PRB_ELL_VMAJOR", "1") != "0")
         self.vmode = USE_VLAYOUT and (self.ell or self.K1 <= 4)
         # warp-per-run layout: 16-bit entries, 64 per row (prb_v_scatter16 / prb_stream_v16);
         # PRB_V16=0 selects the 32-bit entries of round 1 (1.40 vs 1.80 ms at config 4)
@@ -470,10 +471,11 @@ class Engine:
         if not cap:
             cap = int(min(1024, max(64, (total // 64 // n_ctas // 4) * 2)))
         cap = min(cap, 32768) & ~1
-        if self.vmajor and n_seg > 1024:
-            self.vmajor = False
+        vg_bits = max(8, int(P * K1 + 1).bit_length())
+        if self.vmajor and n_seg > (1 << (30 - vg_bits)):
+            self.vmajor = False  # (segment and virtual gene do not fit one header word)
         if self.vmajor:  # the slot of a run in hits: its segment
-            seg_id, id_shift = torch.arange(n_seg, **i64), 20
+            seg_id, id_shift = torch.arange(n_seg, **i64), vg_bits
         else:            # ... its class
             seg_id = (pl["seg_class"].to(torch.int64) if pl["seg_class"] is not None
                       else torch.zeros(n_seg, **i64))
@@ -540,7 +542,8 @@ class Engine:
             return self.hits_buffer(C * self.K1 * self.K1), None, C
         n_seg = v["plan"]["n_seg"]
         cls_slot0 = v["cls_slot0"] if with_y else v["all_slot0"]
-        return self.hits_buffer(n_seg * self.K1 * 2), cls_slot0, n_seg
+        row_words = 2 * ((self.K1 + 3) // 4)  # 32-bit words of one (segment, v) row
+        return self.hits_buffer(n_seg * self.K1 * row_words), cls_slot0, n_seg
 
     def _vpos(self, v):
         """Position of every cell in the per-cell vectors of the V path (sx): the class-sorted

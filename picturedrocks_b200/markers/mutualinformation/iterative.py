@@ -77,7 +77,9 @@ class _DeviceScores:
         self.score = self.base.clone()
         self.selected = torch.zeros(max(self.P, 1), dtype=torch.uint8, device=self.dev)
         # V-layout path: the whole step runs in engine.fused_step (three launches)
-        self.fused = (e.vmode and e.K1 <= 4 and self.be.ycol is None
+        if e.vmode and self.be.ycol is None and e.P:
+            e._v()  # (the layout decides whether the hit table can be v-major)
+        self.fused = (e.vmode and (e.K1 <= 4 or e.vmajor) and self.be.ycol is None
                       and (self.comm is None or min(self.comm.shard_sizes) > 0))
         self.n_blocks = max(1, -(-self.P // 256))
         n_cand = self.n_blocks

@@ -40,7 +40,8 @@ def main():
         eng.v = None
         eng.epoch += 1
         eng.ell2 = eng.ell and os.environ.get("PRB_ELL_V", "2") == "2"
-        eng.vmajor = eng.ell2 and eng.K1 <= 4
+        eng.vmajor = (eng.ell2 and eng.K1 <= 4
+                      and os.environ.get("PRB_ELL_VMAJOR", "1") != "0")
         eng._hits = None
         inf = pr.markers.SparseInformationSet._from_engine(eng, yd)
         fs = pr.markers.CIFE(inf)
