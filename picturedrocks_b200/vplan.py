@@ -181,9 +181,11 @@ def guided_cuts(cost, n_claimers, min_cost, guide=2.0, max_cost=None):
         left.append(cur * np.power(1.0 - 1.0 / d, np.arange(1, n_g + 1)))
         cur = float(left[-1][-1])
     left.append(np.arange(cur - min_cost, 0.0, -min_cost))  # tail of min_cost items
-    pos = total - np.concatenate(left)
-    cuts = np.unique(np.searchsorted(np.asarray(cost, dtype=np.float64) - c0, pos, side="left"))
+    pos = (total + c0) - np.concatenate(left)  # ascending
+    cuts = np.searchsorted(cost, pos, side="left")
     cuts = cuts[cuts < n]
+    if cuts.size:
+        cuts = cuts[np.concatenate(([True], cuts[1:] != cuts[:-1]))]
     if cuts.size == 0 or cuts[0] != 0:
         cuts = np.concatenate([[0], cuts])
     return cuts.astype(np.int64)
@@ -207,7 +209,7 @@ def ell2_chunks(srow0, tile_b, n_ctas, warps, max_items, bundle_cost=16, min_row
     srow0 = np.asarray(srow0, dtype=np.int64)
     tile_b = np.asarray(tile_b, dtype=np.int64)
     nb, n_st = len(srow0) - 1, len(tile_b) - 1
-    cost = srow0 + bundle_cost * np.arange(nb + 1, dtype=np.int64)
+    cost = (srow0 + bundle_cost * np.arange(nb + 1, dtype=np.int64)).astype(np.float64)
     total = float(cost[-1])
 
     # pieces in stream order: (owner CTA or -1 for the pool, first bundle, end bundle)
@@ -219,7 +221,7 @@ def ell2_chunks(srow0, tile_b, n_ctas, warps, max_items, bundle_cost=16, min_row
     rel = np.concatenate([[1.0 - pool_frac + pool_frac * kk / n_units for kk in k[:-1]], [1.0]]) \
         if n_units else np.array([1.0])
     ends = (np.arange(n_ctas, dtype=np.float64)[:, None] + rel[None, :]).reshape(-1) * per
-    eb = np.searchsorted(cost.astype(np.float64), ends, side="left")
+    eb = np.searchsorted(cost, ends, side="left")
     eb = np.maximum.accumulate(np.minimum(eb, nb))
     eb[-1] = nb
     pieces, b = [], 0
@@ -249,7 +251,7 @@ def ell2_chunks(srow0, tile_b, n_ctas, warps, max_items, bundle_cost=16, min_row
             if o >= 0:
                 own[o].append(ph)
             else:
-                pool.append((-(int(cost[end]) - int(cost[b])), len(pool), ph))
+                pool.append((-(cost[end] - cost[b]), len(pool), ph))
             n_it += cuts.size
             b = end
     phases, cta_ph0 = [], [0]
