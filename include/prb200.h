@@ -231,8 +231,8 @@ int prb_v_check_smem_base(void);
  *  - the stream is cut on the host into one chunk of bundles per CTA, a chunk into phases
  *    (the bundles of at most two consecutive tiles) and a phase into at most `max_items` work
  *    items of decreasing size: item_row0 int32[n_items + 1] (first stream row of every item, the
- *    items of all phases back to back), phase int32[n_phases][4] = {first tile, tiles (1 or 2),
- *    first item, items}, cta_ph0 int32[n_ctas + 1] = the phases of every CTA's own chunk; the
+ *    items of all phases back to back), phase int32[n_phases][4] = {first tile, tiles (1 or 2;
+ *    | 256: the items are claimed last to first), first item, items}, cta_ph0 int32[n_ctas + 1] = the phases of every CTA's own chunk; the
  *    phases [pool0, pool1) form a pool that the CTAs draw from once their chunk is done,
  *    through the device counter *pool_ctr (zero on entry: prb_pick_scatter resets it).
  * prb_stream_ell2, vmajor = 0: adds the joint counts to hits int32[P][n_slot][K-1][K-1];

@@ -65,8 +65,9 @@ struct E2Cfg {
 // ell        uint32[32 * rows]: the stream — per bundle one header row, then L data rows (word of
 //            lane l = entries 2r, 2r+1 of its lane-run: addresses inside the tile window)
 // item_row0  int32[n_items + 1]: first row of every work item (items are consecutive)
-// phase      int4[n_phases]: x = first super-tile, y = tiles resident (1 or 2), z = first item,
-//            w = number of items (<= E2_MAX_ITEMS)
+// phase      int4[n_phases]: x = first super-tile, y = tiles resident (1 or 2) | 256 when the
+//            items are to be claimed last to first, z = first item, w = number of items
+//            (<= E2_MAX_ITEMS)
 // cta_ph0    int32[gridDim.x + 1]: phases of every CTA's own chunk; the phases [pool0, pool1) are
 //            a pool the CTAs draw from afterwards through *pool_ctr (zero on entry), largest
 //            first: equal cost is not equal time
@@ -133,14 +134,11 @@ k_stream_ell2(const uint32_t *__restrict__ ell, const int32_t *__restrict__ item
         const int4 pd = __ldg(phase + ph);
         if (!first_phase) __syncthreads();  // every warp has left the previous phase
         first_phase = false;
-        for (int i = tid; i < pd.y * (E2_HALF / 16); i += THREADS) {
-            const int t = pd.x + i / (E2_HALF / 16), o = i % (E2_HALF / 16);
-            ((uint4 *)smem_raw)[(t & 1) * (E2_HALF / 16) + o] =
-                __ldg((const uint4 *)(sx + (int64_t)t * E2_HALF) + o);
-        }
         for (int i = tid; i <= pd.w; i += THREADS) s_row0[i] = __ldg(item_row0 + pd.z + i);
         if (tid == 0) s_next = 0;
         __syncthreads();
+        const int n_tiles = pd.y & 0xFF;
+        const bool rev = (pd.y >> 8) != 0;  // items are claimed from the far end of the phase
         const int n_items = pd.w;
         // issuing side: rows [.., is_left) of the item it works on are not in flight yet; an item
         // it has claimed ahead of the counting side waits in (b_row0, b_n)
@@ -159,6 +157,7 @@ k_stream_ell2(const uint32_t *__restrict__ ell, const int32_t *__restrict__ item
                         exhausted = true;
                         break;
                     }
+                    if (rev) k = n_items - 1 - k;
                     const int r0 = s_row0[k];
                     if (TIMING) b_k = pd.z + k;
                     b_n = s_row0[k + 1] - r0;
@@ -177,7 +176,13 @@ k_stream_ell2(const uint32_t *__restrict__ ell, const int32_t *__restrict__ item
                 ++n_issued;
             }
         };
-        try_issue();
+        try_issue();  // the stream starts to flow while the tiles are staged
+        for (int i = tid; i < n_tiles * (E2_HALF / 16); i += THREADS) {
+            const int t = pd.x + i / (E2_HALF / 16), o = i % (E2_HALF / 16);
+            ((uint4 *)smem_raw)[(t & 1) * (E2_HALF / 16) + o] =
+                __ldg((const uint4 *)(sx + (int64_t)t * E2_HALF) + o);
+        }
+        __syncthreads();
         // counting side
         uint32_t hdr = 0xFFFFFFFFu;
         uint32_t acc[NREG], wide[2 * NREG];

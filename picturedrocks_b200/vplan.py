@@ -204,7 +204,7 @@ def ell2_chunks(srow0, tile_b, n_ctas, warps, max_items, bundle_cost=16, min_row
     into phases (its bundles of at most two consecutive tiles) and a phase into work items of
     at most max_rows rows (guided_cuts).
     Returns (item_row0 int32[n_items+1] in stream order; phase int32[n_ph][4] = first tile,
-    tiles, first item, items — the phases of the chunks CTA by CTA, then the pool's;
+    tiles (| 256: claim the items last to first), first item, items — the phases of the chunks CTA by CTA, then the pool's;
     cta_ph0 int32[n_ctas+1]; pool0 = index of the first pool phase)."""
     srow0 = np.asarray(srow0, dtype=np.int64)
     tile_b = np.asarray(tile_b, dtype=np.int64)
@@ -240,14 +240,23 @@ def ell2_chunks(srow0, tile_b, n_ctas, warps, max_items, bundle_cost=16, min_row
             t = int(np.searchsorted(tile_b, b, side="right")) - 1
             end = min(b1, int(tile_b[min(t + 2, n_st)]))
             tiles = 2 if (t + 1 < n_st and int(tile_b[t + 1]) < end) else 1
+            # bundles are sorted by length inside a tile, so a phase that crosses a tile boundary
+            # runs short -> long: its items are cut and claimed from the far end, the longest
+            # bundles (44 us of one warp's time each at 512 rows) must not come last
+            rev = tiles == 2
+            seg = cost[b:end + 1]
+            if rev:
+                seg = seg[-1] - seg[::-1]
             mc, xc = float(min_rows), float(max_rows)
             while True:
-                cuts = guided_cuts(cost[b:end + 1], warps, mc, guide, xc)
+                cuts = guided_cuts(seg, warps, mc, guide, xc)
                 if cuts.size <= max_items:
                     break
                 mc, xc = mc * 1.25, xc * 1.25
+            if rev:
+                cuts = np.concatenate(([0], (end - b) - cuts[:0:-1]))
             item_row0.append(srow0[b + cuts])
-            ph = (t, tiles, n_it, cuts.size)
+            ph = (t, tiles | (256 if rev else 0), n_it, cuts.size)
             if o >= 0:
                 own[o].append(ph)
             else:

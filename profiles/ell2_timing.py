@@ -69,7 +69,7 @@ def main():
         if b <= a:
             continue
         i0, i1 = phase[a, 2], phase[b - 1, 2] + phase[b - 1, 3]
-        ends.append((end[i0:i1].max(), c, phase[a, 0], phase[a:b, 1].sum(), i1 - i0,
+        ends.append((end[i0:i1].max(), c, phase[a, 0], (phase[a:b, 1] & 255).sum(), i1 - i0,
                      rows[i0:i1].sum(), nb[i0:i1].sum()))
     ends.sort()
     for e, c, t0_, nt, ni, r, nbb in ends[:8] + ends[-16:]:

@@ -161,7 +161,9 @@ def _check_ell2_plan(srow0, tile_b, n_ctas, warps, max_items, **kw):
     assert np.all(np.diff(cta_ph0) >= 0)
     covered = np.zeros(len(item_row0) - 1, dtype=np.int64)
     for t0, nt, i0, n in phase:
-        assert 1 <= n <= max_items and nt in (1, 2)
+        assert nt & 255 in (1, 2) and (nt >> 8) == (1 if nt & 255 == 2 else 0)
+        nt &= 255
+        assert 1 <= n <= max_items
         covered[i0: i0 + n] += 1
         # every bundle of the phase lies in tile t0 or (nt == 2) t0 + 1
         b0 = np.searchsorted(srow0, item_row0[i0])
