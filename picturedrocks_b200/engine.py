@@ -500,7 +500,7 @@ class Engine:
         env = os.environ.get
         item_row0, phase, cta_ph0, pool0 = vplan.ell2_chunks(
             srow0.cpu().numpy(), tb, n_ctas, warps, max_items,
-            bundle_cost=int(env("PRB_ELL_BCOST", 16)), min_rows=int(env("PRB_ELL_MIN_ROWS", 40)),
+            bundle_cost=int(env("PRB_ELL_BCOST", 8)), min_rows=int(env("PRB_ELL_MIN_ROWS", 40)),
             guide=float(env("PRB_ELL_GUIDE", 2.0)), max_rows=int(env("PRB_ELL_MAX_ROWS", 512)),
             pool_frac=float(env("PRB_ELL_POOL", 0.15)), pool_unit=float(env("PRB_ELL_POOL_UNIT", 8000)))
         torch.cuda.current_stream().synchronize()  # tmp / lr_* are released below

@@ -191,7 +191,7 @@ def guided_cuts(cost, n_claimers, min_cost, guide=2.0, max_cost=None):
     return cuts.astype(np.int64)
 
 
-def ell2_chunks(srow0, tile_b, n_ctas, warps, max_items, bundle_cost=16, min_rows=40, guide=2.0,
+def ell2_chunks(srow0, tile_b, n_ctas, warps, max_items, bundle_cost=8, min_rows=40, guide=2.0,
                 max_rows=512, pool_frac=0.15, pool_unit=8000, pool_min=150000):
     """Work plan of k_stream_ell2 (csrc/vell2.cu).  srow0 int64[nb+1]: first STREAM row of every
     bundle (header rows included); tile_b int64[n_st+1]: first bundle of every super-tile.

@@ -171,7 +171,7 @@ def _check_ell2_plan(srow0, tile_b, n_ctas, warps, max_items, **kw):
         assert tile_b[t0] <= b0 and b1 <= tile_b[min(t0 + nt, len(tile_b) - 1)]
     assert np.all(covered == 1)
     # pool phases: largest first
-    bc = kw.get("bundle_cost", 16)
+    bc = kw.get("bundle_cost", 8)
     cost = [int(item_row0[i0 + n] - item_row0[i0])
             + bc * int(np.searchsorted(srow0, item_row0[i0 + n]) - np.searchsorted(srow0, item_row0[i0]))
             for _, _, i0, n in phase[pool0:]]
