@@ -502,7 +502,8 @@ class Engine:
             srow0.cpu().numpy(), tb, n_ctas, warps, max_items,
             bundle_cost=int(env("PRB_ELL_BCOST", 8)), min_rows=int(env("PRB_ELL_MIN_ROWS", 40)),
             guide=float(env("PRB_ELL_GUIDE", 2.0)), max_rows=int(env("PRB_ELL_MAX_ROWS", 512)),
-            pool_frac=float(env("PRB_ELL_POOL", 0.15)), pool_unit=float(env("PRB_ELL_POOL_UNIT", 8000)))
+            pool_frac=float(env("PRB_ELL_POOL", 0.15)), pool_unit=float(env("PRB_ELL_POOL_UNIT", 8000)),
+            pool_min=float(env("PRB_ELL_POOL_MIN", 150000)))
         torch.cuda.current_stream().synchronize()  # tmp / lr_* are released below
         del tmp, lr_src, lr_len, lr_hdr
         cls_slot0 = all_slot0 = None

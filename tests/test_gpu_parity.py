@@ -360,23 +360,35 @@ def test_class_sorted_cells_and_v_layout(pr, O, monkeypatch, tile_cells, vlayout
     assert np.array_equal(Xg.indices, Xs.indices) and np.array_equal(Xg.data, Xs.data)
 
 
-@pytest.mark.parametrize("layout", ["ell", "ell-cap64", "rows16", "rows32"])
+@pytest.mark.parametrize("layout", ["ell", "ell-cap64", "ell-pool", "ell-int32hits", "ell1",
+                                    "rows16", "rows32"])
 @pytest.mark.parametrize("tile_cells", [None, 4096])
 def test_v_layout_variants(pr, O, monkeypatch, tile_cells, layout):
-    """The streamed layouts of the K <= 5 path — lane-runs (csrc/vell.cu, the default; also with
-    lane-runs cut at 64 entries) and warp-per-run rows with 16- or 32-bit entries
-    (csrc/vstream.cu): entropies, scores and sequences bit-identical to the oracle."""
+    """The streamed layouts of the K <= 5 path: the streamed lane-runs of csrc/vell2.cu (the
+    default; also with lane-runs cut at 64 entries — pieces of runs, added with REDs —, with the
+    work pool forced on, and with the x_j-major int32 hit table), the lane-runs of csrc/vell.cu
+    (global work queue) and warp-per-run rows with 16- or 32-bit entries (csrc/vstream.cu):
+    entropies, scores and sequences bit-identical to the oracle."""
     from picturedrocks_b200.synth import DiscretisedSpec
 
     monkeypatch.setenv("PRB_V_KERNEL", "ell" if layout.startswith("ell") else "rows")
     monkeypatch.setenv("PRB_V16", "0" if layout == "rows32" else "1")
     if layout == "ell-cap64":
         monkeypatch.setenv("PRB_ELL_CAP", "64")
+    if layout == "ell-pool":
+        monkeypatch.setenv("PRB_ELL_POOL_MIN", "0")
+        monkeypatch.setenv("PRB_ELL_POOL_UNIT", "60")
+    if layout == "ell-int32hits":
+        monkeypatch.setenv("PRB_ELL_VMAJOR", "0")
+    if layout == "ell1":
+        monkeypatch.setenv("PRB_ELL_V", "1")
     if tile_cells:
         monkeypatch.setenv("PRB_V_TILE_CELLS", str(tile_cells))
-    spec = DiscretisedSpec(N=70001, P=301, C=7, K=5, mean_density=0.09, seed=12)  # two 64 K tiles
+    spec = DiscretisedSpec(N=70001, P=301, C=7, K=5, mean_density=0.09, seed=12)  # several tiles
     eng, yd = spec.device_engine()
     assert eng.ell == layout.startswith("ell") and eng.v16 == (layout == "rows16")
+    assert eng.ell2 == (layout.startswith("ell") and layout != "ell1")
+    assert eng.vmajor == (eng.ell2 and layout != "ell-int32hits")
     inf = pr.markers.SparseInformationSet._from_engine(eng, yd)
     y = spec.cpu_labels()
     ora = O.SparseInformationSet(spec.cpu_csc(range(spec.P), y), y)
@@ -389,11 +401,13 @@ def test_v_layout_variants(pr, O, monkeypatch, tile_cells, layout):
         b.autoselect(9)
         assert a.S == [int(s) for s in b.S], kind
         assert np.array_equal(a.score, b.score), kind
+    if layout == "ell-pool":
+        assert eng.v["pool1"] > eng.v["pool0"]  # the pool really was in use
 
 
 @pytest.mark.parametrize("K,C", [(6, 3), (10, 20), (17, 5), (20, 20), (21, 2)])
 def test_lane_run_layout_more_bins(pr, O, K, C):
-    """K = 6..21 bins on the lane-run layout (2..5 counter registers per lane, csrc/vell.cu):
+    """K = 6..21 bins on the lane-run layout (2..5 counter registers per lane, csrc/vell2.cu):
     the K > 5 points of BASELINE config 5 no longer go through the shared-histogram kernel."""
     from picturedrocks_b200.synth import DiscretisedSpec
 
