@@ -398,6 +398,29 @@ int prb_finalize_update(int32_t *hits, const int32_t *cnt, const int64_t *classs
                         const int64_t *col_end, const int32_t *newpos, uint8_t *sx, int vmajor,
                         const int32_t *cls_slot0, int n_slot, const uint64_t *const *peer_bufs,
                         int W, int rank, int32_t *xtag, prb_stream_t stream);
+/* The same tail for 5 < K <= 21 (finalize_wide.cu) on the v-major table uint16
+ * hits[P][C][K-1][4*ceil((K-1)/4)] written by prb_stream_ell2(vmajor = 1, n_slot = C) — every
+ * class must be ONE segment of the layout —, in two kernels: k_wide_terms turns every gene's
+ * block into its ordered list of fp64 terms (terms double[P][prb_wide_terms_stride(C, K)],
+ * n_terms int32[P]; the K*K terms of H(x_j, x_g) in terms2 double[P][K*K] for the supervised
+ * kinds) and leaves the table all zero; k_wide_chain adds them one thread per gene and runs
+ * the fused tail.  cand_score / cand_idx need prb_wide_chain_blocks(P) entries.
+ * prb_wide_supported(C, K): the per-gene scratch fits in shared memory. */
+int64_t prb_wide_terms_stride(int C, int K);
+int prb_wide_supported(int C, int K);
+int64_t prb_wide_chain_blocks(int64_t P);
+int prb_finalize_update_wide(int32_t *hits, const int32_t *cnt, const int64_t *classsizes,
+                             const int32_t *hsize, const int32_t *hs_ysum, const int32_t *ha,
+                             int C, int K, const double *table, int64_t N, int64_t P,
+                             double *terms, double *terms2, int32_t *n_terms, int kind,
+                             int is_remove, const double *base, double *penalty, double *score,
+                             const uint8_t *selected, const double *Hx_all, const double *Hyx_all,
+                             const int32_t *gene_ptr, const int32_t *n_sel_ptr, int32_t gene_lo,
+                             double *cand_score, int64_t *cand_idx, double *best, int32_t *ticket,
+                             const uint32_t *col_packed, const int64_t *col_begin,
+                             const int64_t *col_end, const int32_t *newpos, uint8_t *sx,
+                             const uint64_t *const *peer_bufs, int W, int rank, int32_t *xtag,
+                             prb_stream_t stream);
 /* sx <- 255 at the stored entries of gene *gene_ptr (after a stand-alone streaming pass). */
 int prb_v_unscatter(const int32_t *gene_ptr, const uint32_t *col_packed, const int64_t *col_begin,
                     const int64_t *col_end, const int32_t *newpos, uint8_t *sx,

@@ -64,6 +64,12 @@ _SIGS = {
     "prb_finalize_update": [_vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _vp, _i64, _i64, _int, _int,
                             _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp,
                             _vp, _vp, _vp, _vp, _vp, _int, _vp, _int, _vp, _int, _int, _vp, _vp],
+    "prb_wide_terms_stride": [_int, _int],
+    "prb_wide_supported": [_int, _int],
+    "prb_wide_chain_blocks": [_i64],
+    "prb_finalize_update_wide": [_vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _vp, _i64, _i64, _vp, _vp,
+                                 _vp, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp,
+                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _vp, _vp],
     "prb_v_unscatter": [_vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "prb_best_record": [_vp, _vp, _i64, _vp, _vp],
     "prb_state_direct": [_vp, _vp, _i64, _int, _int, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp],
@@ -98,7 +104,8 @@ _SIGS = {
                                     _vp, _vp, _i64, _vp],
     "prb_sparse_entropy_host": [_vp, _i64, _i64, _i64, _vp],
 }
-_RESTYPES = {"prb_last_error": ctypes.c_char_p, "prb_finalize_update_blocks": _i64}
+_RESTYPES = {"prb_last_error": ctypes.c_char_p, "prb_finalize_update_blocks": _i64,
+             "prb_wide_terms_stride": _i64, "prb_wide_chain_blocks": _i64}
 
 EXPORTED = tuple(_SIGS)
 
@@ -141,6 +148,7 @@ KERNELS = {
     "prb_pack_csc": 1, "prb_unpack_csc": 1, "prb_pack_chunk": 1, "prb_check_columns": 1, "prb_dense_count_nnz": 1, "prb_dense_fill_csc": 1,
     "prb_tile_ptrs": 1, "prb_stream_hits": 1,
     "prb_argmax_commit": 1, "prb_pick_scatter": 1, "prb_peer_share": 1, "prb_finalize_update": 1,
+    "prb_finalize_update_wide": 2,
     "prb_v_unscatter": 1, "prb_best_record": 1, "prb_v_scatter_flat": 1, "prb_ell_build": 1,
     "prb_stream_ell": 1, "prb_stream_ell2": 1, "prb_v_count": 1, "prb_v_scatter": 1,
     "prb_stream_v": 1, "prb_scatter_gene_u8": 1,

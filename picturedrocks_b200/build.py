@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["stream.cu", "vstream.cu", "vell.cu", "vell2.cu", "state.cu", "finalize.cu", "selector.cu", "discretize.cu", "synth.cu",
+SOURCES = ["stream.cu", "vstream.cu", "vell.cu", "vell2.cu", "state.cu", "finalize.cu", "finalize_wide.cu", "selector.cu", "discretize.cu", "synth.cu",
            "step.cu", "peer.cu", "ingest.cu", "host.cu"]
 LIB = os.path.join(HERE, "libprb200.so")
 OBJ = os.path.join(HERE, "_obj")

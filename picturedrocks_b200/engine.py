@@ -506,6 +506,13 @@ class Engine:
             pool_min=float(env("PRB_ELL_POOL_MIN", 150000)))
         torch.cuda.current_stream().synchronize()  # tmp / lr_* are released below
         del tmp, lr_src, lr_len, lr_hdr
+        # 5 < K <= 21: the fused step on a v-major table with slot = class (finalize_wide.cu) needs
+        # every class in ONE segment (two segments would store to the same row)
+        seg_cls = pl["seg_class"].cpu().tolist() if pl["seg_class"] is not None else [0] * n_seg
+        wide = (K1 > 4 and not self.vmajor and len(set(seg_cls)) == n_seg
+                and os.environ.get("PRB_WIDE_FUSED", "1") != "0"
+                and bool(nat.load().prb_wide_supported(self.C, self.K))
+                and P * int(nat.load().prb_wide_terms_stride(self.C, self.K)) * 8 <= (24 << 30))
         cls_slot0 = all_slot0 = None
         if self.vmajor:  # segments of class y = a range of slots of the hit table
             all_slot0 = torch.tensor([0, n_seg], dtype=torch.int32, device=dev)
@@ -515,7 +522,7 @@ class Engine:
                     pl["seg_class"].contiguous(),
                     torch.arange(self.C + 1, dtype=torch.int32, device=dev)).to(torch.int32)
         self.v = dict(plan=pl, kind="ell2", ell=ell, n_bundles=n_bundles, seglen=seglen, rows=rows,
-                      id_shift=id_shift, cls_slot0=cls_slot0, all_slot0=all_slot0,
+                      id_shift=id_shift, cls_slot0=cls_slot0, all_slot0=all_slot0, wide=wide,
                       relabelled=pl["pos"] is not None, pos=pl["pos"], item_rows=0, cap=cap,
                       n_items=int(item_row0.size - 1), n_ctas=n_ctas, pool0=pool0,
                       pool1=int(phase.shape[0]),
@@ -571,28 +578,31 @@ class Engine:
         cnt = cnt.permute(0, 2, 1).contiguous().view(-1)
         return cnt if cnt.numel() else torch.zeros(1, dtype=torch.int32, device=dev)
 
-    def _stream_v(self, with_y, C, hits):
+    def _stream_v(self, with_y, C, hits, vm=None):
         """The streaming pass (counters were zeroed by prb_pick_scatter)."""
         ev = getattr(self, "profile_events", None)
         if ev is not None:
             e0 = torch.cuda.Event(enable_timing=True)
             e1 = torch.cuda.Event(enable_timing=True)
             e0.record()
-            self._stream_v_launch(with_y, C, hits)
+            self._stream_v_launch(with_y, C, hits, vm)
             e1.record()
             ev.append((e0, e1))
         else:
-            self._stream_v_launch(with_y, C, hits)
+            self._stream_v_launch(with_y, C, hits, vm)
 
-    def _stream_v_launch(self, with_y, C, hits):
+    def _stream_v_launch(self, with_y, C, hits, vm=None):
+        """vm: v-major 16-bit hit table (default: the engine's choice for K <= 5; the wide
+        fused step passes True with slot = class)."""
         v = self._v()
         pl = v["plan"]
         if self.ell2:
+            vm = self.vmajor if vm is None else vm
             n_slot = v["plan"]["n_seg"] if self.vmajor else C
             nat.call("prb_stream_ell2", nat.ptr(v["ell"]), nat.ptr(v["item_row0"]),
                      nat.ptr(v["phase"]), nat.ptr(v["cta_ph0"]), v["n_ctas"], v["pool0"],
                      v["pool1"], nat.ptr(self.counters), nat.ptr(self.sx),
-                     self.K1, n_slot, v["id_shift"], nat.ptr(hits), int(self.vmajor),
+                     self.K1, n_slot, v["id_shift"], nat.ptr(hits), int(vm),
                      self.P * self.K1, nat.ptr(getattr(self, "ell_timing", None)), nat.stream())
             return
         if self.ell:
@@ -646,10 +656,32 @@ class Engine:
         if self.P == 0:
             return
         self._pick_scatter(with_y, sel.records, sel.n_rec if pick else 0, sel)
-        hits, cls_slot0, n_slot = self._hits_v(with_y, v)
-        self._stream_v(with_y, C, hits)
         newpos = self._vpos(v)
         peer = getattr(sel, "peer", None)  # the step's record goes out from the kernel's tail
+        if self.K1 > 4:
+            # 5 < K <= 21 (csrc/finalize_wide.cu): v-major table with slot = class, the ordered
+            # term list of every gene, then the thread-per-gene chain with the fused tail
+            assert self.wide_ok(with_y)
+            row_words = 2 * ((self.K1 + 3) // 4)
+            hits = self.hits_buffer(C * self.K1 * row_words)
+            self._stream_v(with_y, C, hits, vm=True)
+            terms, terms2, n_terms = self._wide_buffers(C)
+            nat.call("prb_finalize_update_wide", nat.ptr(hits), nat.ptr(cnt), nat.ptr(clsz),
+                     nat.ptr(self.hsize), nat.ptr(self.hs_ysum), nat.ptr(self.ha), C, self.K,
+                     nat.ptr(self.term), self.N, self.P, nat.ptr(terms), nat.ptr(terms2),
+                     nat.ptr(n_terms), kind, int(is_remove), nat.ptr(sel.base),
+                     nat.ptr(sel.penalty), nat.ptr(sel.score), nat.ptr(sel.selected),
+                     nat.ptr(sel.Hx_all), nat.ptr(sel.Hyx_all), nat.ptr(self.gene_ptr),
+                     nat.ptr(sel.n_sel), _i32(self.gene_lo), nat.ptr(sel.cand_score),
+                     nat.ptr(sel.cand_idx), nat.ptr(sel.best), nat.ptr(self.ticket),
+                     nat.ptr(self.col_packed), nat.ptr(self.col_begin), nat.ptr(self.col_end),
+                     nat.ptr(newpos), nat.ptr(self.sx),
+                     nat.ptr(peer.peer_ptrs) if peer else None, peer.comm.world if peer else 0,
+                     peer.comm.rank if peer else 0, nat.ptr(peer.xtag) if peer else None,
+                     nat.stream())
+            return
+        hits, cls_slot0, n_slot = self._hits_v(with_y, v)
+        self._stream_v(with_y, C, hits)
         nat.call("prb_finalize_update", nat.ptr(hits), nat.ptr(cnt), nat.ptr(clsz),
                  nat.ptr(self.hsize), nat.ptr(self.hs_ysum), nat.ptr(self.ha), C, self.K,
                  nat.ptr(self.term), self.N, self.P, kind, int(is_remove), nat.ptr(sel.base),
@@ -662,6 +694,27 @@ class Engine:
                  nat.ptr(peer.peer_ptrs) if peer else None, peer.comm.world if peer else 0,
                  peer.comm.rank if peer else 0, nat.ptr(peer.xtag) if peer else None,
                  nat.stream())
+
+    def wide_ok(self, with_y):
+        """The fused step of the 5 < K <= 21 path is available: the layout keeps every class
+        in one segment (and a call without labels sees a single segment)."""
+        if not (self.vmode and self.ell2 and self.K1 > 4 and self.P):
+            return False
+        v = self._v()
+        return bool(v.get("wide")) and (with_y or v["plan"]["n_seg"] == 1)
+
+    def _wide_buffers(self, C):
+        key = (C, self.P, self.K)
+        if getattr(self, "_wide_key", None) != key:
+            self._wide = None
+            self.epoch += 1  # (a captured step points at the old buffers)
+            stride = int(nat.load().prb_wide_terms_stride(C, self.K))
+            self._wide = (torch.empty(self.P * stride, dtype=torch.float64, device=self.device),
+                          torch.empty(self.P * self.K * self.K, dtype=torch.float64,
+                                      device=self.device),
+                          torch.empty(self.P, dtype=torch.int32, device=self.device))
+            self._wide_key = key
+        return self._wide
 
     # --------------------------------------------------------------- primitives
     def hits_buffer(self, n_bins):

@@ -79,13 +79,14 @@ class _DeviceScores:
         # V-layout path: the whole step runs in engine.fused_step (three launches)
         if e.vmode and self.be.ycol is None and e.P:
             e._v()  # (the layout decides whether the hit table can be v-major)
-        self.fused = (e.vmode and (e.K1 <= 4 or e.vmajor) and self.be.ycol is None
+        self.fused = (e.vmode and (e.K1 <= 4 or e.wide_ok(supervised)) and self.be.ycol is None
                       and (self.comm is None or min(self.comm.shard_sizes) > 0))
         self.n_blocks = max(1, -(-self.P // 256))
         n_cand = self.n_blocks
         if self.fused:
             C = e.C if supervised else 1
-            n_cand = max(n_cand, int(nat.load().prb_finalize_update_blocks(self.P, C)))
+            n_cand = max(n_cand, int(nat.load().prb_finalize_update_blocks(self.P, C)),
+                         int(nat.load().prb_wide_chain_blocks(self.P)))
         self.cand_score = torch.zeros(n_cand, **f64)
         self.cand_idx = torch.full((n_cand,), -1, dtype=torch.int64, device=self.dev)
         # one 16-byte (score, idx) record: a single all-gather moves both
