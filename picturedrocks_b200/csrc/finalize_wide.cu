@@ -40,6 +40,8 @@
 namespace prb {
 
 constexpr int WT_WARPS = 8, WT_THREADS = WT_WARPS * 32;  // k_wide_terms
+constexpr int WT_LIST = 384;  // word pairs per compaction round of k_wide_terms
+constexpr int WT_U = 8;       // table loads a lane keeps in flight
 constexpr int WC_WARPS = 4, WC_THREADS = WC_WARPS * 32;  // k_wide_chain (34 KB of staging tiles)
 
 __device__ __forceinline__ int wt_scan_excl(int v, int lane, int &total)
@@ -55,7 +57,8 @@ __device__ __forceinline__ int wt_scan_excl(int v, int lane, int &total)
 }
 
 // hits: uint32 words of uint16 hits[P][C][K1][4 * NQ] (slot = class).  Shared memory per warp
-// (ints): bm[CK] E[CK] rs[CK] cs[CK] z0[C] m2[K1*K1] xc[K1], CK = C * K1.
+// (ints): bm[CK] E[CK] rs[CK] cs[CK] z0[C] m2[K1*K1] xc[K1] cr[CK] (pad), CK = C * K1, then the
+// compaction list lp[WT_LIST] lw uint2[WT_LIST].
 // terms: double[P][stride], stride >= C*(1+2*K1) + C*K1*K1; terms2: double[P][K*K] (want_marg);
 // n_terms: int32[P].
 __global__ void __launch_bounds__(WT_THREADS)
@@ -69,38 +72,70 @@ k_wide_terms(uint32_t *__restrict__ hits, const int32_t *__restrict__ cnt,
     extern __shared__ int wt_sh[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int CK = C * K1, NQ = (K1 + 3) >> 2, RW = 2 * NQ, K = K1 + 1, D = 1 + 2 * K1;
-    int *bm = wt_sh + (size_t)warp * per_warp_ints;
+    int *bm = wt_sh + (size_t)warp * (per_warp_ints + 3 * WT_LIST);
     int *E = bm + CK;
     int *rs = E + CK;
     int *cs = rs + CK;
     int *z0 = cs + CK;
     int *m2 = z0 + C;
     int *xc = m2 + K1 * K1;
+    const int n_zero = 4 * CK + C + K1 * K1 + K1;  // everything up to here is zeroed per gene
+    int *cr = xc + K1;  // the gene's row of the count table
+    // compaction list of non-zero word pairs (index, words), behind the per-gene tables
+    int *lp = bm + per_warp_ints;
+    uint2 *lw = reinterpret_cast<uint2 *>(lp + WT_LIST);
     const bool marg = want_marg != 0;
     auto T = [&](int c) -> double { return c > 0 ? __ldg(term + c) : 0.0; };
     const int n_pairs = CK * NQ;  // (w02, w13) word pairs of a gene's block
     for (int64_t g = (int64_t)blockIdx.x * WT_WARPS + warp; g < P; g += (int64_t)gridDim.x * WT_WARPS) {
-        for (int i = lane; i < per_warp_ints; i += 32) bm[i] = 0;
+        for (int i = lane; i < n_zero; i += 32) bm[i] = 0;
+        for (int i = lane; i < CK; i += 32) cr[i] = __ldg(cnt + g * (int64_t)CK + i);
         __syncwarp();
-        const int32_t *crow = cnt + g * (int64_t)CK;
+        const int *crow = cr;
         uint32_t *hg = hits + g * (int64_t)CK * RW;
-        // ---- pass 1
-        for (int p = lane; p < n_pairs; p += 32) {
-            const uint2 w = *reinterpret_cast<const uint2 *>(hg + 2 * p);
-            if ((w.x | w.y) == 0u) continue;
-            const int row = p / NQ, q = p - row * NQ;  // row = y * K1 + v
-            const int y = row / K1, v = row - y * K1;
-            const int cf[4] = {(int)(w.x & 0xFFFFu), (int)(w.y & 0xFFFFu), (int)(w.x >> 16),
-                               (int)(w.y >> 16)};
+        // ---- pass 1 (non-zero word pairs compacted first: every lane then has work)
+        for (int p0 = 0; p0 < n_pairs;) {
+            int n_list = 0;
+            for (; p0 < n_pairs && n_list <= WT_LIST - 32 * WT_U; p0 += 32 * WT_U) {
+                uint2 wu[WT_U];  // WT_U loads in flight before the first ballot needs one
 #pragma unroll
-            for (int f = 0; f < 4; ++f) {
-                const int c = cf[f], a = 4 * q + f;
-                if (c == 0 || a >= K1) continue;
-                atomicOr(bm + y * K1 + a, 1 << v);
-                atomicAdd(rs + y * K1 + a, c);
-                atomicAdd(cs + y * K1 + v, c);
-                if (marg) atomicAdd(m2 + a * K1 + v, c);
+                for (int u = 0; u < WT_U; ++u) {
+                    const int p = p0 + 32 * u + lane;
+                    wu[u] = *reinterpret_cast<const uint2 *>(hg + 2 * min(p, n_pairs - 1));
+                }
+#pragma unroll
+                for (int u = 0; u < WT_U; ++u) {
+                    const int p = p0 + 32 * u + lane;
+                    const uint2 w = wu[u];
+                    const bool nz = p < n_pairs && (w.x | w.y) != 0u;
+                    const unsigned m = __ballot_sync(0xffffffffu, nz);
+                    if (nz) {
+                        const int at = n_list + __popc(m & ((1u << lane) - 1u));
+                        lp[at] = p;
+                        lw[at] = w;
+                    }
+                    n_list += __popc(m);
+                }
             }
+            __syncwarp();
+            for (int i = lane; i < n_list; i += 32) {
+                const int p = lp[i];
+                const uint2 w = lw[i];
+                const int row = p / NQ, q = p - row * NQ;  // row = y * K1 + v
+                const int y = row / K1, v = row - y * K1;
+                const int cf[4] = {(int)(w.x & 0xFFFFu), (int)(w.y & 0xFFFFu), (int)(w.x >> 16),
+                                   (int)(w.y >> 16)};
+#pragma unroll
+                for (int f = 0; f < 4; ++f) {
+                    const int c = cf[f], a = 4 * q + f;
+                    if (c == 0 || a >= K1) continue;
+                    atomicOr(bm + y * K1 + a, 1 << v);
+                    atomicAdd(rs + y * K1 + a, c);
+                    atomicAdd(cs + y * K1 + v, c);
+                    if (marg) atomicAdd(m2 + a * K1 + v, c);
+                }
+            }
+            __syncwarp();
         }
         __syncwarp();
         // ---- scan of the non-zero hit bins per (y, a) row, per-class totals of the x_j = 0 group
@@ -128,41 +163,80 @@ k_wide_terms(uint32_t *__restrict__ hits, const int32_t *__restrict__ cnt,
         }
         __syncwarp();
         double *tg = terms + g * stride;
-        // ---- terms of the marginal bins: D = 1 + 2*K1 per class
-        for (int i = lane; i < C * D; i += 32) {
-            const int y = i / D, t = i - y * D;
-            int c, pos;
-            if (t == 0) {
-                c = (int)(clsz[y] - hs_ysum[y] - z0[y]);
-                pos = y * D + E[y * K1];
-            } else if (t <= K1) {
-                c = crow[y * K1 + t - 1] - cs[y * K1 + t - 1];
-                pos = y * D + E[y * K1] + t;
-            } else {
-                const int a = t - 1 - K1;
-                c = hsize[y * K1 + a] - rs[y * K1 + a];
-                pos = y * D + 1 + K1 + a + E[y * K1 + a];
-            }
-            tg[pos] = T(c);
-        }
-        // ---- terms of the hit bins (second pass over the block), the block is left all zero
-        for (int p = lane; p < n_pairs; p += 32) {
-            uint2 *wp = reinterpret_cast<uint2 *>(hg + 2 * p);
-            const uint2 w = *wp;
-            if ((w.x | w.y) == 0u) continue;
-            *wp = make_uint2(0u, 0u);
-            const int row = p / NQ, q = p - row * NQ;
-            const int y = row / K1, v = row - y * K1;
-            const int cf[4] = {(int)(w.x & 0xFFFFu), (int)(w.y & 0xFFFFu), (int)(w.x >> 16),
-                               (int)(w.y >> 16)};
+        // ---- terms of the marginal bins: D = 1 + 2*K1 per class (four bins per lane and round:
+        // the four gathers are in flight together)
+        for (int i0 = 0; i0 < C * D; i0 += 128) {
+            int cc[4], pp[4];
 #pragma unroll
-            for (int f = 0; f < 4; ++f) {
-                const int c = cf[f], a = 4 * q + f;
-                if (c == 0 || a >= K1) continue;
-                const int pos = y * D + 2 + K1 + a + E[y * K1 + a] +
-                                __popc((unsigned)bm[y * K1 + a] & ((1u << v) - 1u));
-                tg[pos] = T(c);
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + 32 * u + lane;
+                cc[u] = 0, pp[u] = -1;
+                if (i < C * D) {
+                    const int y = i / D, t = i - y * D;
+                    if (t == 0) {
+                        cc[u] = (int)(clsz[y] - hs_ysum[y] - z0[y]);
+                        pp[u] = y * D + E[y * K1];
+                    } else if (t <= K1) {
+                        cc[u] = crow[y * K1 + t - 1] - cs[y * K1 + t - 1];
+                        pp[u] = y * D + E[y * K1] + t;
+                    } else {
+                        const int a = t - 1 - K1;
+                        cc[u] = hsize[y * K1 + a] - rs[y * K1 + a];
+                        pp[u] = y * D + 1 + K1 + a + E[y * K1 + a];
+                    }
+                }
             }
+            double tv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) tv[u] = __ldg(term + max(cc[u], 0));
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (pp[u] >= 0) tg[pp[u]] = cc[u] > 0 ? tv[u] : 0.0;
+        }
+        // ---- terms of the hit bins (second pass over the block, L1 / L2 hits; compacted the
+        // same way), the block is left all zero
+        for (int p0 = 0; p0 < n_pairs;) {
+            int n_list = 0;
+            for (; p0 < n_pairs && n_list <= WT_LIST - 32 * WT_U; p0 += 32 * WT_U) {
+                uint2 wu[WT_U];  // WT_U loads in flight before the first ballot needs one
+#pragma unroll
+                for (int u = 0; u < WT_U; ++u) {
+                    const int p = p0 + 32 * u + lane;
+                    wu[u] = *reinterpret_cast<const uint2 *>(hg + 2 * min(p, n_pairs - 1));
+                }
+#pragma unroll
+                for (int u = 0; u < WT_U; ++u) {
+                    const int p = p0 + 32 * u + lane;
+                    const uint2 w = wu[u];
+                    const bool nz = p < n_pairs && (w.x | w.y) != 0u;
+                    const unsigned m = __ballot_sync(0xffffffffu, nz);
+                    if (nz) {
+                        *reinterpret_cast<uint2 *>(hg + 2 * p) = make_uint2(0u, 0u);
+                        const int at = n_list + __popc(m & ((1u << lane) - 1u));
+                        lp[at] = p;
+                        lw[at] = w;
+                    }
+                    n_list += __popc(m);
+                }
+            }
+            __syncwarp();
+            for (int i = lane; i < n_list; i += 32) {
+                const int p = lp[i];
+                const uint2 w = lw[i];
+                const int row = p / NQ, q = p - row * NQ;
+                const int y = row / K1, v = row - y * K1;
+                const int cf[4] = {(int)(w.x & 0xFFFFu), (int)(w.y & 0xFFFFu), (int)(w.x >> 16),
+                                   (int)(w.y >> 16)};
+#pragma unroll
+                for (int f = 0; f < 4; ++f) {
+                    const int c = cf[f], a = 4 * q + f;
+                    if (c == 0 || a >= K1) continue;
+                    const int pos = y * D + 2 + K1 + a + E[y * K1 + a] +
+                                    __popc((unsigned)bm[y * K1 + a] & ((1u << v) - 1u));
+                    tg[pos] = T(c);
+                }
+            }
+            __syncwarp();
         }
         if (lane == 0) n_terms[g] = C * D + n_hit;
         // ---- H(x_j, x_g): bins (a, v) in order, a = 0: x_j = 0 (as k_finalize's marginal part)
@@ -221,13 +295,26 @@ k_wide_chain(const double *__restrict__ terms, int64_t stride, const double *__r
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) n_max = max(n_max, __shfl_xor_sync(0xffffffffu, n_max, o));
         double h = 0.0;
-        for (int c0 = 0; c0 < n_max; c0 += 32) {
-#pragma unroll 8
+        double nxt[32];  // the next chunk's terms of the 32 genes, in flight while this one is added
+        unsigned ok = 0;  // bit j: nxt[j] holds a term of gene j (else: a dummy load)
+        auto fetch = [&](int c0) {
+            ok = 0;
+#pragma unroll
             for (int j = 0; j < 32; ++j) {
                 const int nj = __shfl_sync(0xffffffffu, n_mine, j);
-                tw[j][lane] = (c0 + lane < nj) ? __ldg(base + (g0 + j) * st + c0 + lane) : 0.0;
+                const bool v = c0 + lane < nj;
+                ok |= (unsigned)v << j;
+                // (unconditional load from a safe address: a predicated load would be followed by
+                // a select that waits for it, and the 32 loads would no longer be in flight together)
+                nxt[j] = __ldg(v ? base + (g0 + j) * st + c0 + lane : base);
             }
+        };
+        if (n_max > 0) fetch(0);
+        for (int c0 = 0; c0 < n_max; c0 += 32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) tw[j][lane] = ((ok >> j) & 1u) ? nxt[j] : 0.0;
             __syncwarp();
+            if (c0 + 32 < n_max) fetch(c0 + 32);
 #pragma unroll 8
             for (int i = 0; i < 32; ++i) h = __dadd_rn(h, tw[lane][i]);
             __syncwarp();
@@ -263,7 +350,11 @@ k_wide_chain(const double *__restrict__ terms, int64_t stride, const double *__r
 
 using namespace prb;
 
-static int wt_per_warp_ints(int C, int K1) { return 4 * C * K1 + C + K1 * K1 + K1; }
+static int wt_per_warp_ints(int C, int K1)
+{
+    const int n = 5 * C * K1 + C + K1 * K1 + K1;
+    return n + (n & 1);  // (the compaction list behind it holds 8-byte entries)
+}
 
 // doubles per gene of the term buffer, bytes of shared memory of k_wide_terms (0: does not fit)
 extern "C" int64_t prb_wide_terms_stride(int C, int K)
@@ -276,7 +367,7 @@ extern "C" int prb_wide_supported(int C, int K)
 {
     const int K1 = K - 1;
     if (K1 < 1 || K1 > 20 || C < 1) return 0;
-    return (int64_t)wt_per_warp_ints(C, K1) * 4 * WT_WARPS <= devinfo().smem_optin - 1024;
+    return (int64_t)(wt_per_warp_ints(C, K1) + 3 * WT_LIST) * 4 * WT_WARPS <= devinfo().smem_optin - 1024;
 }
 
 extern "C" int64_t prb_wide_chain_blocks(int64_t P) { return ceil_div(hmax(P, 1), WC_THREADS); }
@@ -306,7 +397,7 @@ extern "C" int prb_finalize_update_wide(
                 "bad peer buffer arguments");
     const int K1 = K - 1;
     const int pwi = wt_per_warp_ints(C, K1);
-    const int smem = pwi * 4 * WT_WARPS;
+    const int smem = (pwi + 3 * WT_LIST) * 4 * WT_WARPS;
     PRB_CUDA(cudaFuncSetAttribute(k_wide_terms, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int64_t stride = prb_wide_terms_stride(C, K);
     const int grid_a = (int)hmin(ceil_div(P, WT_WARPS), (int64_t)devinfo().sm_count * 8);
