@@ -26,6 +26,25 @@ def partition_genes(P_total, world):
     return out
 
 
+def partition_genes_weighted(weights, world):
+    """Contiguous gene ranges [(lo, hi), ...] of nearly equal total weight — the stored entries
+    per gene: a rank's step time is its shard's nnz, not its gene count (config 4 cut into 8
+    equal-count ranges leaves the fullest shard 5.9 % above the mean, and every step waits for
+    it).  Every rank gets at least one gene when there are enough."""
+    import numpy as np
+
+    w = np.asarray(weights, dtype=np.float64).ravel()
+    P, world = w.size, int(world)
+    c = np.concatenate([[0.0], np.cumsum(w)])
+    cuts = np.searchsorted(c, c[-1] * np.arange(1, world) / world, side="left")
+    bounds = np.concatenate([[0], cuts, [P]]).astype(np.int64)
+    if P >= world:  # strictly increasing bounds
+        for r in range(1, world):
+            bounds[r] = min(max(bounds[r], bounds[r - 1] + 1), P - (world - r))
+    bounds = np.maximum.accumulate(bounds)
+    return [(int(bounds[r]), int(bounds[r + 1])) for r in range(world)]
+
+
 class Comm:
     def __init__(self, group=None, shard_sizes=None):
         assert dist.is_initialized(), "torch.distributed is not initialised"

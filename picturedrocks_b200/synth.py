@@ -153,6 +153,22 @@ class DiscretisedSpec:
                  ctypes.c_uint64(self.seed & M64), nat.stream())
         return y
 
+    def device_gene_nnz(self, y=None):
+        """int64[P] stored entries of every gene (host array; one counting pass on the GPU)."""
+        import torch
+
+        from . import _native as nat
+
+        nat.require_cuda()
+        if y is None:
+            y = self.device_labels()
+        cum = torch.from_numpy(self.cum_table().astype(np.int32).view(np.int32)).cuda()
+        counts = torch.zeros(self.P, dtype=torch.int64, device="cuda")
+        nat.call("prb_synth_count", nat.ptr(y), self.N, 0, self.P, self.C, self.K,
+                 ctypes.c_uint32(self.mean_q24), ctypes.c_uint64(self.seed & M64), nat.ptr(cum),
+                 nat.ptr(counts), nat.stream())
+        return counts.cpu().numpy()
+
     def device_engine(self, gene_lo=0, gene_hi=None, comm=None, y=None):
         """Engine holding genes [gene_lo, gene_hi) generated on the current GPU."""
         import torch

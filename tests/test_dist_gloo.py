@@ -128,3 +128,20 @@ def test_sharded_protocol_matches_single_process():
     ref.autoselect(6)
     assert ret["S"] == [int(s) for s in ref.S]
     assert np.array_equal(ret["score"], ref.score)
+
+
+def test_partition_genes_weighted():
+    from picturedrocks_b200.dist import partition_genes_weighted
+
+    rng = np.random.RandomState(0)
+    w = rng.gamma(0.5, 100.0, 2801).astype(np.int64)
+    for world in (1, 2, 4, 8):
+        parts = partition_genes_weighted(w, world)
+        assert parts[0][0] == 0 and parts[-1][1] == w.size
+        assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+        assert all(hi > lo for lo, hi in parts)
+        tot = [w[lo:hi].sum() for lo, hi in parts]
+        assert max(tot) <= np.mean(tot) + w.max()  # within one gene of the mean
+    # fewer genes than ranks, all-zero weights
+    parts = partition_genes_weighted(np.zeros(10), 3)
+    assert parts[0][0] == 0 and parts[-1][1] == 10 and all(hi > lo for lo, hi in parts)

@@ -27,11 +27,11 @@ def _worker(rank, world, port, ret):
                             device_id=torch.device("cuda", rank))
     try:
         import picturedrocks_b200 as pr
-        from picturedrocks_b200.dist import Comm, partition_genes
+        from picturedrocks_b200.dist import Comm, partition_genes_weighted
         from picturedrocks_b200.synth import DiscretisedSpec
 
         spec = DiscretisedSpec(N=40000, P=1203, C=9, K=5, mean_density=0.08, seed=21)
-        parts = partition_genes(spec.P, world)
+        parts = partition_genes_weighted(spec.device_gene_nnz(), world)  # unequal gene counts
         comm = Comm(shard_sizes=[b - a for a, b in parts])
         eng, yd = spec.device_engine(parts[rank][0], parts[rank][1], comm=comm)
         inf = pr.markers.SparseInformationSet._from_engine(eng, yd)
