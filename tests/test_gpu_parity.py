@@ -428,6 +428,38 @@ def test_lane_run_layout_more_bins(pr, O, K, C):
         assert np.array_equal(a.score, b.score), kind
 
 
+@pytest.mark.parametrize("case", ["fused", "class-split", "forced-generic"])
+def test_more_bins_step_paths(pr, O, monkeypatch, case):
+    """K > 5 selectors: the fused step with the term-list tail (csrc/finalize_wide.cu) needs
+    every class in one segment; a class of more than 32 752 cells is cut into two and the step
+    falls back to the unfused generic path, as it does with PRB_WIDE_FUSED=0 — same bits."""
+    from picturedrocks_b200.synth import DiscretisedSpec
+
+    if case == "forced-generic":
+        monkeypatch.setenv("PRB_WIDE_FUSED", "0")
+    N, C = (70001, 2) if case == "class-split" else (30011, 6)
+    spec = DiscretisedSpec(N=N, P=157, C=C, K=9, mean_density=0.12, seed=3)
+    eng, yd = spec.device_engine()
+    inf = pr.markers.SparseInformationSet._from_engine(eng, yd)
+    y = spec.cpu_labels()
+    ora = O.SparseInformationSet(spec.cpu_csc(range(spec.P), y), y)
+    for kind in ("CIFE", "JMI"):
+        a, b = getattr(pr.markers, kind)(inf), getattr(O, kind)(ora)
+        assert a._d.fused == (case == "fused")
+        a.autoselect(7)
+        a.remove(a.S[1])
+        a.add(5)
+        a.autoselect(2)
+        b.autoselect(7)
+        b.remove(b.S[1])
+        b.add(5)
+        b.autoselect(2)
+        assert a.S == [int(s) for s in b.S], kind
+        assert np.array_equal(a.score, b.score), kind
+    c = np.array([-1, 3], dtype=np.int64)
+    assert np.array_equal(inf.entropy_wrt(c), ora.entropy_wrt(c))  # the table is clean again
+
+
 @pytest.mark.parametrize("K", [2, 3, 4])
 def test_v_layout_fewer_bins(pr, O, K):
     from picturedrocks_b200.synth import DiscretisedSpec
