@@ -87,15 +87,23 @@ k_wide_terms(uint32_t *__restrict__ hits, const int32_t *__restrict__ cnt,
     const bool marg = want_marg != 0;
     auto T = [&](int c) -> double { return c > 0 ? __ldg(term + c) : 0.0; };
     const int n_pairs = CK * NQ;  // (w02, w13) word pairs of a gene's block
+    // x / d for 0 <= x < 2^16 as a multiply-shift (all indices here are far below that)
+    const uint32_t mNQ = 0xFFFFFFFFu / (uint32_t)NQ + 1u, mK1 = 0xFFFFFFFFu / (uint32_t)K1 + 1u;
+    const uint32_t mD = 0xFFFFFFFFu / (uint32_t)D + 1u, mK = 0xFFFFFFFFu / (uint32_t)K + 1u;
+    auto dv = [](int x, uint32_t m) { return (int)__umulhi((uint32_t)x, m); };
     for (int64_t g = (int64_t)blockIdx.x * WT_WARPS + warp; g < P; g += (int64_t)gridDim.x * WT_WARPS) {
-        for (int i = lane; i < n_zero; i += 32) bm[i] = 0;
+        for (int i = lane; i < (n_zero + 3) / 4; i += 32)  // (cr behind it is rewritten below)
+            reinterpret_cast<int4 *>(bm)[i] = make_int4(0, 0, 0, 0);
+        __syncwarp();
         for (int i = lane; i < CK; i += 32) cr[i] = __ldg(cnt + g * (int64_t)CK + i);
         __syncwarp();
         const int *crow = cr;
         uint32_t *hg = hits + g * (int64_t)CK * RW;
         // ---- pass 1 (non-zero word pairs compacted first: every lane then has work)
+        int rounds = 0, n_last = 0;
         for (int p0 = 0; p0 < n_pairs;) {
             int n_list = 0;
+            ++rounds;
             for (; p0 < n_pairs && n_list <= WT_LIST - 32 * WT_U; p0 += 32 * WT_U) {
                 uint2 wu[WT_U];  // WT_U loads in flight before the first ballot needs one
 #pragma unroll
@@ -121,8 +129,8 @@ k_wide_terms(uint32_t *__restrict__ hits, const int32_t *__restrict__ cnt,
             for (int i = lane; i < n_list; i += 32) {
                 const int p = lp[i];
                 const uint2 w = lw[i];
-                const int row = p / NQ, q = p - row * NQ;  // row = y * K1 + v
-                const int y = row / K1, v = row - y * K1;
+                const int row = dv(p, mNQ), q = p - row * NQ;  // row = y * K1 + v
+                const int y = dv(row, mK1), v = row - y * K1;
                 const int cf[4] = {(int)(w.x & 0xFFFFu), (int)(w.y & 0xFFFFu), (int)(w.x >> 16),
                                    (int)(w.y >> 16)};
 #pragma unroll
@@ -135,8 +143,10 @@ k_wide_terms(uint32_t *__restrict__ hits, const int32_t *__restrict__ cnt,
                     if (marg) atomicAdd(m2 + a * K1 + v, c);
                 }
             }
+            n_last = n_list;
             __syncwarp();
         }
+        const bool keep_list = rounds == 1;  // the list still holds every non-zero pair of the gene
         __syncwarp();
         // ---- scan of the non-zero hit bins per (y, a) row, per-class totals of the x_j = 0 group
         int run = 0;
@@ -172,7 +182,7 @@ k_wide_terms(uint32_t *__restrict__ hits, const int32_t *__restrict__ cnt,
                 const int i = i0 + 32 * u + lane;
                 cc[u] = 0, pp[u] = -1;
                 if (i < C * D) {
-                    const int y = i / D, t = i - y * D;
+                    const int y = dv(i, mD), t = i - y * D;
                     if (t == 0) {
                         cc[u] = (int)(clsz[y] - hs_ysum[y] - z0[y]);
                         pp[u] = y * D + E[y * K1];
@@ -193,10 +203,17 @@ k_wide_terms(uint32_t *__restrict__ hits, const int32_t *__restrict__ cnt,
             for (int u = 0; u < 4; ++u)
                 if (pp[u] >= 0) tg[pp[u]] = cc[u] > 0 ? tv[u] : 0.0;
         }
-        // ---- terms of the hit bins (second pass over the block, L1 / L2 hits; compacted the
-        // same way), the block is left all zero
+        // ---- terms of the hit bins: from the list of pass 1 when one round held them all, else
+        // a second pass over the block (L1 / L2 hits; compacted the same way); the block is left
+        // all zero
         for (int p0 = 0; p0 < n_pairs;) {
             int n_list = 0;
+            if (keep_list) {
+                n_list = n_last;
+                p0 = n_pairs;
+                for (int i = lane; i < n_list; i += 32)
+                    *reinterpret_cast<uint2 *>(hg + 2 * lp[i]) = make_uint2(0u, 0u);
+            }
             for (; p0 < n_pairs && n_list <= WT_LIST - 32 * WT_U; p0 += 32 * WT_U) {
                 uint2 wu[WT_U];  // WT_U loads in flight before the first ballot needs one
 #pragma unroll
@@ -223,8 +240,8 @@ k_wide_terms(uint32_t *__restrict__ hits, const int32_t *__restrict__ cnt,
             for (int i = lane; i < n_list; i += 32) {
                 const int p = lp[i];
                 const uint2 w = lw[i];
-                const int row = p / NQ, q = p - row * NQ;
-                const int y = row / K1, v = row - y * K1;
+                const int row = dv(p, mNQ), q = p - row * NQ;
+                const int y = dv(row, mK1), v = row - y * K1;
                 const int cf[4] = {(int)(w.x & 0xFFFFu), (int)(w.y & 0xFFFFu), (int)(w.x >> 16),
                                    (int)(w.y >> 16)};
 #pragma unroll
@@ -250,7 +267,7 @@ k_wide_terms(uint32_t *__restrict__ hits, const int32_t *__restrict__ cnt,
             sum_m2 = __reduce_add_sync(0xffffffffu, sum_m2);
             double *t2 = terms2 + g * (int64_t)(K * K);
             for (int t = lane; t < K * K; t += 32) {
-                const int a = t / K, v = t - a * K;
+                const int a = dv(t, mK), v = t - a * K;
                 int c;
                 if (a == 0) {
                     if (v == 0) {
@@ -353,7 +370,8 @@ using namespace prb;
 static int wt_per_warp_ints(int C, int K1)
 {
     const int n = 5 * C * K1 + C + K1 * K1 + K1;
-    return n + (n & 1);  // (the compaction list behind it holds 8-byte entries)
+    return (n + 3) & ~3;  // (16-byte rows: the tables are zeroed with int4 stores, the list behind
+                          // them holds 8-byte entries)
 }
 
 // doubles per gene of the term buffer, bytes of shared memory of k_wide_terms (0: does not fit)
