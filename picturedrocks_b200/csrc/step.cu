@@ -35,7 +35,6 @@ k_pick_scatter(const double *__restrict__ rec, int n_rec, int32_t *gene_ptr, int
 {
     __shared__ int s_j;
     __shared__ double s_rec[2 * PICK_THREADS / 4];
-    int rs = 2;  // doubles between two records
     if (peer_local && n_rec > 0) {
         // the records arrive in this rank's peer buffer (peer.cu): wait for the tag of the
         // current exchange in every rank's slot, then take a private copy
@@ -69,8 +68,8 @@ k_pick_scatter(const double *__restrict__ rec, int n_rec, int32_t *gene_ptr, int
             double sc = rec[0];
             j = ((const int64_t *)rec)[1];
             for (int r = 1; r < n_rec; ++r) {
-                const double s2 = rec[rs * r];
-                const int64_t i2 = ((const int64_t *)rec)[rs * r + 1];
+                const double s2 = rec[2 * r];
+                const int64_t i2 = ((const int64_t *)rec)[2 * r + 1];
                 if (i2 >= 0 && (j < 0 || better(s2, i2, sc, j))) {
                     sc = s2;
                     j = i2;

@@ -81,7 +81,7 @@ __device__ __forceinline__ void v_flush(uint32_t &acc, int32_t *out, int woff, i
 // sx: uint8[N] shift codes 8*(x_j-1), >= 32 where x_j = 0 (prb_state_v).
 // hits: int32[P][C][K1][K1], added to.
 // EPW = entries per 32-bit word of the layout: 1 (word = code<<24 | cell, of which this kernel
-// only reads the cell's low 16 bits) or 2 (EXPERIMENTAL "V16" layout, PRB_V16=1: a row holds
+// only reads the cell's low 16 bits) or 2 (16-bit "V16" layout, the default of this kernel (PRB_V16=0: 32-bit entries): a row holds
 // 64 entries of 16 bits, the cell id inside its super-tile; half the bytes per entry).
 template <typename CFG, int EPW>
 __global__ void __launch_bounds__(CFG::threads, 1)
@@ -346,7 +346,7 @@ k_vcount(const uint32_t *__restrict__ packed, const int64_t *__restrict__ indptr
 // entries inside a run is arbitrary — the streaming kernel only counts them) and leave the
 // chunk group by group: consecutive threads write consecutive words.  The padding words of
 // segment s are seg_pad[s] = 0xFF000000 | (a cell slot the kernel keeps at "x_j = 0").
-// E16: the EXPERIMENTAL V16 layout (PRB_V16=1) — rows of 64 entries, an entry is the low
+// E16: the V16 layout — rows of 64 entries, an entry is the low
 // 16 bits of the word (the cell id inside its super-tile), runs padded to 64 entries.
 constexpr int VS_U = 8, VS_CHUNK = VL_THREADS * VS_U;
 
@@ -592,7 +592,7 @@ extern "C" int prb_v_scatter(const uint32_t *packed, const int64_t *indptr, int6
                                  seg_pad, vpacked, queue, stream);
 }
 
-// EXPERIMENTAL (PRB_V16=1, staged for round 2): run_end counts rows of 64 entries.
+// V16 layout: run_end counts rows of 64 entries.
 extern "C" int prb_v_scatter16(const uint32_t *packed, const int64_t *indptr, int64_t P,
                                const uint32_t *cellmap, const uint16_t *seg16, int n_seg, int K1,
                                const int32_t *seglen, const int32_t *run_end,
@@ -673,7 +673,7 @@ extern "C" int prb_stream_v(const uint32_t *vpacked, const int32_t *run_end,
                             item_row0, item_vg0, n_items, counters_clean, stream);
 }
 
-// EXPERIMENTAL (PRB_V16=1, staged for round 2): the same pass over the V16 layout built by
+// The same pass over the V16 layout built by
 // prb_v_scatter16 (rows of 64 16-bit entries).
 extern "C" int prb_stream_v16(const uint32_t *vpacked, const int32_t *run_end,
                               const int32_t *tile_row0, int n_seg, int64_t P, int K1,
