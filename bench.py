@@ -389,13 +389,18 @@ def measure_resident(ctx, wname, selector, steps, warmup, skip_stream=False, sam
     import picturedrocks_b200 as pr
     import picturedrocks_b200.markers.mutualinformation.iterative as _it
     from picturedrocks_b200 import _native as nat
-    from picturedrocks_b200.dist import Comm, partition_genes_weighted
+    from picturedrocks_b200.dist import Comm, partition_genes, partition_genes_weighted
 
     w = WORKLOADS[wname]
     spec = make_spec(w)
-    # contiguous gene ranges of equal nnz (every rank counts the whole matrix once: 0.1 s)
-    parts = ([(0, spec.P)] if ctx.world == 1
-             else partition_genes_weighted(spec.device_gene_nnz(), ctx.world))
+    # contiguous gene ranges of equal nnz (every rank counts the whole matrix once: 0.1 s);
+    # the dense workloads (configs 1, 2: discretised on the device) are cut by gene count
+    if ctx.world == 1:
+        parts = [(0, spec.P)]
+    elif hasattr(spec, "device_gene_nnz"):
+        parts = partition_genes_weighted(spec.device_gene_nnz(), ctx.world)
+    else:
+        parts = partition_genes(spec.P, ctx.world)
     lo, hi = parts[ctx.rank]
     comm = Comm(shard_sizes=[b - a for a, b in parts]) if ctx.world > 1 else None
     eng, yd = spec.device_engine(lo, hi, comm=comm)
