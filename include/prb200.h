@@ -69,6 +69,18 @@ int prb_pack_chunk(const void *rows, int row_bytes, const void *codes, int code_
                    prb_stream_t stream);
 int prb_check_columns(const uint32_t *packed, const int64_t *indptr, int64_t P, int32_t *flags,
                       prb_stream_t stream);
+/* CSR (cells-major) -> by-gene CSC on the device, a counting transpose (csrc/ingest.cu): the
+ * rows are cut into B blocks; prb_csr_count fills T int32[B][P] (entries of column c in row
+ * block b; column ids outside [0, P) set flag 1); the caller scans the column totals into
+ * indptr int64[P + 1]; prb_csr_fill turns T into first slots (T64 int64[B][P] scratch) and
+ * scatters the entries, rows ascending inside every gene: rows_out int32[nnz], vals_out (4- or
+ * 8-byte values) [nnz].  crow int64[N + 1], col int32 | int64 [nnz]; canonical CSR (the columns
+ * of a row are distinct). */
+int prb_csr_count(const int64_t *crow, const void *col, int col_bytes, int64_t N, int64_t P, int B,
+                  int32_t *T, int32_t *flags, prb_stream_t stream);
+int prb_csr_fill(const int64_t *crow, const void *col, int col_bytes, const void *vals,
+                 int val_bytes, int64_t N, int64_t P, int B, int32_t *T, const int64_t *indptr,
+                 int64_t *T64, int32_t *rows_out, void *vals_out, prb_stream_t stream);
 /* column-major uint8 codes[P][ld] -> per-gene nnz (pass 1) and packed words (pass 2). */
 int prb_dense_count_nnz(const uint8_t *codes, int64_t N, int64_t P, int64_t ld,
                         int64_t *nnz_per_gene, prb_stream_t stream);

@@ -29,6 +29,8 @@ _SIGS = {
     "prb_unpack_csc": [_vp, _i64, _vp, _vp, _vp],
     "prb_pack_chunk": [_vp, _int, _vp, _int, _int, _i64, _i64, _vp, _vp, _vp],
     "prb_check_columns": [_vp, _vp, _i64, _vp, _vp],
+    "prb_csr_count": [_vp, _vp, _int, _i64, _i64, _int, _vp, _vp, _vp],
+    "prb_csr_fill": [_vp, _vp, _int, _vp, _int, _i64, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp],
     "prb_dense_count_nnz": [_vp, _i64, _i64, _i64, _vp, _vp],
     "prb_dense_fill_csc": [_vp, _i64, _i64, _i64, _vp, _vp, _vp],
     "prb_stream_plan": [_i64, _i64, _int, ctypes.POINTER(_i64), ctypes.POINTER(_int),
@@ -145,7 +147,7 @@ class PrbError(RuntimeError):
 
 # kernels launched per entry point (for bench.py's gpu_launches claim)
 KERNELS = {
-    "prb_pack_csc": 1, "prb_unpack_csc": 1, "prb_pack_chunk": 1, "prb_check_columns": 1, "prb_dense_count_nnz": 1, "prb_dense_fill_csc": 1,
+    "prb_pack_csc": 1, "prb_unpack_csc": 1, "prb_pack_chunk": 1, "prb_check_columns": 1, "prb_csr_count": 1, "prb_csr_fill": 2, "prb_dense_count_nnz": 1, "prb_dense_fill_csc": 1,
     "prb_tile_ptrs": 1, "prb_stream_hits": 1,
     "prb_argmax_commit": 1, "prb_pick_scatter": 1, "prb_peer_share": 1, "prb_finalize_update": 1,
     "prb_finalize_update_wide": 2,

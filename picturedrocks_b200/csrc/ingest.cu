@@ -61,9 +61,104 @@ k_check_columns(const uint32_t *__restrict__ packed, const int64_t *__restrict__
     if (bad) atomicOr(flags, bad);
 }
 
+// ---- CSR (cells-major, how AnnData stores counts) -> by-gene CSC, a counting transpose ------
+// Replaces scipy's csc_matrix(X) of infoset.py:191 for CSR input.  The rows are cut into B
+// blocks; T[b][c] = stored entries of column c in row block b (k_csr_count), turned into the
+// first output slot of (b, c) by a scan down every column on top of the column offsets
+// (k_csr_offsets); k_csr_fill then lets block b walk its rows IN ORDER, all threads on the
+// entries of one row (their columns are distinct in a canonical CSR), each taking the next slot
+// of its column — so the rows come out ascending inside every gene, as the layout builders and
+// the reference's two-pointer merge (infoset.py:365-391) need, without any sort.
+__global__ void __launch_bounds__(256)
+k_csr_count(const int64_t *__restrict__ crow, const void *__restrict__ col, int col_bytes,
+            int64_t N, int64_t P, int64_t rows_per_block, int32_t *__restrict__ T,
+            int32_t *__restrict__ flags)
+{
+    const int64_t r0 = blockIdx.x * rows_per_block, r1 = min(N, r0 + rows_per_block);
+    if (r0 >= r1) return;
+    int32_t *Tb = T + (int64_t)blockIdx.x * P;
+    int bad = 0;
+    for (int64_t i = crow[r0] + threadIdx.x; i < crow[r1]; i += blockDim.x) {
+        const int64_t c = col_bytes == 4 ? (int64_t)((const int32_t *)col)[i] : ((const int64_t *)col)[i];
+        if (c < 0 || c >= P)
+            bad = BAD_ROW;
+        else
+            atomicAdd(Tb + c, 1);
+    }
+    if (bad) atomicOr(flags, bad);
+}
+
+// indptr int64[P + 1]: column offsets (exclusive scan of the column totals, by the caller)
+__global__ void __launch_bounds__(256)
+k_csr_offsets(int32_t *__restrict__ T, int B, int64_t P, const int64_t *__restrict__ indptr,
+              int64_t *__restrict__ T64)
+{
+    const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= P) return;
+    int64_t run = indptr[c];
+    for (int b = 0; b < B; ++b) {
+        const int32_t t = T[(int64_t)b * P + c];
+        T64[(int64_t)b * P + c] = run;
+        run += t;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_csr_fill(const int64_t *__restrict__ crow, const void *__restrict__ col, int col_bytes,
+           const void *__restrict__ vals, int val_bytes, int64_t N, int64_t P,
+           int64_t rows_per_block, unsigned long long *__restrict__ T64,
+           int32_t *__restrict__ rows_out, void *__restrict__ vals_out)
+{
+    const int64_t r0 = blockIdx.x * rows_per_block, r1 = min(N, r0 + rows_per_block);
+    unsigned long long *Tb = T64 + (int64_t)blockIdx.x * P;
+    for (int64_t r = r0; r < r1; ++r) {
+        const int64_t e0 = crow[r], e1 = crow[r + 1];
+        for (int64_t i = e0 + threadIdx.x; i < e1; i += blockDim.x) {
+            const int64_t c = col_bytes == 4 ? (int64_t)((const int32_t *)col)[i] : ((const int64_t *)col)[i];
+            const int64_t at = (int64_t)atomicAdd(Tb + c, 1ull);  // (columns of a row are distinct)
+            rows_out[at] = (int32_t)r;
+            if (val_bytes == 4)
+                ((uint32_t *)vals_out)[at] = ((const uint32_t *)vals)[i];
+            else
+                ((uint64_t *)vals_out)[at] = ((const uint64_t *)vals)[i];
+        }
+        __syncthreads();  // row r has taken its slots before row r + 1 asks for the next ones
+    }
+}
+
 }  // namespace prb
 
 using namespace prb;
+
+extern "C" int prb_csr_count(const int64_t *crow, const void *col, int col_bytes, int64_t N,
+                             int64_t P, int B, int32_t *T, int32_t *flags, prb_stream_t stream)
+{
+    if (N == 0 || P == 0) return 0;
+    PRB_REQUIRE(crow && col && T && flags && B >= 1 && (col_bytes == 4 || col_bytes == 8),
+                "bad arguments");
+    PRB_CUDA(cudaMemsetAsync(T, 0, sizeof(int32_t) * (size_t)B * P, S(stream)));
+    k_csr_count<<<B, 256, 0, S(stream)>>>(crow, col, col_bytes, N, P, ceil_div(N, B), T, flags);
+    PRB_LAUNCH_CHECK("k_csr_count");
+    return 0;
+}
+
+extern "C" int prb_csr_fill(const int64_t *crow, const void *col, int col_bytes, const void *vals,
+                            int val_bytes, int64_t N, int64_t P, int B, int32_t *T,
+                            const int64_t *indptr, int64_t *T64, int32_t *rows_out, void *vals_out,
+                            prb_stream_t stream)
+{
+    if (N == 0 || P == 0) return 0;
+    PRB_REQUIRE(crow && col && vals && T && indptr && T64 && rows_out && vals_out && B >= 1,
+                "bad arguments");
+    PRB_REQUIRE((col_bytes == 4 || col_bytes == 8) && (val_bytes == 4 || val_bytes == 8),
+                "column ids must be int32 / int64, values 4 or 8 bytes wide");
+    k_csr_offsets<<<(unsigned)ceil_div(P, 256), 256, 0, S(stream)>>>(T, B, P, indptr, T64);
+    PRB_LAUNCH_CHECK("k_csr_offsets");
+    k_csr_fill<<<B, 256, 0, S(stream)>>>(crow, col, col_bytes, vals, val_bytes, N, P, ceil_div(N, B),
+                                         (unsigned long long *)T64, rows_out, vals_out);
+    PRB_LAUNCH_CHECK("k_csr_fill");
+    return 0;
+}
 
 extern "C" int prb_pack_chunk(const void *rows, int row_bytes, const void *codes, int code_bytes,
                               int code_signed, int64_t n, int64_t N, uint32_t *packed,

@@ -662,3 +662,29 @@ def test_ingestion_accepts_what_the_reference_accepts(pr, O, monkeypatch):
         pr.markers.SparseInformationSet(Xbig, y)
     with pytest.raises(OverflowError):
         pr.markers.SparseInformationSet(scipy.sparse.csc_matrix((50, 4), dtype=np.int64))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,density,dtype", [((3001, 517), 0.03, np.float32),
+                                                 ((257, 4099), 0.2, np.int64),
+                                                 ((70000, 33), 0.01, np.float64),
+                                                 ((5, 7), 0.0, np.float32)])
+def test_csr_to_csc_counting_transpose(pr, shape, density, dtype):
+    """csrc/ingest.cu prb_csr_count / prb_csr_fill: CSR (cells-major) -> by-gene CSC on the
+    device equals scipy's tocsc() — offsets, row ids ascending inside every gene, values."""
+    import scipy.sparse
+
+    from picturedrocks_b200.markers.mutualinformation.infoset import _sparse_csc_on_device
+
+    rng = np.random.RandomState(shape[0])
+    X = scipy.sparse.random(shape[0], shape[1], density=density, format="csr", random_state=rng,
+                            dtype=np.float64)
+    X.data = (1 + np.floor(X.data * 50)).astype(dtype)
+    X.indices = X.indices.astype(np.int64 if shape[0] == 257 else np.int32)
+    ref = X.tocsc()
+    ref.sort_indices()
+    indptr, rows, vals, N, P = _sparse_csc_on_device(X)
+    assert (N, P) == shape
+    assert np.array_equal(indptr.cpu().numpy(), ref.indptr.astype(np.int64))
+    assert np.array_equal(rows.cpu().numpy(), ref.indices.astype(np.int32))
+    assert np.array_equal(vals.cpu().numpy(), ref.data.astype(vals.cpu().numpy().dtype))
