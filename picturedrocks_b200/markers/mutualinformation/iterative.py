@@ -209,6 +209,8 @@ class _GreedyDevice(IterativeFeatureSelection):
             n = len(self._S) + self._pending
             self._S = [int(v) for v in self._d.S_dev[:n].cpu().numpy()]
             self._pending = 0
+            if self._d.peer is not None:
+                self._d.peer.check()  # a peer that never delivered a record: raise, do not return garbage
         return self._S
 
     @S.setter
