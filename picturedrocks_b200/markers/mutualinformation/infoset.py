@@ -408,6 +408,8 @@ class InformationSet:
         codes = torch.from_numpy(np.ascontiguousarray(X.T.astype(np.uint8))).to(dev)
         self._engine = Engine.from_dense_codes(codes, self.N)
         self._n_feats = self.P - 1 if self.has_y else self.P  # infoset.py:162
+        self._codes = codes if self.has_y else None  # (kept for the selectors' engine below)
+        self._feat_engine = None
 
     def entropy(self, cols):
         """Entropy of the joint of `cols`; negative indices count from the end (numpy)."""
@@ -423,9 +425,24 @@ class InformationSet:
         return [c + self.P if c < 0 else c for c in cols]
 
     def _selector_backend(self):
-        return _SelectorBackend(self._engine, self._n_feats,
-                                ycol=self.P - 1 if self.has_y else None) \
-            if self.has_y else _DenseNoY(self._engine, self._n_feats)
+        """Greedy selectors on a set with a label column run on a second engine that holds the
+        feature columns only and takes the label column as y: the same joint counts and the
+        same (y, x_j, x_i) bin order as the generic column path (the label column is the most
+        significant field of the packed state, infoset.py:133-136), but through the fused
+        step — three launches per step, CUDA graph, no host synchronisation — instead of a
+        state-table build with a host sync per step."""
+        if not self.has_y:
+            return _DenseNoY(self._engine, self._n_feats)
+        if self._feat_engine is None and self._n_feats > 0:
+            try:
+                eng = Engine.from_dense_codes(self._codes[: self._n_feats].contiguous(), self.N)
+                eng.set_y(self._codes[self._n_feats].to(torch.int32))
+                self._feat_engine = eng
+            except (ValueError, OverflowError, NotImplementedError):
+                self._feat_engine = False  # (all-zero features, too many classes: generic path)
+        if self._feat_engine:
+            return _SelectorBackend(self._feat_engine, self._n_feats, ycol=None)
+        return _SelectorBackend(self._engine, self._n_feats, ycol=self.P - 1)
 
 
 class _DenseNoY(_SelectorBackend):

@@ -116,6 +116,21 @@ def test_linearxy(pr, golden):
     check_entropies(dense, g, "dense_")
     assert np.array_equal([inf.entropy(np.array([i])) for i in range(20)], g["ent_single"])
     assert np.array_equal([inf.entropy([-1, i]) for i in range(20)], g["ent_y_single"])
+    # selectors on the dense set (label column = last column) take the fused step as well and
+    # give the bits of the sparse set's (which the goldens pin)
+    for kind in ("CIFE", "JMI", "MIM", "CIFEUnsup"):
+        a, b = getattr(pr.markers, kind)(dense), getattr(pr.markers, kind)(inf)
+        if hasattr(a, "_d"):
+            assert a._d.fused
+        a.autoselect(7)
+        b.autoselect(7)
+        if kind in ("CIFE", "JMI"):
+            a.remove(a.S[2])
+            b.remove(b.S[2])
+            a.autoselect(2)
+            b.autoselect(2)
+        assert list(a.S) == list(b.S), kind
+        assert np.array_equal(a.score, b.score), kind
 
 
 def test_planted600(pr, golden):
