@@ -50,3 +50,10 @@ def test_generic_autoselect_is_argmax_then_add():
     assert fs.S == [1, 2, 3]  # first index wins ties
     with pytest.raises(TypeError):
         IterativeFeatureSelection(None)  # abstract
+
+
+def test_universal_feature_selector_alias():
+    import picturedrocks_b200.markers as m
+
+    assert m.UniversalFeatureSelector is m.IterativeFeatureSelection
+    assert issubclass(m.CIFE, m.UniversalFeatureSelector)
