@@ -123,12 +123,26 @@ class FoldTester:
         mask[fold] = False
         return mask
 
-    def selectmarkers(self, select_function):
+    def selectmarkers(self, select_function, comm=None):
         """`select_function(traindata) -> list of gene indices` on the complement of every
-        fold; the results are kept in `self.markers`."""
-        self.markers = []
-        for f in self.folds:
-            self.markers.append(select_function(self.adata[self._train_mask(f), :]))
+        fold; the results are kept in `self.markers` (performance.py:252-262).
+        The folds are independent selections on row subsets: with `comm` (a
+        `picturedrocks_b200.dist.Comm`, one process per GPU) rank r selects for the folds
+        r, r + world, ... on its own GPU and every rank receives all the marker lists."""
+        if comm is None or comm.world == 1:
+            self.markers = [select_function(self.adata[self._train_mask(f), :])
+                            for f in self.folds]
+            return
+        import torch.distributed as dist
+
+        mine = {i: list(select_function(self.adata[self._train_mask(f), :]))
+                for i, f in enumerate(self.folds) if i % comm.world == comm.rank}
+        parts = [None] * comm.world
+        dist.all_gather_object(parts, mine, group=comm.group)
+        merged = {}
+        for d in parts:
+            merged.update(d)
+        self.markers = [merged[i] for i in range(len(self.folds))]
 
     def classify(self, classifier):
         """For every fold: train `classifier()` on the other folds restricted to the fold's

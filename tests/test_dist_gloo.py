@@ -145,3 +145,56 @@ def test_partition_genes_weighted():
     # fewer genes than ranks, all-zero weights
     parts = partition_genes_weighted(np.zeros(10), 3)
     assert parts[0][0] == 0 and parts[-1][1] == 10 and all(hi > lo for lo, hi in parts)
+
+
+def _fold_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from picturedrocks_b200.data import ExpressionData
+        from picturedrocks_b200.performance import FoldTester
+
+        rng = np.random.RandomState(5)
+        X = rng.poisson(1.0, size=(60, 12)).astype(np.float64)
+        y = rng.randint(0, 3, 60)
+        import pandas as pd
+
+        ad = ExpressionData(X, obs=pd.DataFrame({"y": y}))
+        ft = FoldTester(ad)
+        ft.makefolds(k=5, random=False)
+        calls = []
+
+        def select(train):  # a host stand-in for mi_selector: the 3 genes with the largest mean
+            calls.append(train.n_obs)
+            return [int(g) for g in np.argsort(-np.asarray(train.X).mean(0), kind="stable")[:3]]
+
+        ft.selectmarkers(select, comm=Comm())
+        assert len(calls) == len(range(rank, 5, world))  # this rank ran only its folds
+        if rank == 0:
+            ret["markers"] = [list(m) for m in ft.markers]
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_folds_distributed_over_ranks():
+    """FoldTester.selectmarkers(select, comm): rank r runs the folds r, r + world, ...; every
+    rank ends up with all marker lists, equal to the single-process result."""
+    from picturedrocks_b200.data import ExpressionData
+    from picturedrocks_b200.performance import FoldTester
+
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_fold_worker, args=(world, port, ret), nprocs=world, join=True)
+    rng = np.random.RandomState(5)
+    X = rng.poisson(1.0, size=(60, 12)).astype(np.float64)
+    y = rng.randint(0, 3, 60)
+    import pandas as pd
+
+    ft = FoldTester(ExpressionData(X, obs=pd.DataFrame({"y": y})))
+    ft.makefolds(k=5, random=False)
+    ft.selectmarkers(lambda tr: [int(g) for g in np.argsort(-np.asarray(tr.X).mean(0), kind="stable")[:3]])
+    assert ret["markers"] == [list(m) for m in ft.markers]
