@@ -231,3 +231,101 @@ def test_ell_plan_streamed_headers():
     # the run of 2 500 entries is cut into three flagged pieces, nothing else is flagged
     assert split.sum() == 3 and np.all(ln[live][split == 1] >= 833)
     assert ln[live].sum() == int(lens.sum())
+
+
+def _emulate_streamed_layout(lens, n_seg, st, seg_class, cap, n_ctas, rng, **kw):
+    """numpy emulation of the streamed lane-run layout (csrc/vell2.cu): prb_v_scatter_flat +
+    vplan.ell_plan(seg_id=...) + prb_ell_build(hdr_in_stream=1) + vplan.ell2_chunks, then the walk
+    of k_stream_ell2 — CTA by CTA, phase by phase, items in claim order (last to first in a
+    phase that crosses a tile boundary), bundle by bundle with the row count taken from bit 31
+    of the 32 header words.  Every entry of every run must be visited exactly once, by a lane
+    whose header names the run's (segment, virtual gene); the tiles of a phase must be the ones
+    its bundles belong to."""
+    import torch
+
+    id_shift = 20
+    lens_t = torch.from_numpy(lens.astype(np.int64))
+    run_start = torch.cumsum(lens_t, 0) - lens_t
+    total = int(lens.sum())
+    seg_id = torch.arange(n_seg, dtype=torch.int64)
+    ep = vplan.ell_plan(lens_t, run_start, n_seg, st, cap, seg_id=seg_id, id_shift=id_shift)
+    nb = ep["n_bundles"]
+    brow0 = ep["brow0"].numpy()
+    srow0 = brow0 + np.arange(nb + 1)  # one header row per bundle
+    lr_src, lr_len = ep["lr_src"].numpy(), ep["lr_len"].numpy()
+    lr_hdr = ep["lr_hdr"].numpy().astype(np.int64) & 0xFFFFFFFF
+    rows = int(srow0[-1])
+    stream = np.full((rows, 32, 2), -7, dtype=np.int64)  # data rows: two entries per lane
+    header = np.full((rows, 32), -1, dtype=np.int64)     # header rows: one word per lane
+    for b in range(nb):
+        L = int(srow0[b + 1] - srow0[b] - 1)
+        n = lr_len[b * 32:(b + 1) * 32]
+        assert L == (n[0] + 1) // 2 >= 1 and np.all(n <= n[0]) and n[0] <= cap
+        lbits = (L >> np.arange(32)) & 1
+        header[srow0[b]] = (lr_hdr[b * 32:(b + 1) * 32] & 0x7FFFFFFF) | (lbits << 31)
+        for l in range(32):
+            col = np.full(2 * L, -1, dtype=np.int64)
+            col[: n[l]] = np.arange(lr_src[b * 32 + l], lr_src[b * 32 + l] + n[l])
+            stream[srow0[b] + 1: srow0[b + 1], l, :] = col.reshape(L, 2)
+    tile_b = np.concatenate([ep["tile_b0"].numpy(), [nb]])
+    item_row0, phase, cta_ph0, pool0 = vplan.ell2_chunks(srow0, tile_b, n_ctas, 32, 624, **kw)
+    seg_tile = np.repeat(np.arange(len(st) - 1), np.diff(st))
+    owner = np.full(total, -1, dtype=np.int64)
+    seen_rows = np.zeros(rows, dtype=np.int64)
+
+    def walk_phase(ph):
+        t0, nt, i0, n_it = (int(v) for v in phase[ph])
+        rev, nt = nt >> 8, nt & 255
+        resident = set(range(t0, t0 + nt))
+        for k in range(n_it):
+            kk = n_it - 1 - k if rev else k
+            r, r_end = int(item_row0[i0 + kk]), int(item_row0[i0 + kk + 1])
+            while r < r_end:  # a bundle: header row, then L data rows
+                h = header[r]
+                assert np.all(h >= 0), "an item must start at a header row"
+                L = int(sum(((int(h[l]) >> 31) & 1) << l for l in range(32)))
+                seen_rows[r: r + 1 + L] += 1
+                for l in range(32):
+                    vg = int(h[l]) & ((1 << id_shift) - 1)
+                    seg = (int(h[l]) & 0x3FFFFFFF) >> id_shift
+                    ents = stream[r + 1: r + 1 + L, l].reshape(-1)
+                    ents = ents[ents >= 0]
+                    if vg == (1 << id_shift) - 1:
+                        assert ents.size == 0
+                        continue
+                    assert seg_tile[seg] in resident
+                    assert np.all(owner[ents] == -1)
+                    owner[ents] = vg * n_seg + seg
+                    split = (int(h[l]) >> 30) & 1
+                    assert split == int(lens[vg * n_seg + seg] > cap)
+                r += 1 + L
+            assert r == r_end
+
+    for c in range(n_ctas):
+        for ph in range(int(cta_ph0[c]), int(cta_ph0[c + 1])):
+            walk_phase(ph)
+    for ph in range(pool0, len(phase)):
+        walk_phase(ph)
+    assert np.all(seen_rows == 1)
+    assert np.array_equal(owner, np.repeat(np.arange(lens.size), lens))
+
+
+@pytest.mark.parametrize("cap,n_ctas,kw", [
+    (2, 7, {}), (8, 148, {}), (64, 148, dict(pool_min=0, pool_unit=40)),
+    (1024, 5, dict(pool_min=0, pool_unit=200, min_rows=4, max_rows=16))])
+def test_streamed_layout_walk_covers_every_entry_once(cap, n_ctas, kw):
+    rng = np.random.RandomState(cap + n_ctas)
+    n_seg, st = 7, [0, 1, 3, 4, 7]  # four tiles
+    seg_class = [0, 1, 1, 2, 3, 3, 3]
+    PV = 61
+    lens = (rng.gamma(0.4, 60.0, PV * n_seg)).astype(np.int64)
+    lens[rng.rand(lens.size) < 0.3] = 0
+    lens[5] = 3000  # a run much longer than the cap: pieces flagged "split"
+    _emulate_streamed_layout(lens, n_seg, st, seg_class, cap, n_ctas, rng, **kw)
+
+
+def test_streamed_layout_walk_degenerate():
+    rng = np.random.RandomState(0)
+    _emulate_streamed_layout(np.zeros(12, dtype=np.int64), 3, [0, 3], [0, 0, 0], 64, 4, rng)
+    _emulate_streamed_layout(np.array([0, 0, 1, 0], dtype=np.int64), 2, [0, 1, 2], [0, 1], 64, 4, rng)
+    _emulate_streamed_layout(np.full(40, 1, dtype=np.int64), 1, [0, 1], [0], 2, 148, rng)
