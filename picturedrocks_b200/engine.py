@@ -25,10 +25,10 @@ from . import _native as nat
 from . import vplan
 
 _I16_MAX_BINS = 65536
-# K <= 21: the V layouts (cells relabelled by class, register counters): the lane-run layout
-# of csrc/vell.cu (default) or, for K <= 5, the warp-per-run layout of csrc/vstream.cu
-# (PRB_V_KERNEL=rows).  PRB_NO_VLAYOUT=1 forces the generic shared-histogram kernel
-# (csrc/stream.cu) everywhere.
+# K <= 21: the V layouts (cells relabelled by class, register counters): the streamed lane-run
+# layout of csrc/vell2.cu (default), the lane-run layout of csrc/vell.cu (PRB_ELL_V=1) or, for
+# K <= 5, the warp-per-run layout of csrc/vstream.cu (PRB_V_KERNEL=rows).  PRB_NO_VLAYOUT=1
+# forces the generic shared-histogram kernel (csrc/stream.cu) everywhere.
 USE_VLAYOUT = os.environ.get("PRB_NO_VLAYOUT", "0") != "1"
 ELL_MAX_K1 = 20
 PACKED_PAD = 4  # words of slack after the last stored entry
