@@ -577,7 +577,9 @@ def run_ours(args, wname):
             "dtype": "u8 codes / int32 counts / f64 entropies", "data": "synthetic",
             "config": config_of(w, args.selector, args.steps),
             "details": {"nnz": m["nnz_total"],
-                        "parallelism": "genes sharded over %d GPU(s)" % ctx.world,
+                        "parallelism": "genes sharded over %d GPU(s)%s" % (
+                            ctx.world, ", contiguous ranges of equal nnz; per step one 16-byte "
+                            "record per rank over NVLink peer memory" if ctx.world > 1 else ""),
                         "l2": "inputs exceed L2 (%.2f GB streamed per launch and GPU vs 126 MB)"
                               % (m["stream_bytes"] / 1e9),
                         "time_to_top_k_s": m["ms"] * 1e-3,
