@@ -382,14 +382,16 @@ int prb_pick_scatter(const double *records, int n_rec, int32_t *gene_ptr, int32_
                      const int32_t *newpos, uint8_t *sx, const int32_t *cnt_all, int C, int K,
                      int32_t *hsize, int32_t *hs_begin, int32_t *hs_y, int32_t *hs_ysum,
                      int32_t *ha, int32_t *counters, int n_counters, const uint64_t *peer_local,
-                     const int32_t *xtag, int32_t *peer_err, prb_stream_t stream);
+                     int n_peers, const int32_t *xtag, int32_t *peer_err, prb_stream_t stream);
 /* The per-step exchange of the gene-sharded loop over NVLink peer memory (peer.cu) instead of an
  * NCCL all-gather: peer_bufs = device array of W pointers, entry r = rank r's record buffer
  * uint64[2][W][4] as mapped into THIS process (CUDA IPC); the call stores this rank's record
  * best double[2] = (score, index bits) into slot [tag & 1][rank] of every buffer, then the tag
  * (release, system scope), tag = ++*xtag.  prb_pick_scatter with peer_local = this rank's own
- * buffer (records may be NULL) waits until all n_rec = W slots of the half *xtag & 1 carry the
- * tag *xtag and reduces them; *peer_err is set when a peer has not answered within 4 s. */
+ * buffer (records may be NULL) and n_peers = W waits until all W slots of the half *xtag & 1
+ * carry the tag *xtag — also when it does not pick (n_rec = 0), so that no rank runs more than
+ * one exchange ahead — and reduces them (n_rec = W); *peer_err is set when a peer has not
+ * answered within 4 s. */
 int prb_peer_share(const double *best, const uint64_t *const *peer_bufs, int W, int rank,
                    int32_t *xtag, prb_stream_t stream);
 /* prb_finalize_direct + prb_selector_update + the reduction of the block candidates to ONE

@@ -50,7 +50,7 @@ _SIGS = {
     "prb_scatter_gene_u8": [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
     "prb_scatter_gene_or32": [_vp, _vp, _vp, _i64, _int, _vp, _vp],
     "prb_pick_scatter": [_vp, _int, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
-                         _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp, _vp, _vp, _vp],
+                         _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp, _int, _vp, _vp, _vp],
     "prb_peer_share": [_vp, _vp, _int, _int, _vp, _vp],
     "prb_v_scatter_flat": [_vp, _vp, _i64, _vp, _vp, _int, _int, _vp, _vp, _vp, _vp, _vp],
     "prb_ell_build": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _int, _vp],

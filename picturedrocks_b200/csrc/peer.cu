@@ -10,7 +10,9 @@
 //
 // Buffer of a rank: uint64 slot[2][W][4] = {score bits, index, tag, unused}; the parity of the
 // tag picks the half, so a rank that runs one step ahead never overwrites a record a slower
-// peer has not read yet (it cannot run two steps ahead: it needs the peer's next record first).
+// peer has not read yet (it cannot run two steps ahead: it needs the peer's next record first —
+// prb_pick_scatter waits for the W tags at every step that is followed by a send, including
+// the add / remove steps that use no record).
 // tag = number of exchanges so far (a device counter that only this kernel advances; it is the
 // same on all ranks because they all run the same sequence of steps).  The record is written
 // first, then the tag with a release store at system scope; readers acquire the tag.

@@ -30,17 +30,19 @@ k_pick_scatter(const double *__restrict__ rec, int n_rec, int32_t *gene_ptr, int
                const int64_t *__restrict__ col_end, const int32_t *__restrict__ newpos,
                uint8_t *__restrict__ sx, const int32_t *__restrict__ cnt_all, int C, int K1,
                int32_t *hsize, int32_t *hs_begin, int32_t *hs_y, int32_t *hs_ysum, int32_t *ha,
-               int *counters, int n_counters, const unsigned long long *peer_local,
+               int *counters, int n_counters, const unsigned long long *peer_local, int n_peers,
                const int *xtag, int *peer_err)
 {
     __shared__ int s_j;
     __shared__ double s_rec[2 * PICK_THREADS / 4];
-    if (peer_local && n_rec > 0) {
+    if (peer_local) {
         // the records arrive in this rank's peer buffer (peer.cu): wait for the tag of the
-        // current exchange in every rank's slot, then take a private copy
+        // current exchange in every rank's slot, then take a private copy.  A step that does
+        // not pick (add / remove: n_rec = 0) waits all the same: every rank then runs at most
+        // one exchange ahead of the slowest, which is what the two halves of the buffer allow.
         const int tag = *xtag;
-        const unsigned long long *half = peer_local + (size_t)(tag & 1) * n_rec * 4;
-        if (threadIdx.x < n_rec) {
+        const unsigned long long *half = peer_local + (size_t)(tag & 1) * n_peers * 4;
+        if (threadIdx.x < n_peers) {
             const unsigned long long *slot = half + threadIdx.x * 4;
             unsigned long long t = 0, t0 = 0;
             for (unsigned spin = 0;; ++spin) {
@@ -60,7 +62,7 @@ k_pick_scatter(const double *__restrict__ rec, int n_rec, int32_t *gene_ptr, int
             ((unsigned long long *)s_rec)[2 * threadIdx.x + 1] = slot[1];
         }
         __syncthreads();
-        rec = s_rec;
+        if (n_rec > 0) rec = s_rec;
     }
     if (threadIdx.x == 0) {
         int64_t j;
@@ -170,12 +172,14 @@ extern "C" int prb_pick_scatter(const double *records, int n_rec, int32_t *gene_
                                 const int32_t *newpos, uint8_t *sx, const int32_t *cnt_all, int C,
                                 int K, int32_t *hsize, int32_t *hs_begin, int32_t *hs_y,
                                 int32_t *hs_ysum, int32_t *ha, int32_t *counters, int n_counters,
-                                const uint64_t *peer_local, const int32_t *xtag, int32_t *peer_err,
-                                prb_stream_t stream)
+                                const uint64_t *peer_local, int n_peers, const int32_t *xtag,
+                                int32_t *peer_err, prb_stream_t stream)
 {
     PRB_REQUIRE(n_rec >= 0 && (n_rec == 0 || records != nullptr || peer_local != nullptr),
                 "bad candidate records");
-    PRB_REQUIRE(peer_local == nullptr || (xtag && peer_err && n_rec <= PICK_THREADS / 4),
+    PRB_REQUIRE(peer_local == nullptr ||
+                    (xtag && peer_err && n_peers >= 1 && n_peers <= PICK_THREADS / 4 &&
+                     (n_rec == 0 || n_rec == n_peers)),
                 "bad peer buffer arguments");
     PRB_REQUIRE(C >= 1 && K >= 2 && K <= 21, "the V-layout path needs 2 <= K <= 21");
     PRB_REQUIRE(gene_ptr && col_packed && col_begin && col_end && sx && cnt_all && hsize &&
@@ -185,7 +189,8 @@ extern "C" int prb_pick_scatter(const double *records, int n_rec, int32_t *gene_
     k_pick_scatter<<<devinfo().sm_count * 4, PICK_THREADS, 0, S(stream)>>>(
         records, n_rec, gene_ptr, S_out, n_sel_ptr, selected, gene_lo, P_local, col_packed,
         col_begin, col_end, newpos, sx, cnt_all, C, K - 1, hsize, hs_begin, hs_y, hs_ysum, ha,
-        counters, counters ? n_counters : 0, (const unsigned long long *)peer_local, xtag, peer_err);
+        counters, counters ? n_counters : 0, (const unsigned long long *)peer_local, n_peers, xtag,
+        peer_err);
     PRB_LAUNCH_CHECK("k_pick_scatter");
     return 0;
 }

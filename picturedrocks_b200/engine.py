@@ -629,7 +629,7 @@ class Engine:
         v = self._v()
         C = self.C if with_y else 1
         newpos = self._vpos(v)
-        peer = getattr(sel, "peer", None) if (sel is not None and n_rec) else None
+        peer = getattr(sel, "peer", None) if sel is not None else None
         nat.call("prb_pick_scatter", nat.ptr(records), n_rec, nat.ptr(self.gene_ptr),
                  nat.ptr(sel.S_dev) if sel else None, nat.ptr(sel.n_sel) if sel else None,
                  nat.ptr(sel.selected) if sel else None, _i32(self.gene_lo), self.P,
@@ -638,8 +638,8 @@ class Engine:
                  nat.ptr(self.hsize), nat.ptr(self.hs_begin), nat.ptr(self.hs_y),
                  nat.ptr(self.hs_ysum), nat.ptr(self.ha), nat.ptr(self.counters),
                  v["plan"]["n_st"], nat.ptr(peer.local) if peer else None,
-                 nat.ptr(peer.xtag) if peer else None, nat.ptr(peer.err) if peer else None,
-                 nat.stream())
+                 peer.comm.world if peer else 0, nat.ptr(peer.xtag) if peer else None,
+                 nat.ptr(peer.err) if peer else None, nat.stream())
 
     def fused_step(self, sel, kind, is_remove, pick):
         """One greedy step of a selector on the V path, three launches, no host sync:

@@ -40,7 +40,9 @@ def _worker(rank, world, port, ret):
             fs = getattr(pr.markers, kind)(inf)
             fs.autoselect(12)  # >= GRAPH_MIN_STEPS: the step (incl. NCCL) runs as a CUDA graph
             fs.remove(fs.S[2])
-            fs.add(7)
+            for g in (7, 19, 640, 3, 1100):  # consecutive steps that send a record, pick none
+                fs.add(g)
+            fs.remove(19)
             fs.autoselect(2)
             out[kind] = (list(fs.S), fs.score)
         out["wrt"] = inf.entropy_wrt([-1, 3])
@@ -74,7 +76,9 @@ def test_two_rank_selection_equals_single_gpu():
         fs = getattr(pr.markers, kind)(inf)
         fs.autoselect(12)
         fs.remove(fs.S[2])
-        fs.add(7)
+        for g in (7, 19, 640, 3, 1100):
+            fs.add(g)
+        fs.remove(19)
         fs.autoselect(2)
         assert ret[kind][0] == list(fs.S), kind
         assert np.array_equal(ret[kind][1], fs.score), kind
