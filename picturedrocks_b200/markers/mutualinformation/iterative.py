@@ -146,8 +146,13 @@ class _DeviceScores:
                          self.n_blocks, nat.ptr(self.best), s)
             self._share_best()
         self.engine.fused_step(self, _KIND[kind], is_remove, pick)
-        if self.peer is None:  # (with peer buffers prb_finalize_update has sent the record)
+        if self.peer is None:
             self._share_best()
+        else:
+            # with peer buffers the kernel's tail has sent the record — also after an add /
+            # remove that came first: the next pick must wait for THAT exchange, a second send
+            # without a wait in between would break the one-ahead rule of csrc/peer.cu
+            self.records_valid = True
 
     def pick_and_commit(self):
         """best_idx <- argmax(score) (global index; lowest index on ties), then commit it:

@@ -45,6 +45,12 @@ def _worker(rank, world, port, ret):
             fs.remove(19)
             fs.autoselect(2)
             out[kind] = (list(fs.S), fs.score)
+        fs = pr.markers.CIFE(inf)  # add / remove BEFORE the first pick
+        fs.add(5)
+        fs.add(900)
+        fs.remove(5)
+        fs.autoselect(3)
+        out["add_first"] = (list(fs.S), fs.score)
         out["wrt"] = inf.entropy_wrt([-1, 3])
         out["wrt2"] = inf.entropy_wrt([5, 700])
         out["ent"] = inf.entropy([-1, 700])
@@ -82,6 +88,13 @@ def test_two_rank_selection_equals_single_gpu():
         fs.autoselect(2)
         assert ret[kind][0] == list(fs.S), kind
         assert np.array_equal(ret[kind][1], fs.score), kind
+    fs = pr.markers.CIFE(inf)
+    fs.add(5)
+    fs.add(900)
+    fs.remove(5)
+    fs.autoselect(3)
+    assert ret["add_first"][0] == list(fs.S)
+    assert np.array_equal(ret["add_first"][1], fs.score)
     assert np.array_equal(ret["wrt"], inf.entropy_wrt([-1, 3]))
     assert np.array_equal(ret["wrt2"], inf.entropy_wrt([5, 700]))
     assert ret["ent"] == inf.entropy([-1, 700])
