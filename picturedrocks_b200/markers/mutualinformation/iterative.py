@@ -118,7 +118,10 @@ class _DeviceScores:
     def gather(self, v):
         if self.comm is not None:
             v = self.comm.all_gather_shards(v)
-        return v.cpu().numpy()
+        out = v.cpu().numpy()
+        if self.peer is not None:
+            self.peer.check()  # (a record that never arrived: raise instead of returning garbage)
+        return out
 
     # -- device steps ---------------------------------------------------------
     def _share_best(self):
