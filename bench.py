@@ -60,8 +60,19 @@ UNIT = "cell*gene/s"
 
 
 def config_of(w, selector, steps):
-    """The `config` object — identical in both arms, so that the driver can compare them."""
-    return {"workload": w["name"], "selector": selector, "bins": w["K"], "k": steps}
+    """The `config` object — identical in both arms, so that the driver can compare them.
+    `l2`: how the timing rule "flush L2 or use inputs larger than L2" is met by the GPU arm —
+    an estimate from the workload's shape (2 bytes per stored code, the fullest of 8 gene
+    shards), the measured stream size is in details.l2."""
+    cfg = {"workload": w["name"], "selector": selector, "bins": w["K"], "k": steps}
+    if not w.get("dense"):
+        per_gpu8 = 2.0 * w["N"] * w["P"] * w["mean_density"] / 8
+        cfg["l2"] = ("inputs exceed L2 (no flush): >= %.2f GB streamed per step and GPU at 1..8 GPUs "
+                     "vs 126 MB" % (per_gpu8 / 1e9)) if per_gpu8 > 2 * 126e6 else \
+            "inputs may stay L2-resident between steps (the workload is that small)"
+    else:
+        cfg["l2"] = "inputs stay L2-resident between steps (the workload is that small)"
+    return cfg
 
 
 def workload_key(w):
