@@ -30,7 +30,7 @@ def test_reference_arm_prints_one_json_line():
     assert cb["kind"] in ("reference", "port") and cb["cores"] == 1
     assert cb["value"] == d["value"] and cb["sample"]
     assert d["port_all_cores"]["cores"] >= 1 and d["port_all_cores"]["value"] > 0
-    assert set(d["config"]) == {"workload", "selector", "bins", "k"}
+    assert set(d["config"]) == {"workload", "selector", "bins", "k", "l2"}
     e2e = d["e2e"]
     assert e2e["value"] == d["value"] and e2e["unit"] == d["unit"]
     assert e2e["h2d_bytes_per_step"] == 0 and e2e["d2h_bytes_per_step"] == 0
