@@ -493,13 +493,16 @@ class Engine:
         bundle_pad = torch.repeat_interleave(pad_t, nb_t).to(torch.int16)
         ell = torch.empty(rows * 32 + PACKED_PAD, dtype=torch.int32, device=dev)
         srow0_32 = srow0.to(torch.int32)
+        # (the planner's inputs come to the host BEFORE the builder is launched: the host plans
+        # the chunks while the kernel transposes the lane-runs)
+        tb = torch.cat([tile_b0, tile_b0.new_tensor([n_bundles])]).cpu().numpy()
+        srow0_host = srow0.cpu().numpy()
         nat.call("prb_ell_build", nat.ptr(tmp), nat.ptr(lr_src), nat.ptr(lr_len), nat.ptr(lr_hdr),
                  nat.ptr(srow0_32), nat.ptr(bundle_pad), n_bundles, nat.ptr(ell), None, 1,
                  nat.stream())
-        tb = torch.cat([tile_b0, tile_b0.new_tensor([n_bundles])]).cpu().numpy()
         env = os.environ.get
         item_row0, phase, cta_ph0, pool0 = vplan.ell2_chunks(
-            srow0.cpu().numpy(), tb, n_ctas, warps, max_items,
+            srow0_host, tb, n_ctas, warps, max_items,
             bundle_cost=int(env("PRB_ELL_BCOST", 8)), min_rows=int(env("PRB_ELL_MIN_ROWS", 40)),
             guide=float(env("PRB_ELL_GUIDE", 2.0)), max_rows=int(env("PRB_ELL_MAX_ROWS", 512)),
             pool_frac=float(env("PRB_ELL_POOL", 0.15)), pool_unit=float(env("PRB_ELL_POOL_UNIT", 8000)),
